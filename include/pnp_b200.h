@@ -1,0 +1,171 @@
+/*
+ * pnp_b200.h -- C-ABI of the B200-native (sm_100a) PnP-AdaNet hot path.
+ *
+ * The reference (carrenD/Medical-Cross-Modality-Domain-Adaptation) is pure Python over TensorFlow-1.4
+ * and has no FFI of its own; the narrowest stable seam is the layers.py / ops.py operator surface
+ * (SURVEY.md 8b).  Every entry point below replaces the TF-1.4 op(s) that one of those Python
+ * functions instantiates; the reference call site is cited per function as file:line relative to the
+ * reference tree.  The Python host layer (medical-cross-modality-domain-adaptation_b200/layers.py,
+ * ops.py, ...) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise
+ *   - activations NHWC fp32, conv weights HWIO fp32 ([kh][kw][Cin][Cout]) exactly like the reference
+ *   - `stream` is a cudaStream_t passed as void*; launchers are asynchronous and re-entrant
+ *   - return 0 on success, otherwise a cudaError_t value or one of the PNP_ERR_* codes;
+ *     pnp_error_string() renders either.  Launchers never allocate device memory.
+ */
+#ifndef PNP_B200_H_
+#define PNP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNP_ERR_BAD_ARG 100001
+#define PNP_ERR_UNSUPPORTED 100002
+#define PNP_ERR_DRIVER 100003
+
+/* activation codes for the fused BN/activation kernels */
+#define PNP_ACT_NONE 0
+#define PNP_ACT_RELU 1   /* tf.nn.relu         (layers.py:14) */
+#define PNP_ACT_LRELU 2  /* tf.nn.leaky_relu, alpha=0.2 (layers.py:12) */
+
+/* Geometry of one convolution.  Zero padding only: TF 'SAME' is expressed through (pad_t, pad_l)
+ * with the asymmetric remainder falling on the bottom/right implicitly (out-of-range taps read 0);
+ * the reference's 'SYMMETRIC' mode is pnp_mirror_pad_fwd followed by a pad-free ('VALID') conv. */
+typedef struct {
+  int B, H, W, Cin;   /* input  [B,H,W,Cin]    */
+  int Ho, Wo, Cout;   /* output [B,Ho,Wo,Cout] */
+  int kh, kw;
+  int stride, dil;
+  int pad_t, pad_l;
+} pnp_conv_geom;
+
+/* Optional dropout fused into producers: multiplier = (philox(seed, stream, idx) < keep) / keep.
+ * seed_ptr == NULL or keep >= 1 disables it (tf.nn.dropout, layers.py:25,74,93). */
+typedef struct {
+  const unsigned long long* seed_ptr; /* device scalar */
+  unsigned long long stream;
+  float keep;
+} pnp_dropout_cfg;
+
+const char* pnp_error_string(int code);
+int pnp_version(void);
+/* 1 if the loaded library carries the tcgen05/TMA convolution path and the device is sm_100 */
+int pnp_tc_available(void);
+
+/* ---- convolution, general SIMT fp32 path (conv_simt.cu) --------------------------------------
+ * replaces tf.nn.conv2d (layers.py:18,24,67,73) and tf.nn.atrous_conv2d (layers.py:86,92) plus
+ * their TF-generated gradients (Conv2DBackpropInput / Conv2DBackpropFilter). */
+int pnp_conv2d_fwd(const float* x, const float* w, float* y, const pnp_conv_geom* g,
+                   const pnp_dropout_cfg* drop, int accumulate, void* stream);
+/* dx[B,H,W,Cin] (+)= conv^T(dy, w).  wT is w with the last two axes swapped ([kh][kw][Cout][Cin]),
+ * produced by pnp_weight_transpose. */
+int pnp_conv2d_dgrad(const float* dy, const float* wT, float* dx, const pnp_conv_geom* g,
+                     int accumulate, void* stream);
+/* dw[kh][kw][Cin][Cout] += x (*) dy  (always accumulates: gradient arenas are zeroed per step) */
+int pnp_conv2d_wgrad(const float* x, const float* dy, float* dw, const pnp_conv_geom* g, void* stream);
+int pnp_weight_transpose(const float* w, float* wT, int taps, int Cin, int Cout, void* stream);
+
+/* ---- convolution, tcgen05 + TMA tensor-core path (conv_tc.cu) ----------------------------------
+ * Same math as pnp_conv2d_fwd for stride-1 convolutions with Cin % 64 == 0 and Cout % 64 == 0,
+ * operands pre-split into bf16 planes (pnp_split_bf16); nterms = 3 gives fp32-grade results
+ * (hi*hi + hi*lo + lo*hi), nterms = 1 is the plain bf16 path of BASELINE config 5. */
+int pnp_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long long n, void* stream);
+/* w HWIO fp32 -> planes [taps][Cout][Cin] bf16 (K-major B operand), optionally with the
+ * taps flipped and Cin/Cout swapped (operand of the stride-1 dgrad) */
+int pnp_split_weight_bf16(const float* w, uint16_t* hi, uint16_t* lo, int kh, int kw, int Cin, int Cout,
+                          int for_dgrad, void* stream);
+int pnp_conv2d_tc_fwd(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo,
+                      float* y, const pnp_conv_geom* g, int nterms, const pnp_dropout_cfg* drop,
+                      int accumulate, double* bn_sum, double* bn_sumsq, void* stream);
+
+/* ---- batch norm + activation (+ residual skip) (elementwise.cu) ----------------------------------
+ * replaces tf.contrib.layers.batch_norm(decay .9, eps 1e-3) (layers.py:95-100), the activation
+ * (layers.py:12-14) and the residual add with channel-pad skip (layers.py:160-166,182-189). */
+int pnp_bn_stats(const float* z, long long M, int C, double* sum, double* sumsq, void* stream);
+/* training != 0: batch statistics (biased var), moving stats <- 0.9*moving + 0.1*(mean, unbiased var)
+ * training == 0: moving statistics.  Writes scale=gamma*invstd, shift=beta-mean*scale, mean, invstd. */
+int pnp_bn_finalize(const double* sum, const double* sumsq, long long M, int C, const float* gamma,
+                    const float* beta, float* moving_mean, float* moving_var, int training,
+                    float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* y = act(z*scale + shift + skip);  skip (optional) has Cs channels placed at channel offset skip_off */
+int pnp_bn_act_apply(const float* z, const float* scale, const float* shift, const float* skip, int Cs,
+                     int skip_off, int act, float* y, long long M, int C, void* stream);
+/* g = dy * act'(y);  sum_g[c] += g;  sum_gx[c] += g * xhat   (xhat = (z-mean)*invstd) */
+int pnp_bn_bwd_reduce(const float* dy, const float* y, const float* z, const float* mean, const float* invstd,
+                      int act, float* g, double* sum_g, double* sum_gx, long long M, int C, void* stream);
+/* dgamma += sum_gx, dbeta += sum_g (if non-NULL); coef[0..C) = sum_g/M, coef[C..2C) = sum_gx/M */
+int pnp_bn_bwd_finalize(const double* sum_g, const double* sum_gx, long long M, int C, float* dgamma,
+                        float* dbeta, float* coef, void* stream);
+/* training: dz = gamma*invstd*(g - c1 - xhat*c2) ; else dz = gamma*invstd*g ; then * dropout mult */
+int pnp_bn_bwd_apply(const float* g, const float* z, const float* mean, const float* invstd, const float* gamma,
+                     const float* coef, int training, const pnp_dropout_cfg* drop, float* dz, long long M, int C,
+                     void* stream);
+/* activation-only backward (no BN): g = dy * act'(y) */
+int pnp_act_bwd(const float* dy, const float* y, int act, float* g, long long n, void* stream);
+/* dskip[m, c] = g[m, skip_off + c], c < Cs   (gradient of the channel-pad skip) */
+int pnp_channel_slice(const float* g, int C, int off, int Cs, float* out, long long M, int accumulate, void* stream);
+/* standalone dropout (conv2d without BN: layers.py:74) : y = x * mult ; same call serves backward */
+int pnp_dropout_apply(const float* x, float* y, long long n, const pnp_dropout_cfg* drop, void* stream);
+int pnp_seed_advance(unsigned long long* seed_ptr, void* stream);
+
+/* ---- pooling / padding / phase shift ------------------------------------------------------------- */
+/* tf.nn.max_pool 2x2/2 (layers.py:102-103) */
+int pnp_maxpool2_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream);
+int pnp_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, void* stream);
+/* tf.pad(..., 'SYMMETRIC') by p on each spatial side (layers.py:19-23,68-72) */
+int pnp_mirror_pad_fwd(const float* x, float* y, int B, int H, int W, int C, int p, void* stream);
+int pnp_mirror_pad_bwd(const float* dy, float* dx, int B, int H, int W, int C, int p, void* stream);
+/* PS / _phase_shift (ops.py:3-27): X[B,a,b,G*r*r] -> out[B,a*r,b*r, Ctot] channels [coff, coff+ntile*G),
+ * the G output channels repeated ntile times (tf.tile, adversarial.py:326).  order_b1 != 0 selects the
+ * batch_size==1 sub-pixel order of the reference. */
+int pnp_phase_shift_fwd(const float* X, float* out, int B, int a, int b, int G, int r, int Ctot, int coff,
+                        int ntile, int order_b1, void* stream);
+int pnp_phase_shift_bwd(const float* dout, float* dX, int B, int a, int b, int G, int r, int Ctot, int coff,
+                        int ntile, int order_b1, void* stream);
+/* out[..., coff:coff+C] = logits ; out[..., coff+C] = float(argmax logits)  (adversarial.py:334-335) */
+int pnp_logits_argmax_concat(const float* logits, float* out, long long P, int C, int Ctot, int coff, void* stream);
+/* out[m, 0:C] (+)= in[m, coff:coff+C]  -- strided channel slice used by the gather's backward */
+/* (pnp_channel_slice above) */
+
+/* ---- losses and metrics ---------------------------------------------------------------------------- */
+/* layers.py:134-138 */
+int pnp_pixel_softmax2(const float* logits, float* out, long long P, int C, void* stream);
+/* source_segmenter.py:241-273: per-class partial sums acc[4*C] (doubles, zeroed by caller):
+ * [0,C) sum y ; [C,2C) sum p*y ; [2C,3C) sum p*p ; [3C,4C) sum -y*log(clip(p,.005,1)) */
+int pnp_segloss_reduce(const float* logits, const float* y, long long P, int C, double* acc, void* stream);
+/* out[0]=weighted CE, out[1]=dice loss ; coef[3*C] = per-class backward coefficients */
+int pnp_segloss_finalize(const double* acc, long long P, int C, float* out, float* coef, void* stream);
+/* dlogits = g_wce * d wce/dlogits + g_dice * d dice/dlogits */
+int pnp_segloss_bwd(const float* logits, const float* y, const float* coef, const float* g_wce, const float* g_dice,
+                    float* dlogits, long long P, int C, void* stream);
+/* lib.py:96-110 + tf.confusion_matrix: counts[C*C] (confusion, rows = truth), from logits argmax vs one-hot y */
+int pnp_confusion(const float* logits, const float* y, long long P, int C, unsigned long long* counts, void* stream);
+/* tf.matmul [B,F]x[F,1] (adversarial.py:397,440) */
+int pnp_fc_fwd(const float* x, const float* w, float* out, int B, int F, void* stream);
+int pnp_fc_bwd(const float* x, const float* w, const float* dout, float* dx, float* dw, int B, int F, void* stream);
+/* out[0] = ca*mean(a) + cb*mean(b) (b may be NULL)   (adversarial.py:455-459) */
+int pnp_mean_combo(const float* a, float ca, const float* b, float cb, int n, float* out, void* stream);
+/* out[0] += 0.5 * sum(w^2)   (tf.nn.l2_loss) */
+int pnp_l2_loss_acc(const float* w, long long n, double* out, void* stream);
+
+/* ---- optimizers on flat arenas ------------------------------------------------------------------------
+ * chunk_seg[i] = segment id of arena elements [1024*i, 1024*i+1024); seg_wd / seg_clip are per segment.
+ * grad_scale folds the data-parallel 1/N average; wd adds wd*theta to the gradient (tf.nn.l2_loss terms). */
+/* tf.train.AdamOptimizer (source_segmenter.py:378) -- epsilon-hat form; lr_t computed on host */
+int pnp_adam_step(float* theta, const float* grad, float* m, float* v, long long n, const int* chunk_seg,
+                  const float* seg_wd, float lr_t, float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* tf.train.RMSPropOptimizer (adversarial.py:643-652) + clip_by_value (adversarial.py:653-654) */
+int pnp_rmsprop_step(float* theta, const float* grad, float* ms, float* mom, long long n, const int* chunk_seg,
+                     const float* seg_wd, const float* seg_clip, float lr, float decay, float momentum, float eps,
+                     float grad_scale, void* stream);
+int pnp_fill(float* p, float v, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNP_B200_H_ */

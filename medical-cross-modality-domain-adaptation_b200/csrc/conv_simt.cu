@@ -1,0 +1,569 @@
+// General fp32 SIMT implicit-GEMM convolution family for sm_100a.
+//
+// Replaces tf.nn.conv2d / tf.nn.atrous_conv2d and their gradients as instantiated by the reference's
+// layers.py:18,24,67,73,86,92.  This is the *general* path: any kernel size, stride, dilation,
+// zero-pad offsets and channel counts (Cin = 3, 5, 40 ..., Cout = 5 ...).  The dense stride-1
+// Cin%64==0 layers that carry ~85% of the FLOPs go through the tcgen05 path in conv_tc.cu; the
+// layers that stay here are the HBM-leaning small-channel ones plus (for now) every wgrad.
+//
+//   fwd   : y[m, n]  = sum_k A(m,k) * Wmat[k, n]         m=(b,oy,ox)  k=(ky,kx,ci)  n=co
+//   dgrad : dx[m, n] = sum_k A'(m,k) * WTmat[k, n]       m=(b,iy,ix)  k=(ky,kx,co)  n=ci
+//           (A' gathers dy with the transposed coordinate rule, predicated on stride divisibility)
+//   wgrad : dW[kk, n] += sum_m A(m,kk) * dy[m, n]        split over m across CTAs, fp32 atomics
+#include "common.cuh"
+#include "../../include/pnp_b200.h"
+
+namespace {
+
+struct GatherArgs {
+  int B, IH, IW, IC;   // tensor being gathered from
+  int OH, OW, OC;      // tensor being produced
+  int kh, kw, stride, dil, pad_t, pad_l;
+  int M;               // B*OH*OW
+  int K;               // kh*kw*IC
+  int accumulate;
+  PnpDropout drop;
+};
+
+__device__ __forceinline__ int row_index(int i, int t, int T, int BT) {
+  // thread t's i-th row (or column) inside a block tile of extent BT with per-thread extent T.
+  // T == 8 is split in two groups of 4 that sit BT/2 apart so 128-bit shared loads are conflict free.
+  if (T == 8) return (i < 4) ? (t * 4 + i) : (BT / 2 + t * 4 + (i - 4));
+  return t * T + i;
+}
+
+template <int BM, int BN, int BK, int TM, int TN, int VEC, bool TRANSPOSED>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+conv_gather_kernel(const float* __restrict__ in, const float* __restrict__ wmat, float* __restrict__ out, GatherArgs a) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int KCH = BK / VEC;                                   // k-chunks per row
+  constexpr int ROWS_PT = (BM >= NT) ? (BM / NT) : 1;             // rows per thread (A loader)
+  constexpr int THR_PR = (BM >= NT) ? 1 : (NT / BM);              // threads per row
+  constexpr int CH_PT = KCH / THR_PR;                             // k-chunks per thread per row
+  static_assert(KCH % THR_PR == 0, "bad A loader split");
+  constexpr int B_VEC_TOTAL = BK * BN / 4;
+  constexpr int B_ITERS = (B_VEC_TOTAL + NT - 1) / NT;
+
+  __shared__ __align__(16) float As[BK][BM];
+  __shared__ __align__(16) float Bs[BK][BN];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN);
+  const int ty = tid / (BN / TN);
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  // ---- per-thread A-loader row bookkeeping ----
+  int r_row[ROWS_PT];
+  int r_y[ROWS_PT], r_x[ROWS_PT];
+  long long r_base[ROWS_PT];
+  bool r_ok[ROWS_PT];
+  const int kc0 = (BM >= NT) ? 0 : (tid / BM);
+#pragma unroll
+  for (int j = 0; j < ROWS_PT; ++j) {
+    int row = (BM >= NT) ? (tid + j * NT) : (tid % BM);
+    r_row[j] = row;
+    int m = m0 + row;
+    r_ok[j] = m < a.M;
+    int mm = r_ok[j] ? m : 0;
+    int b = mm / (a.OH * a.OW);
+    int rem = mm - b * (a.OH * a.OW);
+    int oy = rem / a.OW;
+    int ox = rem - oy * a.OW;
+    if (TRANSPOSED) {
+      r_y[j] = oy + a.pad_t;
+      r_x[j] = ox + a.pad_l;
+    } else {
+      r_y[j] = oy * a.stride - a.pad_t;
+      r_x[j] = ox * a.stride - a.pad_l;
+    }
+    r_base[j] = (long long)b * a.IH * a.IW * a.IC;
+  }
+
+  float a_reg[ROWS_PT][CH_PT][VEC];
+  float4 b_reg[B_ITERS];
+
+  const bool b_vec_ok = (a.OC % 4) == 0;
+
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < ROWS_PT; ++j) {
+#pragma unroll
+      for (int c = 0; c < CH_PT; ++c) {
+        int kc = kc0 + c * THR_PR;
+        int k = k0 + kc * VEC;
+        bool ok = r_ok[j] && (k < a.K);
+        int tap = k / a.IC;
+        int ci = k - tap * a.IC;
+        int ky = tap / a.kw;
+        int kx = tap - ky * a.kw;
+        int iy, ix;
+        if (TRANSPOSED) {
+          int ty_ = r_y[j] - ky * a.dil;
+          int tx_ = r_x[j] - kx * a.dil;
+          iy = ty_ / a.stride;
+          ix = tx_ / a.stride;
+          ok = ok && ty_ >= 0 && tx_ >= 0 && (iy * a.stride == ty_) && (ix * a.stride == tx_);
+        } else {
+          iy = r_y[j] + ky * a.dil;
+          ix = r_x[j] + kx * a.dil;
+          ok = ok && iy >= 0 && ix >= 0;
+        }
+        ok = ok && iy < a.IH && ix < a.IW;
+        if (VEC == 4) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) v = __ldg(reinterpret_cast<const float4*>(in + r_base[j] + ((long long)iy * a.IW + ix) * a.IC + ci));
+          a_reg[j][c][0] = v.x;
+          a_reg[j][c][VEC > 1 ? 1 : 0] = v.y;
+          a_reg[j][c][VEC > 2 ? 2 : 0] = v.z;
+          a_reg[j][c][VEC > 3 ? 3 : 0] = v.w;
+        } else {
+          a_reg[j][c][0] = ok ? __ldg(in + r_base[j] + ((long long)iy * a.IW + ix) * a.IC + ci) : 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < B_ITERS; ++it) {
+      int p = tid + it * NT;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < B_VEC_TOTAL) {
+        int kr = p / (BN / 4);
+        int nc = (p - kr * (BN / 4)) * 4;
+        int k = k0 + kr;
+        int n = n0 + nc;
+        if (k < a.K) {
+          const float* src = wmat + (long long)k * a.OC + n;
+          if (b_vec_ok && n + 3 < a.OC) {
+            v = __ldg(reinterpret_cast<const float4*>(src));
+          } else {
+            if (n + 0 < a.OC) v.x = __ldg(src + 0);
+            if (n + 1 < a.OC) v.y = __ldg(src + 1);
+            if (n + 2 < a.OC) v.z = __ldg(src + 2);
+            if (n + 3 < a.OC) v.w = __ldg(src + 3);
+          }
+        }
+      }
+      b_reg[it] = v;
+    }
+  };
+
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int j = 0; j < ROWS_PT; ++j)
+#pragma unroll
+      for (int c = 0; c < CH_PT; ++c) {
+        int kc = kc0 + c * THR_PR;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) As[kc * VEC + e][r_row[j]] = a_reg[j][c][e];
+      }
+#pragma unroll
+    for (int it = 0; it < B_ITERS; ++it) {
+      int p = tid + it * NT;
+      if (p < B_VEC_TOTAL) {
+        int kr = p / (BN / 4);
+        int nc = (p - kr * (BN / 4)) * 4;
+        *reinterpret_cast<float4*>(&Bs[kr][nc]) = b_reg[it];
+      }
+    }
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int nkb = (a.K + BK - 1) / BK;
+  load_tiles(0);
+  store_tiles();
+  __syncthreads();
+  for (int kb = 0; kb < nkb; ++kb) {
+    if (kb + 1 < nkb) load_tiles((kb + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float av[TM], bv[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) {
+        float4 t4 = *reinterpret_cast<const float4*>(&As[k][row_index(i, ty, TM, BM)]);
+        av[i] = t4.x; av[i + 1] = t4.y; av[i + 2] = t4.z; av[i + 3] = t4.w;
+      }
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) {
+        float4 t4 = *reinterpret_cast<const float4*>(&Bs[k][row_index(j, tx, TN, BN)]);
+        bv[j] = t4.x; bv[j + 1] = t4.y; bv[j + 2] = t4.z; bv[j + 3] = t4.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+    if (kb + 1 < nkb) {
+      store_tiles();
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue ----
+  const bool drop_on = a.drop.seed_ptr != nullptr;
+  unsigned long long seed = 0ull;
+  if (drop_on) seed = *a.drop.seed_ptr;
+  const bool vec_store = (a.OC % 4) == 0;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + row_index(i, ty, TM, BM);
+    if (m >= a.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; j += 4) {
+      int n = n0 + row_index(j, tx, TN, BN);
+      if (n >= a.OC) continue;
+      long long idx = (long long)m * a.OC + n;
+      float4 v = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+      if (vec_store && n + 3 < a.OC) {
+        if (drop_on) {
+          float4 mu = pnp_dropout_mult4(a.drop, seed, (unsigned long long)idx >> 2);
+          v.x *= mu.x; v.y *= mu.y; v.z *= mu.z; v.w *= mu.w;
+        }
+        float4* dst = reinterpret_cast<float4*>(out + idx);
+        if (a.accumulate) {
+          float4 o = *dst;
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        *dst = v;
+      } else {
+        float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (n + e < a.OC) {
+            float val = vv[e];
+            if (drop_on) val *= pnp_dropout_mult1(a.drop, seed, (unsigned long long)(idx + e));
+            if (a.accumulate) val += out[idx + e];
+            out[idx + e] = val;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int BK, int TM, int TN, int VEC, bool TR>
+int launch_gather(const float* in, const float* wmat, float* out, const GatherArgs& a, cudaStream_t s) {
+  dim3 grid(pnp_cdiv(a.M, BM), pnp_cdiv(a.OC, BN));
+  dim3 block((BM / TM) * (BN / TN));
+  conv_gather_kernel<BM, BN, BK, TM, TN, VEC, TR><<<grid, block, 0, s>>>(in, wmat, out, a);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+template <bool TR>
+int dispatch_gather(const float* in, const float* wmat, float* out, const GatherArgs& a, cudaStream_t s) {
+  const bool vec = (a.IC % 4) == 0;
+  if (!vec) {  // Cin in {3,5}: tiny-K scalar gather
+    if (a.OC <= 8) return launch_gather<1024, 8, 8, 4, 8, 1, TR>(in, wmat, out, a, s);
+    if (a.OC <= 16) return launch_gather<256, 16, 16, 4, 4, 1, TR>(in, wmat, out, a, s);
+    return launch_gather<128, 64, 16, 8, 4, 1, TR>(in, wmat, out, a, s);
+  }
+  const bool k16 = (a.IC % 16) == 0;
+  if (a.OC <= 8) return launch_gather<1024, 8, 8, 4, 8, 4, TR>(in, wmat, out, a, s);
+  if (a.OC <= 16) {
+    if (k16) return launch_gather<256, 16, 16, 4, 4, 4, TR>(in, wmat, out, a, s);
+    return launch_gather<256, 16, 8, 4, 4, 4, TR>(in, wmat, out, a, s);
+  }
+  if (a.OC <= 32) {
+    if (k16) return launch_gather<256, 32, 16, 8, 4, 4, TR>(in, wmat, out, a, s);
+    return launch_gather<256, 32, 8, 8, 4, 4, TR>(in, wmat, out, a, s);
+  }
+  // grid fill heuristic: prefer the 128x128 tile only when it still yields >= 2 waves
+  long long tiles128 = (long long)pnp_cdiv(a.M, 128) * pnp_cdiv(a.OC, 128);
+  if (a.OC <= 64 || tiles128 < 2 * 148) {
+    if (k16) return launch_gather<128, 64, 16, 8, 4, 4, TR>(in, wmat, out, a, s);
+    return launch_gather<128, 64, 8, 8, 4, 4, TR>(in, wmat, out, a, s);
+  }
+  if (k16) return launch_gather<128, 128, 16, 8, 8, 4, TR>(in, wmat, out, a, s);
+  return launch_gather<128, 128, 8, 8, 8, 4, TR>(in, wmat, out, a, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad
+// ------------------------------------------------------------------------------------------------
+struct WgradArgs {
+  int B, H, W, Cin, Ho, Wo, Cout;
+  int kh, kw, stride, dil, pad_t, pad_l;
+  int M;    // B*Ho*Wo
+  int KK;   // kh*kw*Cin
+  int m_per_split;
+};
+
+template <int BKK, int BN, int BR, int TK, int TN, int VEC>
+__global__ void __launch_bounds__((BKK / TK) * (BN / TN))
+conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, WgradArgs a) {
+  constexpr int NT = (BKK / TK) * (BN / TN);
+  constexpr int KCH = BKK / VEC;                 // kk chunks per pixel row
+  constexpr int A_TOTAL = BR * KCH;
+  constexpr int A_ITERS = (A_TOTAL + NT - 1) / NT;
+  constexpr int B_TOTAL = BR * BN / 4;
+  constexpr int B_ITERS = (B_TOTAL + NT - 1) / NT;
+
+  __shared__ __align__(16) float As[BR][BKK];
+  __shared__ __align__(16) float Bs[BR][BN];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN);
+  const int ty = tid / (BN / TN);
+  const int kk0 = blockIdx.x * BKK;
+  const int n0 = blockIdx.y * BN;
+  const int m_begin = blockIdx.z * a.m_per_split;
+  const int m_end = min(a.M, m_begin + a.m_per_split);
+
+  // A loader: element p -> (r = p / KCH, chunk = p % KCH): kk fixed per (thread, iter) => decode once
+  int a_r[A_ITERS], a_kc[A_ITERS], a_dy[A_ITERS], a_dx[A_ITERS], a_ci[A_ITERS];
+  bool a_ok[A_ITERS];
+#pragma unroll
+  for (int it = 0; it < A_ITERS; ++it) {
+    int p = tid + it * NT;
+    int r = p / KCH;
+    int kc = p - r * KCH;
+    int kk = kk0 + kc * VEC;
+    a_r[it] = r;
+    a_kc[it] = kc;
+    a_ok[it] = (p < A_TOTAL) && (kk < a.KK);
+    int kks = a_ok[it] ? kk : 0;
+    int tap = kks / a.Cin;
+    a_ci[it] = kks - tap * a.Cin;
+    int ky = tap / a.kw;
+    int kx = tap - ky * a.kw;
+    a_dy[it] = ky * a.dil - a.pad_t;
+    a_dx[it] = kx * a.dil - a.pad_l;
+  }
+  const bool b_vec_ok = (a.Cout % 4) == 0;
+
+  float a_reg[A_ITERS][VEC];
+  float4 b_reg[B_ITERS];
+
+  auto load_tiles = [&](int mb) {
+#pragma unroll
+    for (int it = 0; it < A_ITERS; ++it) {
+      int m = mb + a_r[it];
+      bool ok = a_ok[it] && m < m_end;
+      int mm = ok ? m : 0;
+      int b = mm / (a.Ho * a.Wo);
+      int rem = mm - b * (a.Ho * a.Wo);
+      int oy = rem / a.Wo;
+      int ox = rem - oy * a.Wo;
+      int iy = oy * a.stride + a_dy[it];
+      int ix = ox * a.stride + a_dx[it];
+      ok = ok && iy >= 0 && ix >= 0 && iy < a.H && ix < a.W;
+      const float* src = x + (((long long)b * a.H + iy) * a.W + ix) * a.Cin + a_ci[it];
+      if (VEC == 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) v = __ldg(reinterpret_cast<const float4*>(src));
+        a_reg[it][0] = v.x;
+        a_reg[it][VEC > 1 ? 1 : 0] = v.y;
+        a_reg[it][VEC > 2 ? 2 : 0] = v.z;
+        a_reg[it][VEC > 3 ? 3 : 0] = v.w;
+      } else {
+        a_reg[it][0] = ok ? __ldg(src) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < B_ITERS; ++it) {
+      int p = tid + it * NT;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < B_TOTAL) {
+        int r = p / (BN / 4);
+        int nc = (p - r * (BN / 4)) * 4;
+        int m = mb + r;
+        int n = n0 + nc;
+        if (m < m_end) {
+          const float* src = dy + (long long)m * a.Cout + n;
+          if (b_vec_ok && n + 3 < a.Cout) {
+            v = __ldg(reinterpret_cast<const float4*>(src));
+          } else {
+            if (n + 0 < a.Cout) v.x = __ldg(src + 0);
+            if (n + 1 < a.Cout) v.y = __ldg(src + 1);
+            if (n + 2 < a.Cout) v.z = __ldg(src + 2);
+            if (n + 3 < a.Cout) v.w = __ldg(src + 3);
+          }
+        }
+      }
+      b_reg[it] = v;
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int it = 0; it < A_ITERS; ++it) {
+      int p = tid + it * NT;
+      if (p < A_TOTAL) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) As[a_r[it]][a_kc[it] * VEC + e] = a_reg[it][e];
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < B_ITERS; ++it) {
+      int p = tid + it * NT;
+      if (p < B_TOTAL) {
+        int r = p / (BN / 4);
+        int nc = (p - r * (BN / 4)) * 4;
+        *reinterpret_cast<float4*>(&Bs[r][nc]) = b_reg[it];
+      }
+    }
+  };
+
+  float acc[TK][TN];
+#pragma unroll
+  for (int i = 0; i < TK; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  if (m_begin < m_end) {
+    load_tiles(m_begin);
+    store_tiles();
+    __syncthreads();
+    for (int mb = m_begin; mb < m_end; mb += BR) {
+      bool more = mb + BR < m_end;
+      if (more) load_tiles(mb + BR);
+#pragma unroll
+      for (int r = 0; r < BR; ++r) {
+        float av[TK], bv[TN];
+#pragma unroll
+        for (int i = 0; i < TK; ++i) av[i] = As[r][ty * TK + i];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) bv[j] = Bs[r][tx * TN + j];
+#pragma unroll
+        for (int i = 0; i < TK; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+      if (more) {
+        store_tiles();
+        __syncthreads();
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TK; ++i) {
+    int kk = kk0 + ty * TK + i;
+    if (kk >= a.KK) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int n = n0 + tx * TN + j;
+      if (n < a.Cout) atomicAdd(dw + (long long)kk * a.Cout + n, acc[i][j]);
+    }
+  }
+}
+
+template <int BKK, int BN, int BR, int TK, int TN, int VEC>
+int launch_wgrad(const float* x, const float* dy, float* dw, WgradArgs a, cudaStream_t s) {
+  int tiles = pnp_cdiv(a.KK, BKK) * pnp_cdiv(a.Cout, BN);
+  int want = (148 * 6 + tiles - 1) / tiles;             // aim at ~6 CTAs per SM in total
+  int max_splits = pnp_cdiv(a.M, BR * 4);               // at least 4 reduction blocks per CTA
+  int splits = want < 1 ? 1 : want;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  int mps = pnp_cdiv(a.M, splits);
+  mps = pnp_cdiv(mps, BR) * BR;
+  splits = pnp_cdiv(a.M, mps);
+  a.m_per_split = mps;
+  dim3 grid(pnp_cdiv(a.KK, BKK), pnp_cdiv(a.Cout, BN), splits);
+  conv_wgrad_kernel<BKK, BN, BR, TK, TN, VEC><<<grid, (BKK / TK) * (BN / TN), 0, s>>>(x, dy, dw, a);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+__global__ void weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ wT, int Cin, int Cout) {
+  // per tap: [Cin][Cout] -> [Cout][Cin]
+  __shared__ float tile[32][33];
+  const float* src = w + (long long)blockIdx.z * Cin * Cout;
+  float* dst = wT + (long long)blockIdx.z * Cin * Cout;
+  int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int ci = ci0 + r, co = co0 + threadIdx.x;
+    tile[r][threadIdx.x] = (ci < Cin && co < Cout) ? src[(long long)ci * Cout + co] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int co = co0 + r, ci = ci0 + threadIdx.x;
+    if (co < Cout && ci < Cin) dst[(long long)co * Cin + ci] = tile[threadIdx.x][r];
+  }
+}
+
+bool geom_ok(const pnp_conv_geom* g) {
+  return g && g->B > 0 && g->H > 0 && g->W > 0 && g->Cin > 0 && g->Ho > 0 && g->Wo > 0 && g->Cout > 0 && g->kh > 0 &&
+         g->kw > 0 && g->stride > 0 && g->dil > 0 && g->pad_t >= 0 && g->pad_l >= 0;
+}
+
+PnpDropout make_drop(const pnp_dropout_cfg* d) {
+  PnpDropout r;
+  r.seed_ptr = nullptr;
+  r.stream = 0;
+  r.keep = 1.f;
+  r.inv_keep = 1.f;
+  if (d && d->seed_ptr && d->keep < 1.0f) {
+    r.seed_ptr = d->seed_ptr;
+    r.stream = d->stream;
+    r.keep = d->keep;
+    r.inv_keep = 1.0f / d->keep;
+  }
+  return r;
+}
+
+}  // namespace
+
+extern "C" int pnp_conv2d_fwd(const float* x, const float* w, float* y, const pnp_conv_geom* g,
+                              const pnp_dropout_cfg* drop, int accumulate, void* stream) {
+  if (!geom_ok(g) || !x || !w || !y) return PNP_ERR_BAD_ARG;
+  long long M = (long long)g->B * g->Ho * g->Wo;
+  if (M > 0x7fffffffLL || (long long)g->kh * g->kw * g->Cin > 0x7fffffffLL) return PNP_ERR_UNSUPPORTED;
+  GatherArgs a;
+  a.B = g->B; a.IH = g->H; a.IW = g->W; a.IC = g->Cin;
+  a.OH = g->Ho; a.OW = g->Wo; a.OC = g->Cout;
+  a.kh = g->kh; a.kw = g->kw; a.stride = g->stride; a.dil = g->dil; a.pad_t = g->pad_t; a.pad_l = g->pad_l;
+  a.M = (int)M; a.K = g->kh * g->kw * g->Cin; a.accumulate = accumulate;
+  a.drop = make_drop(drop);
+  return dispatch_gather<false>(x, w, y, a, (cudaStream_t)stream);
+}
+
+extern "C" int pnp_conv2d_dgrad(const float* dy, const float* wT, float* dx, const pnp_conv_geom* g,
+                                int accumulate, void* stream) {
+  if (!geom_ok(g) || !dy || !wT || !dx) return PNP_ERR_BAD_ARG;
+  long long M = (long long)g->B * g->H * g->W;
+  if (M > 0x7fffffffLL) return PNP_ERR_UNSUPPORTED;
+  GatherArgs a;
+  a.B = g->B; a.IH = g->Ho; a.IW = g->Wo; a.IC = g->Cout;   // gather from dy
+  a.OH = g->H; a.OW = g->W; a.OC = g->Cin;                  // produce dx
+  a.kh = g->kh; a.kw = g->kw; a.stride = g->stride; a.dil = g->dil; a.pad_t = g->pad_t; a.pad_l = g->pad_l;
+  a.M = (int)M; a.K = g->kh * g->kw * g->Cout; a.accumulate = accumulate;
+  a.drop = make_drop(nullptr);
+  return dispatch_gather<true>(dy, wT, dx, a, (cudaStream_t)stream);
+}
+
+extern "C" int pnp_conv2d_wgrad(const float* x, const float* dy, float* dw, const pnp_conv_geom* g, void* stream) {
+  if (!geom_ok(g) || !x || !dy || !dw) return PNP_ERR_BAD_ARG;
+  long long M = (long long)g->B * g->Ho * g->Wo;
+  if (M > 0x7fffffffLL) return PNP_ERR_UNSUPPORTED;
+  WgradArgs a;
+  a.B = g->B; a.H = g->H; a.W = g->W; a.Cin = g->Cin; a.Ho = g->Ho; a.Wo = g->Wo; a.Cout = g->Cout;
+  a.kh = g->kh; a.kw = g->kw; a.stride = g->stride; a.dil = g->dil; a.pad_t = g->pad_t; a.pad_l = g->pad_l;
+  a.M = (int)M; a.KK = g->kh * g->kw * g->Cin; a.m_per_split = (int)M;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec = (g->Cin % 4) == 0;
+  if (!vec) {
+    if (g->Cout <= 16) return launch_wgrad<64, 16, 16, 4, 1, 1>(x, dy, dw, a, s);
+    return launch_wgrad<64, 64, 16, 4, 4, 1>(x, dy, dw, a, s);
+  }
+  if (g->Cout <= 8) return launch_wgrad<128, 8, 16, 4, 1, 4>(x, dy, dw, a, s);
+  if (g->Cout <= 16) return launch_wgrad<64, 16, 16, 4, 1, 4>(x, dy, dw, a, s);
+  if (g->Cout <= 32) return launch_wgrad<64, 32, 16, 4, 2, 4>(x, dy, dw, a, s);
+  if (g->Cout <= 64 || a.KK < 128) return launch_wgrad<64, 64, 16, 4, 4, 4>(x, dy, dw, a, s);
+  return launch_wgrad<128, 128, 16, 8, 8, 4>(x, dy, dw, a, s);
+}
+
+extern "C" int pnp_weight_transpose(const float* w, float* wT, int taps, int Cin, int Cout, void* stream) {
+  if (!w || !wT || taps <= 0 || Cin <= 0 || Cout <= 0) return PNP_ERR_BAD_ARG;
+  dim3 grid(pnp_cdiv(Cout, 32), pnp_cdiv(Cin, 32), taps);
+  weight_transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(w, wT, Cin, Cout);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}

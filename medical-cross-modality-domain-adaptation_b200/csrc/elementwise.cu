@@ -1,0 +1,945 @@
+// HBM-bound kernels of the PnP-AdaNet hot path for sm_100a: batch-norm statistics / apply / backward,
+// activation + residual skip, dropout, 2x2 max-pool, mirror pad, phase shift (pixel shuffle) and the
+// discriminator-input gather, per-pixel softmax losses, FC + WGAN means, L2 sums, fused Adam / RMSProp+clip.
+// All are coalesced 128-bit streaming kernels with warp-shuffle / shared-memory reductions and double
+// precision global accumulators; grids are sized in multiples of the 148 SMs.
+#include "common.cuh"
+#include "../../include/pnp_b200.h"
+
+namespace {
+
+constexpr int kSMs = 148;
+constexpr float kLeak = 0.2f;       // tf.nn.leaky_relu default alpha (layers.py:12)
+constexpr float kBnDecay = 0.90f;   // layers.py:100
+constexpr float kBnEps = 1e-3f;     // tf.contrib.layers.batch_norm default epsilon
+
+__device__ __forceinline__ float act_fwd(float v, int act) {
+  if (act == PNP_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == PNP_ACT_LRELU) return v > 0.f ? v : kLeak * v;
+  return v;
+}
+__device__ __forceinline__ float act_slope(float y, int act) {
+  if (act == PNP_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == PNP_ACT_LRELU) return y > 0.f ? 1.f : kLeak;
+  return 1.f;
+}
+
+inline int grid_for(long long work_items, int per_block) {
+  long long b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > 148LL * 64) b = 148LL * 64;
+  return (int)b;
+}
+
+PnpDropout make_drop(const pnp_dropout_cfg* d) {
+  PnpDropout r;
+  r.seed_ptr = nullptr; r.stream = 0; r.keep = 1.f; r.inv_keep = 1.f;
+  if (d && d->seed_ptr && d->keep < 1.0f) {
+    r.seed_ptr = d->seed_ptr; r.stream = d->stream; r.keep = d->keep; r.inv_keep = 1.0f / d->keep;
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN statistics: per-channel sum and sum of squares of z[M, C] (C % 4 == 0, C <= 1024)
+// ------------------------------------------------------------------------------------------------
+template <bool WITH_G>
+__global__ void __launch_bounds__(256)
+bn_reduce_kernel(const float* __restrict__ z, const float* __restrict__ dy, const float* __restrict__ yact,
+                 const float* __restrict__ mean, const float* __restrict__ invstd, int act, float* __restrict__ gout,
+                 long long M, int C, int tpr, long long rows_per_block, double* __restrict__ out_a, double* __restrict__ out_b) {
+  // WITH_G == false: out_a += sum z, out_b += sum z^2
+  // WITH_G == true : g = dy*act'(y) (written to gout); out_a += sum g ; out_b += sum g*xhat
+  __shared__ double s_a[1024];
+  __shared__ double s_b[1024];
+  for (int i = threadIdx.x; i < C; i += 256) { s_a[i] = 0.0; s_b[i] = 0.0; }
+  __syncthreads();
+  const int C4 = C >> 2;
+  const int q = threadIdx.x % tpr;
+  const int rlane = threadIdx.x / tpr;
+  const int rstep = 256 / tpr;
+  long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > M) r1 = M;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+  if (q < C4) {
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), is = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (WITH_G) {
+      mu = __ldg(reinterpret_cast<const float4*>(mean) + q);
+      is = __ldg(reinterpret_cast<const float4*>(invstd) + q);
+    }
+    for (long long r = r0 + rlane; r < r1; r += rstep) {
+      long long off = r * C4 + q;
+      float4 zv = __ldg(reinterpret_cast<const float4*>(z) + off);
+      if (WITH_G) {
+        float4 d = __ldg(reinterpret_cast<const float4*>(dy) + off);
+        float4 g = d;
+        if (act != PNP_ACT_NONE) {
+          float4 yv = __ldg(reinterpret_cast<const float4*>(yact) + off);
+          g.x *= act_slope(yv.x, act); g.y *= act_slope(yv.y, act);
+          g.z *= act_slope(yv.z, act); g.w *= act_slope(yv.w, act);
+        }
+        reinterpret_cast<float4*>(gout)[off] = g;
+        a0 += g.x; a1 += g.y; a2 += g.z; a3 += g.w;
+        b0 += g.x * (zv.x - mu.x) * is.x; b1 += g.y * (zv.y - mu.y) * is.y;
+        b2 += g.z * (zv.z - mu.z) * is.z; b3 += g.w * (zv.w - mu.w) * is.w;
+      } else {
+        a0 += zv.x; a1 += zv.y; a2 += zv.z; a3 += zv.w;
+        b0 += zv.x * zv.x; b1 += zv.y * zv.y; b2 += zv.z * zv.z; b3 += zv.w * zv.w;
+      }
+    }
+    int c = q * 4;
+    atomicAdd(&s_a[c + 0], (double)a0); atomicAdd(&s_a[c + 1], (double)a1);
+    atomicAdd(&s_a[c + 2], (double)a2); atomicAdd(&s_a[c + 3], (double)a3);
+    atomicAdd(&s_b[c + 0], (double)b0); atomicAdd(&s_b[c + 1], (double)b1);
+    atomicAdd(&s_b[c + 2], (double)b2); atomicAdd(&s_b[c + 3], (double)b3);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) {
+    atomicAdd(out_a + i, s_a[i]);
+    atomicAdd(out_b + i, s_b[i]);
+  }
+}
+
+int reduce_launch_cfg(long long M, int C, int* tpr, long long* rpb, int* grid) {
+  if (C % 4 != 0 || C > 1024 || C <= 0 || M <= 0) return PNP_ERR_UNSUPPORTED;
+  int C4 = C / 4, t = 1;
+  while (t < C4) t <<= 1;
+  if (t > 256) return PNP_ERR_UNSUPPORTED;
+  *tpr = t;
+  int rstep = 256 / t;
+  // per-thread fp32 partial sums stay short (<= ~64 rows) before being promoted to double
+  long long rows = (long long)rstep * 64;
+  long long g = (M + rows - 1) / rows;
+  long long cap = (long long)kSMs * 16;
+  if (g > cap) { g = cap; rows = (M + g - 1) / g; }
+  *rpb = rows;
+  *grid = (int)((M + rows - 1) / rows);
+  return PNP_OK;
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, long long M, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float* moving_mean,
+                                   float* moving_var, int training, float* scale, float* shift, float* mean, float* invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mu, var;
+  if (training) {
+    double m = sum[c] / (double)M;
+    double v = sumsq[c] / (double)M - m * m;
+    if (v < 0.0) v = 0.0;
+    mu = (float)m;
+    var = (float)v;
+    double unb = (M > 1) ? v * ((double)M / (double)(M - 1)) : v;
+    moving_mean[c] = kBnDecay * moving_mean[c] + (1.f - kBnDecay) * mu;
+    moving_var[c] = kBnDecay * moving_var[c] + (1.f - kBnDecay) * (float)unb;
+  } else {
+    mu = moving_mean[c];
+    var = moving_var[c];
+  }
+  float is = rsqrtf(var + kBnEps);
+  // one Newton step: rsqrtf is ~2 ulp, the oracle's rsqrt is correctly rounded
+  is = is * (1.5f - 0.5f * (var + kBnEps) * is * is);
+  float sc = gamma[c] * is;
+  scale[c] = sc;
+  shift[c] = beta[c] - mu * sc;
+  mean[c] = mu;
+  invstd[c] = is;
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ skip, int Cs, int skip_off, int act, float* __restrict__ y,
+                    long long n4, int C4) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    int q = (int)(i % C4);
+    float4 v = __ldg(reinterpret_cast<const float4*>(z) + i);
+    if (scale) {
+      float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + q);
+      float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + q);
+      v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+      v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    }
+    if (skip) {
+      int c = q * 4 - skip_off;
+      if (c >= 0 && c < Cs) {
+        long long m = i / C4;
+        float4 s = __ldg(reinterpret_cast<const float4*>(skip + m * Cs + c));
+        v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+      }
+    }
+    v.x = act_fwd(v.x, act); v.y = act_fwd(v.y, act); v.z = act_fwd(v.z, act); v.w = act_fwd(v.w, act);
+    reinterpret_cast<float4*>(y)[i] = v;
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sum_g, const double* __restrict__ sum_gx, long long M,
+                                       int C, float* dgamma, float* dbeta, float* coef) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sg = sum_g[c], sgx = sum_gx[c];
+  if (dgamma) dgamma[c] += (float)sgx;
+  if (dbeta) dbeta[c] += (float)sg;
+  coef[c] = (float)(sg / (double)M);
+  coef[C + c] = (float)(sgx / (double)M);
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ coef,
+                    int training, PnpDropout drop, float* __restrict__ dz, long long n4, int C4) {
+  unsigned long long seed = 0ull;
+  const bool drop_on = drop.seed_ptr != nullptr;
+  if (drop_on) seed = *drop.seed_ptr;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    int q = (int)(i % C4);
+    float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + q);
+    float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+    float4 o;
+    if (training) {
+      float4 zv = __ldg(reinterpret_cast<const float4*>(z) + i);
+      float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + q);
+      float4 c1 = __ldg(reinterpret_cast<const float4*>(coef) + q);
+      float4 c2 = __ldg(reinterpret_cast<const float4*>(coef) + C4 + q);
+      o.x = ga.x * is.x * (gv.x - c1.x - (zv.x - mu.x) * is.x * c2.x);
+      o.y = ga.y * is.y * (gv.y - c1.y - (zv.y - mu.y) * is.y * c2.y);
+      o.z = ga.z * is.z * (gv.z - c1.z - (zv.z - mu.z) * is.z * c2.z);
+      o.w = ga.w * is.w * (gv.w - c1.w - (zv.w - mu.w) * is.w * c2.w);
+    } else {
+      o.x = ga.x * is.x * gv.x; o.y = ga.y * is.y * gv.y; o.z = ga.z * is.z * gv.z; o.w = ga.w * is.w * gv.w;
+    }
+    if (drop_on) {
+      float4 mu = pnp_dropout_mult4(drop, seed, (unsigned long long)i);
+      o.x *= mu.x; o.y *= mu.y; o.z *= mu.z; o.w *= mu.w;
+    }
+    reinterpret_cast<float4*>(dz)[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int act, float* __restrict__ g, long long n) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    g[i] = dy[i] * act_slope(y[i], act);
+}
+
+__global__ void __launch_bounds__(256)
+channel_slice_kernel(const float* __restrict__ g, int C, int off, int Cs, float* __restrict__ out, long long total, int accumulate) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    long long m = i / Cs;
+    int c = (int)(i - m * Cs);
+    float v = g[m * C + off + c];
+    out[i] = accumulate ? out[i] + v : v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, PnpDropout drop) {
+  unsigned long long seed = *drop.seed_ptr;
+  long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float4 mu = pnp_dropout_mult4(drop, seed, (unsigned long long)i);
+    v.x *= mu.x; v.y *= mu.y; v.z *= mu.z; v.w *= mu.w;
+    reinterpret_cast<float4*>(y)[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    long long i = (n4 << 2) + threadIdx.x;
+    y[i] = x[i] * pnp_dropout_mult1(drop, seed, (unsigned long long)i);
+  }
+}
+
+__global__ void seed_advance_kernel(unsigned long long* s) { *s = *s * 6364136223846793005ull + 1442695040888963407ull; }
+
+// ------------------------------------------------------------------------------------------------
+// pooling / padding / phase shift
+// ------------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256)
+maxpool2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, CV = C / V;
+  long long total = (long long)B * Ho * Wo * CV;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    int cv = (int)(i % CV);
+    long long p = i / CV;
+    int ox = (int)(p % Wo);
+    long long t = p / Wo;
+    int oy = (int)(t % Ho);
+    int b = (int)(t / Ho);
+    const float* base = x + (((long long)b * H + 2 * oy) * W + 2 * ox) * C + cv * V;
+    float m[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) m[e] = base[e];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const float* s = base + ((long long)(k >> 1) * W + (k & 1)) * C;
+#pragma unroll
+      for (int e = 0; e < V; ++e) m[e] = fmaxf(m[e], s[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) y[p * C + cv * V + e] = m[e];
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256)
+maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, CV = C / V;
+  long long total = (long long)B * Ho * Wo * CV;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    int cv = (int)(i % CV);
+    long long p = i / CV;
+    int ox = (int)(p % Wo);
+    long long t = p / Wo;
+    int oy = (int)(t % Ho);
+    int b = (int)(t / Ho);
+    long long base = (((long long)b * H + 2 * oy) * W + 2 * ox) * C + cv * V;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = x[base + ((long long)(k >> 1) * W + (k & 1)) * C + e];
+      int arg = 0;
+      float best = v[0];
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (v[k] > best) { best = v[k]; arg = k; }   // first max in row-major window order
+      float g = dy[p * C + cv * V + e];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dx[base + ((long long)(k >> 1) * W + (k & 1)) * C + e] = (k == arg) ? g : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ int mirror_idx(int i, int n) { return i < 0 ? (-i - 1) : (i >= n ? 2 * n - 1 - i : i); }
+
+__global__ void __launch_bounds__(256)
+mirror_pad_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C, int p) {
+  const int Hp = H + 2 * p, Wp = W + 2 * p;
+  long long total = (long long)B * Hp * Wp * C;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    int c = (int)(i % C);
+    long long t = i / C;
+    int px = (int)(t % Wp);
+    t /= Wp;
+    int py = (int)(t % Hp);
+    int b = (int)(t / Hp);
+    int sy = mirror_idx(py - p, H), sx = mirror_idx(px - p, W);
+    y[i] = x[(((long long)b * H + sy) * W + sx) * C + c];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mirror_pad_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C, int p) {
+  const int Hp = H + 2 * p, Wp = W + 2 * p;
+  long long total = (long long)B * H * W * C;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    int c = (int)(i % C);
+    long long t = i / C;
+    int ix = (int)(t % W);
+    t /= W;
+    int iy = (int)(t % H);
+    int b = (int)(t / H);
+    int ys[3], xs[3], ny = 0, nx = 0;
+    ys[ny++] = iy + p;
+    if (iy < p) ys[ny++] = p - 1 - iy;
+    if (iy >= H - p) ys[ny++] = 2 * H - 1 - iy + p;
+    xs[nx++] = ix + p;
+    if (ix < p) xs[nx++] = p - 1 - ix;
+    if (ix >= W - p) xs[nx++] = 2 * W - 1 - ix + p;
+    float acc = 0.f;
+    for (int a = 0; a < ny; ++a)
+      for (int e = 0; e < nx; ++e) acc += dy[(((long long)b * Hp + ys[a]) * Wp + xs[e]) * C + c];
+    dx[i] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+phase_shift_fwd_kernel(const float* __restrict__ X, float* __restrict__ out, int B, int a, int b, int G, int r, int Ctot,
+                       int coff, int ntile, int order_b1) {
+  const int OH = a * r, OW = b * r;
+  long long total = (long long)B * OH * OW * G;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    int g = (int)(i % G);
+    long long t = i / G;
+    int x = (int)(t % OW);
+    t /= OW;
+    int y = (int)(t % OH);
+    int n = (int)(t / OH);
+    int iy = y / r, ry = y - iy * r, ix = x / r, rx = x - ix * r;
+    int sub = order_b1 ? (ry * r + rx) : (rx * r + ry);
+    float v = X[(((long long)n * a + iy) * b + ix) * ((long long)G * r * r) + (long long)g * r * r + sub];
+    float* dst = out + (((long long)n * OH + y) * OW + x) * Ctot + coff + g;
+    for (int tl = 0; tl < ntile; ++tl) dst[tl * G] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+phase_shift_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dX, int B, int a, int b, int G, int r, int Ctot,
+                       int coff, int ntile, int order_b1) {
+  const int OH = a * r, OW = b * r, rr = r * r;
+  const long long Cx = (long long)G * rr;
+  long long total = (long long)B * a * b * Cx;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    int ch = (int)(i % Cx);
+    long long t = i / Cx;
+    int ix = (int)(t % b);
+    t /= b;
+    int iy = (int)(t % a);
+    int n = (int)(t / a);
+    int g = ch / rr, sub = ch - g * rr;
+    int ry, rx;
+    if (order_b1) { ry = sub / r; rx = sub - ry * r; }
+    else { rx = sub / r; ry = sub - rx * r; }
+    const float* src = dout + (((long long)n * OH + iy * r + ry) * OW + ix * r + rx) * Ctot + coff + g;
+    float acc = 0.f;
+    for (int tl = 0; tl < ntile; ++tl) acc += src[tl * G];
+    dX[i] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+logits_argmax_concat_kernel(const float* __restrict__ logits, float* __restrict__ out, long long P, int C, int Ctot, int coff) {
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += (long long)gridDim.x * 256) {
+    const float* l = logits + p * C;
+    float* o = out + p * Ctot + coff;
+    float best = l[0];
+    int arg = 0;
+    o[0] = best;
+    for (int c = 1; c < C; ++c) {
+      float v = l[c];
+      o[c] = v;
+      if (v > best) { best = v; arg = c; }   // tf.argmax: lowest index on ties
+    }
+    o[C] = (float)arg;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// losses / metrics (C <= 8 classes)
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxC = 8;
+
+__global__ void __launch_bounds__(256)
+pixel_softmax2_kernel(const float* __restrict__ logits, float* __restrict__ out, long long P, int C) {
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += (long long)gridDim.x * 256) {
+    float e[kMaxC], s = 0.f;
+    for (int c = 0; c < C; ++c) { e[c] = expf(logits[p * C + c]); s += e[c]; }   // no max subtraction (layers.py:135)
+    for (int c = 0; c < C; ++c) out[p * C + c] = fminf(fmaxf(e[c] / s, -1e15f), 1e15f);
+  }
+}
+
+__device__ __forceinline__ void stable_softmax(const float* l, int C, float* p) {
+  float mx = l[0];
+  for (int c = 1; c < C; ++c) mx = fmaxf(mx, l[c]);
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) { p[c] = expf(l[c] - mx); s += p[c]; }
+  float inv = 1.f / s;
+  for (int c = 0; c < C; ++c) p[c] *= inv;
+}
+
+__global__ void __launch_bounds__(256)
+segloss_reduce_kernel(const float* __restrict__ logits, const float* __restrict__ y, long long P, int C, double* __restrict__ acc) {
+  __shared__ double s_acc[4 * kMaxC];
+  if (threadIdx.x < 4 * kMaxC) s_acc[threadIdx.x] = 0.0;
+  __syncthreads();
+  float a[4 * kMaxC];
+#pragma unroll
+  for (int i = 0; i < 4 * kMaxC; ++i) a[i] = 0.f;
+  int iter = 0;
+  double d[4 * kMaxC];
+#pragma unroll
+  for (int i = 0; i < 4 * kMaxC; ++i) d[i] = 0.0;
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += (long long)gridDim.x * 256) {
+    float l[kMaxC], pr[kMaxC];
+    for (int c = 0; c < C; ++c) l[c] = logits[p * C + c];
+    stable_softmax(l, C, pr);
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) {
+      if (c < C) {
+        float yy = y[p * C + c];
+        a[c] += yy;
+        a[kMaxC + c] += pr[c] * yy;
+        a[2 * kMaxC + c] += pr[c] * pr[c];
+        a[3 * kMaxC + c] += -yy * logf(fminf(fmaxf(pr[c], 0.005f), 1.0f));
+      }
+    }
+    if (++iter == 32) {   // promote to double before fp32 partials grow long
+#pragma unroll
+      for (int i = 0; i < 4 * kMaxC; ++i) { d[i] += (double)a[i]; a[i] = 0.f; }
+      iter = 0;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4 * kMaxC; ++i) {
+    double v = pnp_warp_sum_d(d[i] + (double)a[i]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[i], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 * kMaxC) {
+    int q = threadIdx.x / kMaxC, c = threadIdx.x % kMaxC;
+    if (c < C) atomicAdd(acc + q * C + c, s_acc[threadIdx.x]);
+  }
+}
+
+__global__ void segloss_finalize_kernel(const double* __restrict__ acc, long long P, int C, float* out, float* coef) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double tot = 0.0;
+  for (int c = 0; c < C; ++c) tot += acc[c];
+  double wce = 0.0, dice = 0.0;
+  for (int c = 0; c < C; ++c) {
+    double sy = acc[c], inse = acc[C + c], l = acc[2 * C + c], ce = acc[3 * C + c];
+    double w = 1.0 - sy / tot;
+    wce += w * ce;
+    double D = l + sy + 1e-7;
+    dice += 2.0 * inse / D;
+    coef[c] = (float)(w / (double)P);
+    coef[C + c] = (float)(-(2.0 / C) / D);
+    coef[2 * C + c] = (float)((4.0 / C) * inse / (D * D));
+  }
+  out[0] = (float)(wce / (double)P);
+  out[1] = (float)(-dice / C);
+}
+
+__global__ void __launch_bounds__(256)
+segloss_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ y, const float* __restrict__ coef,
+                   const float* __restrict__ g_wce, const float* __restrict__ g_dice, float* __restrict__ dlogits,
+                   long long P, int C) {
+  const float gw = g_wce ? *g_wce : 0.f;
+  const float gd = g_dice ? *g_dice : 0.f;
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += (long long)gridDim.x * 256) {
+    float l[kMaxC], pr[kMaxC], dp[kMaxC];
+    for (int c = 0; c < C; ++c) l[c] = logits[p * C + c];
+    stable_softmax(l, C, pr);
+    float dot = 0.f;
+    for (int c = 0; c < C; ++c) {
+      float yy = y[p * C + c];
+      float d = gd * (coef[C + c] * yy + coef[2 * C + c] * pr[c]);
+      if (pr[c] >= 0.005f) d += gw * (-coef[c] * yy / pr[c]);
+      dp[c] = d;
+      dot += d * pr[c];
+    }
+    for (int c = 0; c < C; ++c) dlogits[p * C + c] = pr[c] * (dp[c] - dot);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+confusion_kernel(const float* __restrict__ logits, const float* __restrict__ y, long long P, int C, unsigned long long* counts) {
+  __shared__ unsigned int s_cnt[kMaxC * kMaxC];
+  if (threadIdx.x < kMaxC * kMaxC) s_cnt[threadIdx.x] = 0u;
+  __syncthreads();
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += (long long)gridDim.x * 256) {
+    int pa = 0, ya = 0;
+    float pb = logits[p * C], yb = y[p * C];
+    for (int c = 1; c < C; ++c) {
+      float v = logits[p * C + c], w = y[p * C + c];
+      if (v > pb) { pb = v; pa = c; }
+      if (w > yb) { yb = w; ya = c; }
+    }
+    atomicAdd(&s_cnt[ya * C + pa], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < C * C && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256)
+fc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out, int F) {
+  __shared__ float s[8];
+  const float* row = x + (long long)blockIdx.x * F;
+  float acc = 0.f;
+  for (int f = threadIdx.x; f < F; f += 256) acc = fmaf(row[f], w[f], acc);
+  acc = pnp_warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s[i];
+    out[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ dout, float* __restrict__ dx,
+              float* __restrict__ dw, int B, int F) {
+  int f = blockIdx.x * 256 + threadIdx.x;
+  if (f >= F) return;
+  float wf = w[f], acc = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float d = dout[b];
+    if (dx) dx[(long long)b * F + f] = d * wf;
+    acc = fmaf(d, x[(long long)b * F + f], acc);
+  }
+  if (dw) dw[f] += acc;
+}
+
+__global__ void __launch_bounds__(256)
+mean_combo_kernel(const float* __restrict__ a, float ca, const float* __restrict__ b, float cb, int n, float* out) {
+  __shared__ float s[8];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) acc += ca * a[i] + (b ? cb * b[i] : 0.f);
+  acc = pnp_warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s[i];
+    out[0] = t / (float)n;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+l2_loss_kernel(const float* __restrict__ w, long long n, double* out) {
+  __shared__ double s[8];
+  double acc = 0.0;
+  float part = 0.f;
+  int it = 0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    float v = w[i];
+    part = fmaf(v, v, part);
+    if (++it == 64) { acc += (double)part; part = 0.f; it = 0; }
+  }
+  acc += (double)part;
+  acc = pnp_warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += s[i];
+    atomicAdd(out, 0.5 * t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// optimizers over flat arenas: one CTA per 1024-element chunk, 256 threads x float4
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
+            const int* __restrict__ chunk_seg, const float* __restrict__ seg_wd, float lr_t, float b1, float b2, float eps,
+            float gscale) {
+  const float wd = seg_wd[chunk_seg[blockIdx.x]];
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  float4 t = reinterpret_cast<float4*>(theta)[i];
+  float4 g = __ldg(reinterpret_cast<const float4*>(grad) + i);
+  float4 mm = reinterpret_cast<float4*>(m)[i];
+  float4 vv = reinterpret_cast<float4*>(v)[i];
+#define PNP_ADAM1(F)                                   \
+  {                                                    \
+    float gg = fmaf(wd, t.F, g.F * gscale);            \
+    mm.F = b1 * mm.F + (1.f - b1) * gg;                \
+    vv.F = b2 * vv.F + (1.f - b2) * gg * gg;           \
+    t.F -= lr_t * mm.F / (sqrtf(vv.F) + eps);          \
+  }
+  PNP_ADAM1(x) PNP_ADAM1(y) PNP_ADAM1(z) PNP_ADAM1(w)
+#undef PNP_ADAM1
+  reinterpret_cast<float4*>(theta)[i] = t;
+  reinterpret_cast<float4*>(m)[i] = mm;
+  reinterpret_cast<float4*>(v)[i] = vv;
+}
+
+__global__ void __launch_bounds__(256)
+rmsprop_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ ms, float* __restrict__ mom,
+               const int* __restrict__ chunk_seg, const float* __restrict__ seg_wd, const float* __restrict__ seg_clip,
+               float lr, float decay, float momentum, float eps, float gscale) {
+  const int seg = chunk_seg[blockIdx.x];
+  const float wd = seg_wd[seg];
+  const float clip = seg_clip ? seg_clip[seg] : 0.f;
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  float4 t = reinterpret_cast<float4*>(theta)[i];
+  float4 g = __ldg(reinterpret_cast<const float4*>(grad) + i);
+  float4 s = reinterpret_cast<float4*>(ms)[i];
+  float4 mo = reinterpret_cast<float4*>(mom)[i];
+#define PNP_RMS1(F)                                              \
+  {                                                              \
+    float gg = fmaf(wd, t.F, g.F * gscale);                      \
+    s.F = decay * s.F + (1.f - decay) * gg * gg;                 \
+    mo.F = momentum * mo.F + lr * gg / sqrtf(s.F + eps);         \
+    t.F -= mo.F;                                                 \
+    if (clip > 0.f) t.F = fminf(fmaxf(t.F, -clip), clip);        \
+  }
+  PNP_RMS1(x) PNP_RMS1(y) PNP_RMS1(z) PNP_RMS1(w)
+#undef PNP_RMS1
+  reinterpret_cast<float4*>(theta)[i] = t;
+  reinterpret_cast<float4*>(ms)[i] = s;
+  reinterpret_cast<float4*>(mom)[i] = mo;
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ p, float v, long long n) {
+  long long n4 = n >> 2;
+  float4 vv = make_float4(v, v, v, v);
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256)
+    reinterpret_cast<float4*>(p)[i] = vv;
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) p[(n4 << 2) + threadIdx.x] = v;
+}
+
+}  // namespace
+
+#define S_ ((cudaStream_t)stream)
+
+extern "C" int pnp_bn_stats(const float* z, long long M, int C, double* sum, double* sumsq, void* stream) {
+  if (!z || !sum || !sumsq) return PNP_ERR_BAD_ARG;
+  int tpr, grid; long long rpb;
+  int rc = reduce_launch_cfg(M, C, &tpr, &rpb, &grid);
+  if (rc) return rc;
+  bn_reduce_kernel<false><<<grid, 256, 0, S_>>>(z, nullptr, nullptr, nullptr, nullptr, 0, nullptr, M, C, tpr, rpb, sum, sumsq);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_bn_finalize(const double* sum, const double* sumsq, long long M, int C, const float* gamma,
+                               const float* beta, float* moving_mean, float* moving_var, int training, float* scale,
+                               float* shift, float* mean, float* invstd, void* stream) {
+  if (!gamma || !beta || !moving_mean || !moving_var || !scale || !shift || !mean || !invstd || C <= 0) return PNP_ERR_BAD_ARG;
+  if (training && (!sum || !sumsq || M <= 0)) return PNP_ERR_BAD_ARG;
+  bn_finalize_kernel<<<pnp_cdiv(C, 128), 128, 0, S_>>>(sum, sumsq, M, C, gamma, beta, moving_mean, moving_var, training, scale,
+                                                       shift, mean, invstd);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_bn_act_apply(const float* z, const float* scale, const float* shift, const float* skip, int Cs,
+                                int skip_off, int act, float* y, long long M, int C, void* stream) {
+  if (!z || !y || M <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
+  if (C % 4 != 0) return PNP_ERR_UNSUPPORTED;
+  if (skip && (Cs % 4 != 0 || skip_off % 4 != 0 || skip_off < 0 || skip_off + Cs > C)) return PNP_ERR_UNSUPPORTED;
+  if ((scale == nullptr) != (shift == nullptr)) return PNP_ERR_BAD_ARG;
+  long long n4 = M * (C / 4);
+  bn_act_apply_kernel<<<grid_for(n4, 256 * 4), 256, 0, S_>>>(z, scale, shift, skip, Cs, skip_off, act, y, n4, C / 4);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_bn_bwd_reduce(const float* dy, const float* y, const float* z, const float* mean, const float* invstd,
+                                 int act, float* g, double* sum_g, double* sum_gx, long long M, int C, void* stream) {
+  if (!dy || !z || !mean || !invstd || !g || !sum_g || !sum_gx) return PNP_ERR_BAD_ARG;
+  if (act != PNP_ACT_NONE && !y) return PNP_ERR_BAD_ARG;
+  int tpr, grid; long long rpb;
+  int rc = reduce_launch_cfg(M, C, &tpr, &rpb, &grid);
+  if (rc) return rc;
+  bn_reduce_kernel<true><<<grid, 256, 0, S_>>>(z, dy, y, mean, invstd, act, g, M, C, tpr, rpb, sum_g, sum_gx);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_bn_bwd_finalize(const double* sum_g, const double* sum_gx, long long M, int C, float* dgamma,
+                                   float* dbeta, float* coef, void* stream) {
+  if (!sum_g || !sum_gx || !coef || C <= 0 || M <= 0) return PNP_ERR_BAD_ARG;
+  bn_bwd_finalize_kernel<<<pnp_cdiv(C, 128), 128, 0, S_>>>(sum_g, sum_gx, M, C, dgamma, dbeta, coef);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_bn_bwd_apply(const float* g, const float* z, const float* mean, const float* invstd, const float* gamma,
+                                const float* coef, int training, const pnp_dropout_cfg* drop, float* dz, long long M, int C,
+                                void* stream) {
+  if (!g || !invstd || !gamma || !dz || M <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
+  if (training && (!z || !mean || !coef)) return PNP_ERR_BAD_ARG;
+  if (C % 4 != 0) return PNP_ERR_UNSUPPORTED;
+  long long n4 = M * (C / 4);
+  bn_bwd_apply_kernel<<<grid_for(n4, 256 * 4), 256, 0, S_>>>(g, z, mean, invstd, gamma, coef, training, make_drop(drop), dz, n4, C / 4);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_act_bwd(const float* dy, const float* y, int act, float* g, long long n, void* stream) {
+  if (!dy || !y || !g || n <= 0) return PNP_ERR_BAD_ARG;
+  act_bwd_kernel<<<grid_for(n, 256 * 8), 256, 0, S_>>>(dy, y, act, g, n);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_channel_slice(const float* g, int C, int off, int Cs, float* out, long long M, int accumulate, void* stream) {
+  if (!g || !out || M <= 0 || Cs <= 0 || off < 0 || off + Cs > C) return PNP_ERR_BAD_ARG;
+  long long total = M * Cs;
+  channel_slice_kernel<<<grid_for(total, 256 * 8), 256, 0, S_>>>(g, C, off, Cs, out, total, accumulate);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_dropout_apply(const float* x, float* y, long long n, const pnp_dropout_cfg* drop, void* stream) {
+  if (!x || !y || n <= 0) return PNP_ERR_BAD_ARG;
+  PnpDropout d = make_drop(drop);
+  if (!d.seed_ptr) {
+    if (x != y) PNP_CUDA(cudaMemcpyAsync(y, x, n * sizeof(float), cudaMemcpyDeviceToDevice, S_));
+    return PNP_OK;
+  }
+  dropout_kernel<<<grid_for(n / 4 + 1, 256 * 4), 256, 0, S_>>>(x, y, n, d);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_seed_advance(unsigned long long* seed_ptr, void* stream) {
+  if (!seed_ptr) return PNP_ERR_BAD_ARG;
+  seed_advance_kernel<<<1, 1, 0, S_>>>(seed_ptr);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_maxpool2_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+  if (!x || !y || B <= 0 || H <= 0 || W <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
+  if ((H | W) & 1) return PNP_ERR_UNSUPPORTED;
+  long long total = (long long)B * (H / 2) * (W / 2) * C;
+  if (C % 4 == 0) maxpool2_fwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S_>>>(x, y, B, H, W, C);
+  else maxpool2_fwd_kernel<1><<<grid_for(total, 256 * 4), 256, 0, S_>>>(x, y, B, H, W, C);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, void* stream) {
+  if (!x || !dy || !dx || B <= 0 || H <= 0 || W <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
+  if ((H | W) & 1) return PNP_ERR_UNSUPPORTED;
+  long long total = (long long)B * (H / 2) * (W / 2) * C;
+  if (C % 4 == 0) maxpool2_bwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S_>>>(x, dy, dx, B, H, W, C);
+  else maxpool2_bwd_kernel<1><<<grid_for(total, 256 * 4), 256, 0, S_>>>(x, dy, dx, B, H, W, C);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_mirror_pad_fwd(const float* x, float* y, int B, int H, int W, int C, int p, void* stream) {
+  if (!x || !y || B <= 0 || H <= 0 || W <= 0 || C <= 0 || p < 0) return PNP_ERR_BAD_ARG;
+  if (p > H || p > W) return PNP_ERR_UNSUPPORTED;
+  long long total = (long long)B * (H + 2 * p) * (W + 2 * p) * C;
+  mirror_pad_fwd_kernel<<<grid_for(total, 256 * 8), 256, 0, S_>>>(x, y, B, H, W, C, p);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_mirror_pad_bwd(const float* dy, float* dx, int B, int H, int W, int C, int p, void* stream) {
+  if (!dy || !dx || B <= 0 || H <= 0 || W <= 0 || C <= 0 || p < 0) return PNP_ERR_BAD_ARG;
+  if (2 * p > H || 2 * p > W) return PNP_ERR_UNSUPPORTED;
+  long long total = (long long)B * H * W * C;
+  mirror_pad_bwd_kernel<<<grid_for(total, 256 * 8), 256, 0, S_>>>(dy, dx, B, H, W, C, p);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_phase_shift_fwd(const float* X, float* out, int B, int a, int b, int G, int r, int Ctot, int coff,
+                                   int ntile, int order_b1, void* stream) {
+  if (!X || !out || B <= 0 || a <= 0 || b <= 0 || G <= 0 || r <= 0 || ntile <= 0 || coff < 0 || coff + ntile * G > Ctot)
+    return PNP_ERR_BAD_ARG;
+  long long total = (long long)B * a * r * b * r * G;
+  phase_shift_fwd_kernel<<<grid_for(total, 256 * 8), 256, 0, S_>>>(X, out, B, a, b, G, r, Ctot, coff, ntile, order_b1);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_phase_shift_bwd(const float* dout, float* dX, int B, int a, int b, int G, int r, int Ctot, int coff,
+                                   int ntile, int order_b1, void* stream) {
+  if (!dout || !dX || B <= 0 || a <= 0 || b <= 0 || G <= 0 || r <= 0 || ntile <= 0 || coff < 0 || coff + ntile * G > Ctot)
+    return PNP_ERR_BAD_ARG;
+  long long total = (long long)B * a * b * G * r * r;
+  phase_shift_bwd_kernel<<<grid_for(total, 256 * 8), 256, 0, S_>>>(dout, dX, B, a, b, G, r, Ctot, coff, ntile, order_b1);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_logits_argmax_concat(const float* logits, float* out, long long P, int C, int Ctot, int coff, void* stream) {
+  if (!logits || !out || P <= 0 || C <= 0 || coff < 0 || coff + C + 1 > Ctot) return PNP_ERR_BAD_ARG;
+  logits_argmax_concat_kernel<<<grid_for(P, 256 * 2), 256, 0, S_>>>(logits, out, P, C, Ctot, coff);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_pixel_softmax2(const float* logits, float* out, long long P, int C, void* stream) {
+  if (!logits || !out || P <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
+  if (C > kMaxC) return PNP_ERR_UNSUPPORTED;
+  pixel_softmax2_kernel<<<grid_for(P, 256 * 2), 256, 0, S_>>>(logits, out, P, C);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_segloss_reduce(const float* logits, const float* y, long long P, int C, double* acc, void* stream) {
+  if (!logits || !y || !acc || P <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
+  if (C > kMaxC) return PNP_ERR_UNSUPPORTED;
+  segloss_reduce_kernel<<<grid_for(P, 256 * 8), 256, 0, S_>>>(logits, y, P, C, acc);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_segloss_finalize(const double* acc, long long P, int C, float* out, float* coef, void* stream) {
+  if (!acc || !out || !coef || P <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
+  segloss_finalize_kernel<<<1, 32, 0, S_>>>(acc, P, C, out, coef);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_segloss_bwd(const float* logits, const float* y, const float* coef, const float* g_wce, const float* g_dice,
+                               float* dlogits, long long P, int C, void* stream) {
+  if (!logits || !y || !coef || !dlogits || P <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
+  if (C > kMaxC) return PNP_ERR_UNSUPPORTED;
+  segloss_bwd_kernel<<<grid_for(P, 256 * 2), 256, 0, S_>>>(logits, y, coef, g_wce, g_dice, dlogits, P, C);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_confusion(const float* logits, const float* y, long long P, int C, unsigned long long* counts, void* stream) {
+  if (!logits || !y || !counts || P <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
+  if (C > kMaxC) return PNP_ERR_UNSUPPORTED;
+  confusion_kernel<<<grid_for(P, 256 * 16), 256, 0, S_>>>(logits, y, P, C, counts);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_fc_fwd(const float* x, const float* w, float* out, int B, int F, void* stream) {
+  if (!x || !w || !out || B <= 0 || F <= 0) return PNP_ERR_BAD_ARG;
+  fc_fwd_kernel<<<B, 256, 0, S_>>>(x, w, out, F);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_fc_bwd(const float* x, const float* w, const float* dout, float* dx, float* dw, int B, int F, void* stream) {
+  if (!x || !w || !dout || B <= 0 || F <= 0) return PNP_ERR_BAD_ARG;
+  fc_bwd_kernel<<<pnp_cdiv(F, 256), 256, 0, S_>>>(x, w, dout, dx, dw, B, F);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_mean_combo(const float* a, float ca, const float* b, float cb, int n, float* out, void* stream) {
+  if (!a || !out || n <= 0) return PNP_ERR_BAD_ARG;
+  mean_combo_kernel<<<1, 256, 0, S_>>>(a, ca, b, cb, n, out);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_l2_loss_acc(const float* w, long long n, double* out, void* stream) {
+  if (!w || !out || n <= 0) return PNP_ERR_BAD_ARG;
+  l2_loss_kernel<<<grid_for(n, 256 * 16), 256, 0, S_>>>(w, n, out);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_adam_step(float* theta, const float* grad, float* m, float* v, long long n, const int* chunk_seg,
+                             const float* seg_wd, float lr_t, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  if (!theta || !grad || !m || !v || !chunk_seg || !seg_wd || n <= 0 || (n % 1024) != 0) return PNP_ERR_BAD_ARG;
+  adam_kernel<<<(unsigned)(n / 1024), 256, 0, S_>>>(theta, grad, m, v, chunk_seg, seg_wd, lr_t, beta1, beta2, eps, grad_scale);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_rmsprop_step(float* theta, const float* grad, float* ms, float* mom, long long n, const int* chunk_seg,
+                                const float* seg_wd, const float* seg_clip, float lr, float decay, float momentum, float eps,
+                                float grad_scale, void* stream) {
+  if (!theta || !grad || !ms || !mom || !chunk_seg || !seg_wd || n <= 0 || (n % 1024) != 0) return PNP_ERR_BAD_ARG;
+  rmsprop_kernel<<<(unsigned)(n / 1024), 256, 0, S_>>>(theta, grad, ms, mom, chunk_seg, seg_wd, seg_clip, lr, decay, momentum, eps,
+                                                      grad_scale);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_fill(float* p, float v, long long n, void* stream) {
+  if (!p || n <= 0) return PNP_ERR_BAD_ARG;
+  fill_kernel<<<grid_for(n / 4 + 1, 256 * 4), 256, 0, S_>>>(p, v, n);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" const char* pnp_error_string(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case PNP_ERR_BAD_ARG: return "pnp: bad argument";
+    case PNP_ERR_UNSUPPORTED: return "pnp: unsupported shape/configuration";
+    case PNP_ERR_DRIVER: return "pnp: CUDA driver entry point unavailable";
+    default: return cudaGetErrorString((cudaError_t)code);
+  }
+}
+
+extern "C" int pnp_version(void) { return 100; }
