@@ -145,6 +145,8 @@ int pnp_segloss_bwd(const float* logits, const float* y, const float* coef, cons
                     float* dlogits, long long P, int C, void* stream);
 /* lib.py:96-110 + tf.confusion_matrix: counts[C*C] (confusion, rows = truth), from logits argmax vs one-hot y */
 int pnp_confusion(const float* logits, const float* y, long long P, int C, unsigned long long* counts, void* stream);
+/* lib._label_decomp (lib.py:75-92): int64 label map -> one-hot fp32 [P, C], on the device */
+int pnp_one_hot(const long long* labels, float* out, long long P, int C, void* stream);
 /* tf.matmul [B,F]x[F,1] (adversarial.py:397,440) */
 int pnp_fc_fwd(const float* x, const float* w, float* out, int B, int F, void* stream);
 int pnp_fc_bwd(const float* x, const float* w, const float* dout, float* dx, float* dw, int B, int F, void* stream);
@@ -156,13 +158,17 @@ int pnp_l2_loss_acc(const float* w, long long n, double* out, void* stream);
 /* ---- optimizers on flat arenas ------------------------------------------------------------------------
  * chunk_seg[i] = segment id of arena elements [1024*i, 1024*i+1024); seg_wd / seg_clip are per segment.
  * grad_scale folds the data-parallel 1/N average; wd adds wd*theta to the gradient (tf.nn.l2_loss terms). */
-/* tf.train.AdamOptimizer (source_segmenter.py:378) -- epsilon-hat form; lr_t computed on host */
+/* tf.train.AdamOptimizer (source_segmenter.py:378) -- epsilon-hat form.  Hyper state lives in device memory so a
+ * captured CUDA graph stays valid across steps: state = [beta1^t, beta2^t, lr, lr_t] (doubles).
+ * pnp_adam_advance: t += 1, lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t); pnp_adam_step applies the update with lr_t. */
+int pnp_adam_advance(double* state, float beta1, float beta2, void* stream);
 int pnp_adam_step(float* theta, const float* grad, float* m, float* v, long long n, const int* chunk_seg,
-                  const float* seg_wd, float lr_t, float beta1, float beta2, float eps, float grad_scale, void* stream);
+                  const float* seg_wd, const double* state, float beta1, float beta2, float eps, float grad_scale,
+                  void* stream);
 /* tf.train.RMSPropOptimizer (adversarial.py:643-652) + clip_by_value (adversarial.py:653-654) */
 int pnp_rmsprop_step(float* theta, const float* grad, float* ms, float* mom, long long n, const int* chunk_seg,
-                     const float* seg_wd, const float* seg_clip, float lr, float decay, float momentum, float eps,
-                     float grad_scale, void* stream);
+                     const float* seg_wd, const float* seg_clip, const float* lr_ptr /* device scalar */, float decay,
+                     float momentum, float eps, float grad_scale, void* stream);
 int pnp_fill(float* p, float v, long long n, void* stream);
 
 #ifdef __cplusplus

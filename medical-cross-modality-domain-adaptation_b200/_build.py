@@ -52,7 +52,7 @@ def build(force=False, verbose=True):
         with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
             list(ex.map(run, jobs))
     if force or jobs or _stale(LIB, objs):
-        run([nvcc, "-shared", "-o", LIB] + objs + ["-cudart", "static"])
+        run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-cudart", "static"])
     return LIB
 
 

@@ -1,0 +1,458 @@
+"""PnP-AdaNet adversarial graph and its alternating D / G training steps -- the B200-native counterpart
+of the reference's adversarial.py (Full_DRN :44-574, Trainer :576-1108), eager instead of TF-1 graph.
+
+    MR stream : group_1..6 (frozen source segmenter front, BN scopes pred_*)      adversarial.py:130-199
+    CT stream : adapt_1..6 (domain adaptation module "DAM", BN scopes adapt_*)      adversarial.py:201-269
+    shared    : group_7..10 + output (frozen back half)                              adversarial.py:273-318
+    D         : cls_scope  -- multi-scale feature-map discriminator                  adversarial.py:320-400
+    M         : mask_cls_scope -- segmentation-mask critic                            adversarial.py:402-443
+    losses    : WGAN critic means + L2 regularisers                                   adversarial.py:445-476
+    steps     : RMSProp(cls_vars) + clip +-0.03 ; RMSProp(adapt_vars)                 adversarial.py:633-656,840-882
+
+Reference defects reproduced or fixed: `predictor`/`predicter` both exposed; critics
+run with hard-wired keep_prob=0.75 and batch-statistics BN (overridable for parity runs); every critic
+weight is counted twice in the L2 sums because create_classifier/create_mask_critic append to the weight
+lists on each of their two calls.
+"""
+import logging
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import functional as F
+from . import layers as L
+from . import optim
+from . import parallel
+from . import runtime as rt
+from .data import SyntheticSource, to_device
+from .lib import _save
+from .networks import FB, FRONT, BACK, SegmenterHalf, SegmenterTail
+
+# feature discriminator stages: (scope, cin, cout, inc_dim, down kernel, down stride)  adversarial.py:337-386
+_CLS_STAGES = [("cls_1", 2 * FB, 4 * FB, True, 3, 2), ("cls_2", 4 * FB, 8 * FB, True, 5, 2), ("cls_3", 8 * FB, 16 * FB, True, 3, 2),
+               ("cls_4", 16 * FB, 32 * FB, True, 3, 2), ("cls_5", 32 * FB, 32 * FB, False, 5, 4)]
+
+
+def _pred_namer(gi, blk, kind):
+    base = "pred_%d_%d" % (gi, blk)
+    return base if kind == "b" else (base + "_1", base + "_2")
+
+
+def _adapt_namer(gi, blk, kind):
+    # adversarial.py:206-267: scope 'adapt_1' / 'adapt_2' for groups 1-2, 'adapt_k_b' afterwards
+    base = "adapt_%d" % gi if gi <= 2 else "adapt_%d_%d" % (gi, blk)
+    return (base + "_1", base + "_2")
+
+
+class Full_DRN(object):
+
+    def __init__(self, channels, n_class, batch_size, cost_kwargs={}, network_config={}, critic_keep_prob=0.75, **kwargs):
+        rt.reset_default_graph()
+        self.n_class = n_class
+        self.batch_size = batch_size
+        self.network_config = network_config
+        self.mr_front_trainable = network_config.get("mr_front_trainable", False)
+        self.ct_front_trainable = network_config.get("ct_front_trainable", True)
+        self.joint_trainable = network_config.get("joint_trainable", False)
+        self.cls_trainable = network_config.get("cls_trainable", True)
+        self.m_cls_trainable = network_config.get("m_cls_trainable", True)
+        # hard-wired Python defaults of create_classifier / create_mask_critic (adversarial.py:320,402)
+        self.critic_keep_prob = critic_keep_prob
+        sd_plain = kwargs.get("stddev_plain", 0.01)    # weight_variable        (groups 1-4 of the MR path)
+        sd_share = kwargs.get("stddev", 0.1)           # sharable_weight_variable (everything else)
+
+        self.mr_front_a = SegmenterHalf({g: FRONT[g] for g in (1, 2, 3, 4)}, "group_%d", channels, _pred_namer,
+                                        self.mr_front_trainable, sd_plain)
+        self.mr_front_b = SegmenterHalf({g: FRONT[g] for g in (5, 6)}, "group_%d", self.mr_front_a.out_channels, _pred_namer,
+                                        self.mr_front_trainable, sd_share)
+        self.back = SegmenterHalf(BACK, "group_%d", self.mr_front_b.out_channels, _pred_namer, self.joint_trainable, sd_share)
+        self.tail = SegmenterTail(n_class, self.joint_trainable, sd_share)
+        self.ct_front = SegmenterHalf(FRONT, "adapt_%d", channels, _adapt_namer, self.ct_front_trainable, sd_share)
+
+        # weight lists exactly as the reference fills them (used for the L2 terms, adversarial.py:463-470)
+        back_ws = self.back.weights + [self.tail.w10]
+        self.mr_front_weights = self.mr_front_a.weights + self.mr_front_b.weights + back_ws + back_ws
+        self.ct_front_weights = list(self.ct_front.weights)
+        self.joint_weights = []
+        self.cls_weights_unique, self.m_cls_weights_unique = self._build_critics(sd_share)
+        self.cls_weights = self.cls_weights_unique * 2        # appended on each of the two create_classifier calls
+        self.m_cls_weights = self.m_cls_weights_unique * 2
+
+        ck = dict(cost_kwargs)
+        self.miu_dis = ck["miu_dis"]
+        self.miu_gen = ck["miu_gen"]
+        lam = ck.pop("lambda_mask_loss", 1.0)
+        self.lambda_mask_loss = 1.0 if lam is None else lam
+        self.reg_coeff = ck.pop("regularizer", 1.0e-4)
+        self.gan_reg_coeff = ck.pop("gan_regularizer", 1.0e-4)
+        self._get_variables_by_scope()
+
+    # ---- variable creation for the critics ---------------------------------------------------------------
+    def _build_critics(self, sd):
+        cls_w, m_w = [], []
+        with rt.variable_scope("cls_scope"):
+            for name, cin, cout, inc, dk, ds in _CLS_STAGES:
+                with rt.variable_scope(name):
+                    cls_w.append(L.sharable_weight_variable([3, 3, cin, cout], sd, self.cls_trainable, "Variable"))
+                    cls_w.append(L.sharable_weight_variable([3, 3, cout, cout], sd, self.cls_trainable, "Variable_1"))
+                    cls_w.append(L.sharable_weight_variable([dk, dk, cout, cout], sd, self.cls_trainable, "Variable_2"))
+                    for sfx in ("_1", "_2", "_3"):
+                        L.bn_variables(name + sfx, cout, self.cls_trainable)
+            with rt.variable_scope("cls_6"):
+                cls_w.append(L.sharable_weight_variable([3, 3, 32 * FB, 32 * FB], sd, self.cls_trainable, "Variable"))
+                L.bn_variables("cls_6", 32 * FB, self.cls_trainable)
+            with rt.variable_scope("cls_out"):
+                cls_w.append(L.sharable_weight_variable([32 * FB * 4, 1], sd, self.cls_trainable, "Variable"))
+        t = self.m_cls_trainable
+        nc = self.n_class
+        with rt.variable_scope("mask_cls_scope"):
+            with rt.variable_scope("mask_cls_1"):
+                m_w.append(L.sharable_weight_variable([3, 3, nc, FB], sd, t, "Variable"))
+                L.bn_variables("mask_cls_1", FB, t)
+            with rt.variable_scope("mask_cls_2"):
+                m_w.append(L.sharable_weight_variable([3, 3, FB, FB], sd, t, "Variable"))
+                m_w.append(L.sharable_weight_variable([3, 3, FB, FB], sd, t, "Variable_1"))
+                m_w.append(L.sharable_weight_variable([5, 5, FB, 2 * FB], sd, t, "Variable_2"))
+                for sfx, c in (("_1", FB), ("_2", FB), ("_3", 2 * FB)):
+                    L.bn_variables("m_cls_2" + sfx, c, t)
+            with rt.variable_scope("mask_cls_3"):
+                m_w.append(L.sharable_weight_variable([3, 3, 2 * FB, 4 * FB], sd, t, "Variable"))
+                m_w.append(L.sharable_weight_variable([3, 3, 4 * FB, 4 * FB], sd, t, "Variable_1"))
+                m_w.append(L.sharable_weight_variable([5, 5, 4 * FB, 8 * FB], sd, t, "Variable_2"))
+                for sfx, c in (("_1", 4 * FB), ("_2", 4 * FB), ("_3", 8 * FB)):
+                    L.bn_variables("m_cls_3" + sfx, c, t)
+            with rt.variable_scope("mask_cls_4"):
+                m_w.append(L.sharable_weight_variable([5, 5, 8 * FB, 16 * FB], sd, t, "Variable"))
+                L.bn_variables("m_cls_4", 16 * FB, t)
+            with rt.variable_scope("m_cls_out"):
+                m_w.append(L.sharable_weight_variable([16 * FB * 4, 1], sd, t, "Variable"))
+        return cls_w, m_w
+
+    def _get_variables_by_scope(self):
+        """adversarial.py:478-501: membership by substring of the variable name"""
+        self.adapt_vars, self.cls_vars, self.seg_vars, self.mri_seg_vars = [], [], [], []
+        for name in rt.graph.order:
+            v = rt.graph.vars[name]
+            if "cls" in name:
+                self.cls_vars.append(v)
+            elif "adapt" in name:
+                self.adapt_vars.append(v)
+            elif "output" in name:
+                self.seg_vars.append(v)
+                self.mri_seg_vars.append(v)
+            elif "group" in name:
+                self.mri_seg_vars.append(v)
+
+    # ---- sub-graphs ------------------------------------------------------------------------------------------
+    def segment(self, x, stream, keep_prob, front_bn, joint_bn=False):
+        """create_zip_network + create_second_half for one stream ('mr' | 'ct')"""
+        if stream == "mr":
+            h, ta = self.mr_front_a.run(x, keep_prob, front_bn, self.mr_front_trainable)
+            h, tb = self.mr_front_b.run(h, keep_prob, front_bn, self.mr_front_trainable)
+            c4, c6 = ta[4], tb[6]
+        else:
+            h, t = self.ct_front.run(x, keep_prob, front_bn, self.ct_front_trainable)
+            c4, c6 = t[4], t[6]
+        h, t3 = self.back.run(h, keep_prob, joint_bn, self.joint_trainable)
+        logits = self.tail.run(h, keep_prob, self.batch_size)
+        return {"c4_2": c4, "c6_2": c6, "b7": t3[7], "b8": t3[8], "c9_2": t3[9], "logits": logits}
+
+    def create_classifier(self, input_conv4, input_conv6, input_b7, input_conv9, seg_logits, keep_prob=None, cls_bn=True):
+        """adversarial.py:320-400 -> [B,1] critic logits"""
+        kp = self.critic_keep_prob if keep_prob is None else keep_prob
+        tr = self.cls_trainable
+        with rt.variable_scope("cls_scope"):
+            h = F.disc_input(input_conv4, input_conv6, input_b7, input_conv9, seg_logits, self.batch_size)
+            v = rt.graph.vars
+            for name, cin, cout, inc, dk, ds in _CLS_STAGES:
+                with rt.variable_scope(name):
+                    p = "cls_scope/%s/" % name
+                    h = L.residual_block(h, v[p + "Variable"], v[p + "Variable_1"], keep_prob=kp, inc_dim=inc, is_train=cls_bn,
+                                         bn_trainable=tr, scope=name, leak=True)
+                    h = L.conv_bn_relu2d(h, v[p + "Variable_2"], kp, strides=[1, ds, ds, 1], is_train=cls_bn, bn_trainable=tr,
+                                         scope=name + "_3", leak=True)
+            with rt.variable_scope("cls_6"):
+                h = L.conv_bn_relu2d(h, v["cls_scope/cls_6/Variable"], strides=[1, 2, 2, 1], keep_prob=kp, padding="SYMMETRIC",
+                                     scope="cls_6", is_train=cls_bn, bn_trainable=tr, leak=True)
+            flat = h.reshape(-1, FB * 32 * 4)
+            return F.fc(flat, v["cls_scope/cls_out/Variable"])
+
+    def create_mask_critic(self, input_mask, keep_prob=None, m_cls_bn=True):
+        """adversarial.py:402-443 -> [B,1] critic logits"""
+        kp = self.critic_keep_prob if keep_prob is None else keep_prob
+        tr = self.m_cls_trainable
+        v = rt.graph.vars
+        m = "mask_cls_scope/"
+        with rt.variable_scope("mask_cls_scope"):
+            with rt.variable_scope("mask_cls_1"):
+                h = L.conv_bn_relu2d(input_mask, v[m + "mask_cls_1/Variable"], kp, strides=[1, 2, 2, 1], is_train=m_cls_bn,
+                                     bn_trainable=tr, scope="mask_cls_1", leak=True)
+            with rt.variable_scope("mask_cls_2"):
+                h = L.residual_block(h, v[m + "mask_cls_2/Variable"], v[m + "mask_cls_2/Variable_1"], keep_prob=kp, inc_dim=False,
+                                     is_train=m_cls_bn, bn_trainable=tr, scope="m_cls_2", leak=True)
+                h = L.conv_bn_relu2d(h, v[m + "mask_cls_2/Variable_2"], kp, strides=[1, 4, 4, 1], is_train=m_cls_bn,
+                                     bn_trainable=tr, scope="m_cls_2_3", leak=True)
+            with rt.variable_scope("mask_cls_3"):
+                h = L.residual_block(h, v[m + "mask_cls_3/Variable"], v[m + "mask_cls_3/Variable_1"], keep_prob=kp, inc_dim=True,
+                                     is_train=m_cls_bn, bn_trainable=tr, scope="m_cls_3", leak=True)
+                h = L.conv_bn_relu2d(h, v[m + "mask_cls_3/Variable_2"], kp, strides=[1, 4, 4, 1], is_train=m_cls_bn,
+                                     bn_trainable=tr, scope="m_cls_3_3", leak=True)
+            with rt.variable_scope("mask_cls_4"):
+                h = L.conv_bn_relu2d(h, v[m + "mask_cls_4/Variable"], strides=[1, 4, 4, 1], keep_prob=kp, padding="SYMMETRIC",
+                                     scope="m_cls_4", is_train=m_cls_bn, bn_trainable=tr, leak=True)
+            flat = h.reshape(-1, FB * 16 * 4)
+            return F.fc(flat, v[m + "m_cls_out/Variable"])
+
+    def classify(self, feats):
+        return self.create_classifier(feats["c4_2"], feats["c6_2"], feats["b7"], feats["c9_2"], feats["logits"])
+
+    # ---- predictions / metrics ------------------------------------------------------------------------------------
+    def predicter(self, logits):
+        return L.pixel_wise_softmax_2(logits)
+
+    predictor = predicter   # adversarial.py:101-102 uses both spellings
+
+    def compact_pred(self, logits):
+        return torch.argmax(self.predicter(logits), 3)
+
+    def dice_eval(self, logits, y):
+        from .lib import _dice_eval
+        return _dice_eval(logits, y, self.n_class)
+
+    # ---- losses (adversarial.py:445-476) ------------------------------------------------------------------------------
+    def dis_loss_terms(self, ct_cls, mr_cls, ct_mask, mr_mask):
+        """returns [(loss tensor, weight in the total)]: dis_loss = -miu*mean(mr-ct) + lambda * (same for masks)"""
+        terms = [(F.mean_combo(mr_cls, -self.miu_dis, ct_cls, self.miu_dis), 1.0)]
+        if ct_mask is not None:
+            terms.append((F.mean_combo(mr_mask, -self.miu_dis, ct_mask, self.miu_dis), self.lambda_mask_loss))
+        return terms
+
+    def gen_loss_terms(self, ct_cls, ct_mask):
+        terms = [(F.mean_combo(ct_cls, -self.miu_gen), 1.0)]
+        if ct_mask is not None:
+            terms.append((F.mean_combo(ct_mask, -self.miu_gen), self.lambda_mask_loss))
+        return terms
+
+    def dis_reg(self):
+        l2 = lambda ws: float(F.l2_loss_sum(ws).item())
+        return self.gan_reg_coeff * self.miu_dis * (2 * l2(self.cls_weights_unique) + self.lambda_mask_loss * 2 * l2(self.m_cls_weights_unique))
+
+    def gen_reg(self):
+        return self.gan_reg_coeff * self.miu_gen * float(F.l2_loss_sum(self.ct_front_weights).item())
+
+    def fixed_coeff_reg(self):
+        """monitoring scalar of adversarial.py:465 (back-half weights counted twice, joint_weights empty)"""
+        uniq = self.mr_front_a.weights + self.mr_front_b.weights
+        back = self.back.weights + [self.tail.w10]
+        return self.reg_coeff * (float(F.l2_loss_sum(uniq).item()) + 2 * float(F.l2_loss_sum(back).item()))
+
+    # ---- checkpoint naming contract --------------------------------------------------------------------------
+    def restore(self, model_path, no_gan=False, clear_rms=False, skip_keywords=("Adam", "RMS", "cls")):
+        """adversarial.py:503-574.  no_gan: only 'group*'/'output*' conv weights (no BN) from a baseline
+        segmenter checkpoint; otherwise every known variable except names containing a skip keyword when
+        clear_rms is set (optimizer slots are not stored in our checkpoints at all)."""
+        d = dict(np.load(model_path))
+        if no_gan:
+            d = {k: v for k, v in d.items() if (k.startswith("group") or k.startswith("output")) and "/Variable" in k}
+        return rt.load_state_dict(d, strict=False)
+
+    def load_batch_norm_weights(self, baseline_path):
+        """adversarial.py:743-765: baseline 'BatchNorm_k/*' -> 'group_g/pred_*' in creation order
+        (lists/old_bn_list -> lists/pred_bn_list)."""
+        d = dict(np.load(baseline_path))
+        scopes = []
+        for half in (self.mr_front_a, self.mr_front_b, self.back):
+            for gi, scope, ops_ in half.plan:
+                for op in ops_:
+                    if op[0] in ("r", "R", "d"):
+                        scopes += [scope + "/" + op[3][0], scope + "/" + op[3][1]]
+                    elif op[0] == "b":
+                        scopes.append(scope + "/" + op[2])
+        out = {}
+        for k, s in enumerate(scopes):
+            old = "BatchNorm" if k == 0 else "BatchNorm_%d" % k
+            for leaf in ("beta", "gamma", "moving_mean", "moving_variance"):
+                if old + "/" + leaf in d:
+                    out[s + "/" + leaf] = d[old + "/" + leaf]
+        return rt.load_state_dict(out, strict=True)
+
+    def adapt_copy_weights(self):
+        """adversarial.py:706-741: initialise the CT DAM (adapt_k) from the MR front (group_k), conv weights
+        and BN variables, by structural correspondence (lists/half_zip_mri_vars -> lists/half_zip_ct_vars)."""
+        src_plan = self.mr_front_a.plan + self.mr_front_b.plan
+        with torch.no_grad():
+            for (g1, s1, ops1), (g2, s2, ops2) in zip(src_plan, self.ct_front.plan):
+                for o1, o2 in zip(ops1, ops2):
+                    if o1[0] == "p":
+                        continue
+                    nw = 1 if o1[0] in ("c", "b") else 2
+                    for a, b in zip(o1[1:1 + nw], o2[1:1 + nw]):
+                        b.copy_(a)
+                        b.pnp_version += 1
+                    if o1[0] in ("r", "R", "d"):
+                        for sa, sb in zip(o1[3], o2[3]):
+                            for leaf in ("beta", "gamma", "moving_mean", "moving_variance"):
+                                rt.graph.vars["%s/%s/%s" % (s2, sb, leaf)].copy_(rt.graph.vars["%s/%s/%s" % (s1, sa, leaf)])
+
+
+class Trainer(object):
+    """adversarial.py:576-1108 re-hosted: alternating D (x dis_sub_iter, + clip) / G (x gen_sub_iter) updates."""
+
+    def __init__(self, net, mr_train_list=None, mr_val_list=None, ct_train_list=None, ct_val_list=None, adapt_var_list=None,
+                 mr_var_list=None, old_bn_list=None, new_bn_list=None, test_label_list=None, test_nii_list=None, num_cls=None,
+                 batch_size=6, opt_kwargs={}, train_config={}, mr_source=None, ct_source=None):
+        self.net = net
+        self.batch_size = batch_size
+        self.num_cls = num_cls
+        self.opt_kwargs = dict(opt_kwargs)
+        self.train_config = dict(train_config)
+        self.lr_update_flag = self.train_config.get("lr_update", False)
+        self.mr_source, self.ct_source = mr_source, ct_source
+        self.dp = parallel.DataParallel()
+        self.global_step = 0
+        self.dis_sub_iter = self.train_config.get("dis_sub_iter", 1)
+        self.gen_sub_iter = self.train_config.get("gen_sub_iter", 1)
+        self._build_optimizers()
+
+    def _build_optimizers(self):
+        """adversarial.py:633-656"""
+        net = self.net
+        lr = self.opt_kwargs.pop("learning_rate", 3e-4)
+        self.LR_refresh = lr
+        opt = lambda v: getattr(v, "pnp_kind", "") in ("weight", "bn_gamma", "bn_beta")   # moving stats get no gradient
+        self.d_vars = [v for v in net.cls_vars if opt(v)]
+        self.g_vars = [v for v in net.adapt_vars if opt(v)]
+        self.d_arena = optim.Arena(self.d_vars)
+        self.g_arena = optim.Arena(self.g_vars)
+        # clip_op: every cls var whose name contains "Variable" (conv + FC weights of D and M)
+        clip = [0.03 if "Variable" in v.pnp_name else 0.0 for v in self.d_vars]
+        self.dis_optimizer = optim.RMSProp(self.d_arena, lr=lr, clip=clip, **self.opt_kwargs)
+        self.gen_optimizer = optim.RMSProp(self.g_arena, lr=lr, **self.opt_kwargs)
+        self._refresh_weight_decay()
+        self._others = [v for v in rt.global_variables() if id(v) not in {id(x) for x in self.d_vars + self.g_vars}]
+        dev = self.d_arena.theta.device
+        self._one = torch.tensor(1.0, device=dev)
+        self._lam = torch.tensor(float(net.lambda_mask_loss), device=dev)
+        self._mode = None
+
+    def _refresh_weight_decay(self):
+        """gradient of  dis_reg / dis_sub_iter  and  gen_reg / gen_sub_iter  folded into the optimizer kernels"""
+        net = self.net
+        d_ids = {id(w) for w in net.cls_weights_unique}
+        m_ids = {id(w) for w in net.m_cls_weights_unique}
+        base = net.gan_reg_coeff * net.miu_dis * 2.0 / float(self.dis_sub_iter)
+        wd = [base if id(v) in d_ids else (base * net.lambda_mask_loss if id(v) in m_ids else 0.0) for v in self.d_vars]
+        self.dis_optimizer.set_weight_decay(wd)
+        g_ids = {id(w) for w in net.ct_front_weights}
+        gb = net.gan_reg_coeff * net.miu_gen / float(self.gen_sub_iter)
+        self.gen_optimizer.set_weight_decay([gb if id(v) in g_ids else 0.0 for v in self.g_vars])
+
+    def _set_mode(self, mode):
+        """minimize(var_list=...): only the listed variables receive gradients"""
+        if self._mode == mode:
+            return
+        for v in self.d_vars:
+            v.requires_grad_(mode == "D")
+        for v in self.g_vars:
+            v.requires_grad_(mode == "G")
+        for v in self._others:
+            if v.requires_grad:
+                v.requires_grad_(False)
+        self._mode = mode
+
+    # ---- the two hot steps --------------------------------------------------------------------------------------------
+    def d_step(self, mr_batch, ct_batch, keep_prob=0.75):
+        """adversarial.py:840-862: feed mr+ct, all segmenter BN switches False, dropout on; dis_optimizer; clip."""
+        net = self.net
+        self._set_mode("D")
+        self.d_arena.zero_grad()
+        rt.rng.advance()
+        with torch.no_grad():
+            fm = net.segment(mr_batch, "mr", keep_prob, front_bn=False, joint_bn=False)
+            fc_ = net.segment(ct_batch, "ct", keep_prob, front_bn=False, joint_bn=False)
+        ct_cls = net.classify(fc_)
+        mr_cls = net.classify(fm)
+        ct_m = mr_m = None
+        if net.lambda_mask_loss != 0:
+            ct_m = net.create_mask_critic(fc_["logits"])
+            mr_m = net.create_mask_critic(fm["logits"])
+        terms = net.dis_loss_terms(ct_cls, mr_cls, ct_m, mr_m)
+        torch.autograd.backward([t for t, _ in terms], [self._one, self._lam][:len(terms)])
+        scale = self.dp.allreduce(self.d_arena.grad)
+        self.dis_optimizer.step(grad_scale=scale)
+        self.global_step += 1
+        return terms
+
+    def g_step(self, ct_batch, keep_prob=0.75):
+        """adversarial.py:869-882: feed ct only, ct_front_bn True (DAM BN trains), others False; gen_optimizer."""
+        net = self.net
+        self._set_mode("G")
+        self.g_arena.zero_grad()
+        rt.rng.advance()
+        fc_ = net.segment(ct_batch, "ct", keep_prob, front_bn=True, joint_bn=False)
+        ct_cls = net.classify(fc_)
+        ct_m = net.create_mask_critic(fc_["logits"]) if net.lambda_mask_loss != 0 else None
+        terms = net.gen_loss_terms(ct_cls, ct_m)
+        torch.autograd.backward([t for t, _ in terms], [self._one, self._lam][:len(terms)])
+        scale = self.dp.allreduce(self.g_arena.grad)
+        self.gen_optimizer.step(grad_scale=scale)
+        self.global_step += 1
+        return terms
+
+    @staticmethod
+    def loss_value(terms):
+        return sum(float(t) * w for t, w in terms)
+
+    # ---- schedule (adversarial.py:767-940) ---------------------------------------------------------------------------------
+    def train(self, output_path, restore=True, restored_path=None, training_iters=200, epochs=1000, dropout=0.75, display_step=5):
+        save_path = os.path.join(output_path, "model.cpkt")
+        if epochs == 0:
+            return save_path
+        os.makedirs(output_path, exist_ok=True)
+        cfg = self.train_config
+        if restore and restored_path and os.path.exists(os.path.join(restored_path, "latest.npz")):
+            ck = os.path.join(restored_path, "latest.npz")
+            self.net.restore(ck, no_gan=cfg.get("restore_from_baseline", False), clear_rms=cfg.get("clear_rms", False))
+            if cfg.get("restore_from_baseline", False):
+                self.net.load_batch_norm_weights(ck)
+                print("initializing from baseline model!")
+                self.net.adapt_copy_weights()
+        if self.lr_update_flag:
+            self.dis_optimizer.set_lr(self.LR_refresh)
+            self.gen_optimizer.set_lr(self.LR_refresh)
+        B = self.batch_size
+        mr_src = self.mr_source or SyntheticSource(B, seed=1234 + self.dp.rank, num_cls=self.num_cls or 5)
+        ct_src = self.ct_source or SyntheticSource(B, seed=4321 + self.dp.rank, shift=0.3, scale=0.8, num_cls=self.num_cls or 5)
+        dev = rt.device()
+        dis_interval, gen_interval = cfg.get("dis_interval", 1), cfg.get("gen_interval", 1)
+        dis_inc, gen_inc = cfg.get("dis_sub_iter_inc", 0), cfg.get("gen_sub_iter_inc", 0)
+        upd_interval = cfg.get("iter_upd_interval", 999999999999)
+        ckpt_space = cfg.get("checkpoint_space", 100)
+        decay = cfg.get("lr_decay_factor", 0.98)
+        for epoch in range(epochs):
+            for step in range(epoch * training_iters, (epoch + 1) * training_iters):
+                start = time.time()
+                if dis_interval != 0 and step % dis_interval == 0 and step != 0:       # nothing trains at step 0
+                    for _ in range(self.dis_sub_iter):
+                        ct, _ = ct_src.next()
+                        mr, _ = mr_src.next()
+                        self.d_step(to_device(mr, dev), to_device(ct, dev), dropout)
+                if gen_interval != 0 and step % gen_interval == 0 and step != 0:
+                    for _ in range(self.gen_sub_iter):
+                        ct, _ = ct_src.next()
+                        self.g_step(to_device(ct, dev), dropout)
+                if step % upd_interval == 0 and step != 0:
+                    self.dis_sub_iter += dis_inc
+                    self.gen_sub_iter += gen_inc
+                    self._refresh_weight_decay()
+                if step % display_step == 0:
+                    logging.info("Training step %s epoch %s finished, %.3f s" % (step, epoch, time.time() - start))
+                if step % ckpt_space == 0 and step != 0:
+                    _save(rt.state_dict(), save_path, global_step=self.global_step)
+                    _save(rt.state_dict(), os.path.join(output_path, "latest"))
+                    lr = self.dis_optimizer.get_lr() * decay
+                    self.dis_optimizer.set_lr(lr)
+                    self.gen_optimizer.set_lr(lr)
+        return save_path

@@ -543,6 +543,14 @@ confusion_kernel(const float* __restrict__ logits, const float* __restrict__ y, 
 }
 
 __global__ void __launch_bounds__(256)
+one_hot_kernel(const long long* __restrict__ labels, float* __restrict__ out, long long P, int C) {
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += (long long)gridDim.x * 256) {
+    long long l = labels[p];
+    for (int c = 0; c < C; ++c) out[p * C + c] = (l == c) ? 1.f : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256)
 fc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out, int F) {
   __shared__ float s[8];
   const float* row = x + (long long)blockIdx.x * F;
@@ -614,9 +622,10 @@ l2_loss_kernel(const float* __restrict__ w, long long n, double* out) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
-            const int* __restrict__ chunk_seg, const float* __restrict__ seg_wd, float lr_t, float b1, float b2, float eps,
-            float gscale) {
+            const int* __restrict__ chunk_seg, const float* __restrict__ seg_wd, const double* __restrict__ state, float b1,
+            float b2, float eps, float gscale) {
   const float wd = seg_wd[chunk_seg[blockIdx.x]];
+  const float lr_t = (float)state[3];
   long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   float4 t = reinterpret_cast<float4*>(theta)[i];
   float4 g = __ldg(reinterpret_cast<const float4*>(grad) + i);
@@ -639,8 +648,9 @@ adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __
 __global__ void __launch_bounds__(256)
 rmsprop_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ ms, float* __restrict__ mom,
                const int* __restrict__ chunk_seg, const float* __restrict__ seg_wd, const float* __restrict__ seg_clip,
-               float lr, float decay, float momentum, float eps, float gscale) {
+               const float* __restrict__ lr_ptr, float decay, float momentum, float eps, float gscale) {
   const int seg = chunk_seg[blockIdx.x];
+  const float lr = *lr_ptr;
   const float wd = seg_wd[seg];
   const float clip = seg_clip ? seg_clip[seg] : 0.f;
   long long i = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -661,6 +671,14 @@ rmsprop_kernel(float* __restrict__ theta, const float* __restrict__ grad, float*
   reinterpret_cast<float4*>(theta)[i] = t;
   reinterpret_cast<float4*>(ms)[i] = s;
   reinterpret_cast<float4*>(mom)[i] = mo;
+}
+
+// state = [beta1^t, beta2^t, lr, lr_t]: advance t and refresh lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t) (TF Adam)
+__global__ void adam_advance_kernel(double* state, double b1, double b2) {
+  double p1 = state[0] * b1, p2 = state[1] * b2;
+  state[0] = p1;
+  state[1] = p2;
+  state[3] = state[2] * sqrt(1.0 - p2) / (1.0 - p1);
 }
 
 __global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ p, float v, long long n) {
@@ -879,6 +897,13 @@ extern "C" int pnp_confusion(const float* logits, const float* y, long long P, i
   return PNP_OK;
 }
 
+extern "C" int pnp_one_hot(const long long* labels, float* out, long long P, int C, void* stream) {
+  if (!labels || !out || P <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
+  one_hot_kernel<<<grid_for(P, 256 * 2), 256, 0, S_>>>(labels, out, P, C);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
 extern "C" int pnp_fc_fwd(const float* x, const float* w, float* out, int B, int F, void* stream) {
   if (!x || !w || !out || B <= 0 || F <= 0) return PNP_ERR_BAD_ARG;
   fc_fwd_kernel<<<B, 256, 0, S_>>>(x, w, out, F);
@@ -907,19 +932,27 @@ extern "C" int pnp_l2_loss_acc(const float* w, long long n, double* out, void* s
   return PNP_OK;
 }
 
+extern "C" int pnp_adam_advance(double* state, float beta1, float beta2, void* stream) {
+  if (!state) return PNP_ERR_BAD_ARG;
+  adam_advance_kernel<<<1, 1, 0, S_>>>(state, (double)beta1, (double)beta2);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
 extern "C" int pnp_adam_step(float* theta, const float* grad, float* m, float* v, long long n, const int* chunk_seg,
-                             const float* seg_wd, float lr_t, float beta1, float beta2, float eps, float grad_scale, void* stream) {
-  if (!theta || !grad || !m || !v || !chunk_seg || !seg_wd || n <= 0 || (n % 1024) != 0) return PNP_ERR_BAD_ARG;
-  adam_kernel<<<(unsigned)(n / 1024), 256, 0, S_>>>(theta, grad, m, v, chunk_seg, seg_wd, lr_t, beta1, beta2, eps, grad_scale);
+                             const float* seg_wd, const double* state, float beta1, float beta2, float eps, float grad_scale,
+                             void* stream) {
+  if (!theta || !grad || !m || !v || !chunk_seg || !seg_wd || !state || n <= 0 || (n % 1024) != 0) return PNP_ERR_BAD_ARG;
+  adam_kernel<<<(unsigned)(n / 1024), 256, 0, S_>>>(theta, grad, m, v, chunk_seg, seg_wd, state, beta1, beta2, eps, grad_scale);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
 
 extern "C" int pnp_rmsprop_step(float* theta, const float* grad, float* ms, float* mom, long long n, const int* chunk_seg,
-                                const float* seg_wd, const float* seg_clip, float lr, float decay, float momentum, float eps,
-                                float grad_scale, void* stream) {
-  if (!theta || !grad || !ms || !mom || !chunk_seg || !seg_wd || n <= 0 || (n % 1024) != 0) return PNP_ERR_BAD_ARG;
-  rmsprop_kernel<<<(unsigned)(n / 1024), 256, 0, S_>>>(theta, grad, ms, mom, chunk_seg, seg_wd, seg_clip, lr, decay, momentum, eps,
+                                const float* seg_wd, const float* seg_clip, const float* lr_ptr, float decay, float momentum,
+                                float eps, float grad_scale, void* stream) {
+  if (!theta || !grad || !ms || !mom || !chunk_seg || !seg_wd || !lr_ptr || n <= 0 || (n % 1024) != 0) return PNP_ERR_BAD_ARG;
+  rmsprop_kernel<<<(unsigned)(n / 1024), 256, 0, S_>>>(theta, grad, ms, mom, chunk_seg, seg_wd, seg_clip, lr_ptr, decay, momentum, eps,
                                                       grad_scale);
   PNP_LAUNCH_CHECK();
   return PNP_OK;

@@ -1,0 +1,612 @@
+"""Host-side operators of the B200 hot path: thin torch.autograd.Function wrappers whose forward and
+backward are sequences of launches into libpnp_b200.so (include/pnp_b200.h).  PyTorch supplies device
+memory, the stream and the autograd tape; every arithmetic kernel is ours.  NHWC fp32 activations,
+HWIO weights, exactly like the reference (layers.py / ops.py).
+
+Trainable variables receive their gradients by direct accumulation into `var.grad` (normally a view
+of a flat gradient arena, see optim.py); the Functions return None for them so autograd adds nothing.
+"""
+import ctypes
+import math
+import torch
+
+from . import _C
+from . import runtime as rt
+from ._C import call, ptr, ConvGeom, DropCfg
+
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+
+# fuse BN batch statistics into the tcgen05 conv epilogue (otherwise a separate pnp_bn_stats pass)
+FUSE_BN_STATS = True
+# bench.py sets this to a list to time every tcgen05 launch with CUDA events: (start, end, flops, tag)
+PROFILE = None
+
+
+def _tc_launch(tag, flops, *args):
+    if PROFILE is None:
+        call("pnp_conv2d_tc_fwd", *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call("pnp_conv2d_tc_fwd", *args)
+    e1.record()
+    PROFILE.append((e0, e1, flops, tag))
+
+
+def same_pad(n, k, s, d=1):
+    """TF 'SAME' (before, after) padding -- asymmetric for strided convs."""
+    out = -(-n // s)
+    total = max((out - 1) * s + (k - 1) * d + 1 - n, 0)
+    return total // 2, total - total // 2
+
+
+def _zeros_f64(n, dev):
+    t = torch.empty(n, dtype=torch.float64, device=dev)
+    call("pnp_fill", ptr(t), 0.0, 2 * n, rt.stream())
+    return t
+
+
+def _drop_cfg(keep_prob):
+    """-> (ctypes DropCfg or None, (stream_id, keep) or None)"""
+    if keep_prob is None or keep_prob >= 1.0:
+        return None, None
+    sid = rt.rng.next_stream()
+    return DropCfg(rt.rng.seed_ptr(), sid, float(keep_prob)), (sid, float(keep_prob))
+
+
+def _drop_from(info):
+    if info is None:
+        return None
+    return DropCfg(rt.rng.seed_ptr(), info[0], info[1])
+
+
+def _byref(x):
+    return None if x is None else ctypes.byref(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# low-level convolution launches
+# ------------------------------------------------------------------------------------------------
+def _tc_mode():
+    b = rt.conv_backend()
+    if b == "simt" or not rt.tc_available():
+        return 0
+    return 1 if b == "tc1" else 3
+
+
+def _tc_ok(cin, cout, stride, wo):
+    return stride == 1 and cin % 64 == 0 and cout % 64 == 0 and (wo < 128 or wo % 128 == 0)
+
+
+def split_bf16(x, nterms):
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if nterms == 3 else None
+    call("pnp_split_bf16", ptr(x), ptr(hi), ptr(lo), x.numel(), rt.stream())
+    return hi, lo
+
+
+def _weight_planes(W, for_dgrad, nterms):
+    ver = getattr(W, "pnp_version", None)
+    cache = W.__dict__.setdefault("_pnp_planes", {})
+    key = (for_dgrad, nterms)
+    hit = cache.get(key)
+    if hit is not None and ver is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    kh, kw, cin, cout = W.shape
+    hi = torch.empty(kh * kw * cin * cout, dtype=torch.bfloat16, device=W.device)
+    lo = torch.empty_like(hi) if nterms == 3 else None
+    call("pnp_split_weight_bf16", ptr(W), ptr(hi), ptr(lo), kh, kw, cin, cout, 1 if for_dgrad else 0, rt.stream())
+    cache[key] = (ver, hi, lo)
+    return hi, lo
+
+
+def _weight_T(W):
+    ver = getattr(W, "pnp_version", None)
+    hit = W.__dict__.get("_pnp_wT")
+    if hit is not None and ver is not None and hit[0] == ver:
+        return hit[1]
+    kh, kw, cin, cout = W.shape
+    wT = torch.empty(kh, kw, cout, cin, dtype=W.dtype, device=W.device)
+    call("pnp_weight_transpose", ptr(W), ptr(wT), kh * kw, cin, cout, rt.stream())
+    W.__dict__["_pnp_wT"] = (ver, wT)
+    return wT
+
+
+def conv_fwd_raw(xp, W, geom, drop=None, stats=None):
+    """z = conv(xp, W) [* dropout]; xp already mirror-padded if needed.  stats=(sum,sumsq) f64 buffers
+    are filled only when the tcgen05 path can fuse them; returns (z, stats_done)."""
+    z = torch.empty(geom.B, geom.Ho, geom.Wo, geom.Cout, dtype=torch.float32, device=xp.device)
+    nt = _tc_mode()
+    if nt and _tc_ok(geom.Cin, geom.Cout, geom.stride, geom.Wo):
+        hi, lo = split_bf16(xp, nt)
+        whi, wlo = _weight_planes(W, False, nt)
+        fuse = stats is not None and FUSE_BN_STATS
+        flops = 2.0 * geom.B * geom.Ho * geom.Wo * geom.Cout * geom.kh * geom.kw * geom.Cin
+        _tc_launch("fwd", flops, ptr(hi), ptr(lo), ptr(whi), ptr(wlo), ptr(z), ctypes.byref(geom), nt, _byref(drop), 0,
+                   ptr(stats[0]) if fuse else None, ptr(stats[1]) if fuse else None, rt.stream())
+        return z, fuse
+    call("pnp_conv2d_fwd", ptr(xp), ptr(W), ptr(z), ctypes.byref(geom), _byref(drop), 0, rt.stream())
+    return z, False
+
+
+def conv_dgrad_raw(dz, W, geom, into=None):
+    """dx[B,H,W,Cin] = conv^T(dz, W); if `into` is given the result is accumulated into it."""
+    acc = 1 if into is not None else 0
+    dx = into if into is not None else torch.empty(geom.B, geom.H, geom.W, geom.Cin, dtype=torch.float32, device=dz.device)
+    nt = _tc_mode()
+    if nt and _tc_ok(geom.Cout, geom.Cin, geom.stride, geom.W):
+        g2 = ConvGeom(geom.B, geom.Ho, geom.Wo, geom.Cout, geom.H, geom.W, geom.Cin, geom.kh, geom.kw, 1, geom.dil,
+                      (geom.kh - 1) * geom.dil - geom.pad_t, (geom.kw - 1) * geom.dil - geom.pad_l)
+        hi, lo = split_bf16(dz, nt)
+        whi, wlo = _weight_planes(W, True, nt)
+        flops = 2.0 * geom.B * geom.Ho * geom.Wo * geom.Cout * geom.kh * geom.kw * geom.Cin
+        _tc_launch("dgrad", flops, ptr(hi), ptr(lo), ptr(whi), ptr(wlo), ptr(dx), ctypes.byref(g2), nt, None, acc, None, None,
+                   rt.stream())
+        return dx
+    call("pnp_conv2d_dgrad", ptr(dz), ptr(_weight_T(W)), ptr(dx), ctypes.byref(geom), acc, rt.stream())
+    return dx
+
+
+def conv_wgrad_raw(xp, dz, W, geom):
+    if W.grad is None:
+        W.grad = torch.empty_like(W)
+        call("pnp_fill", ptr(W.grad), 0.0, W.numel(), rt.stream())
+    call("pnp_conv2d_wgrad", ptr(xp), ptr(dz), ptr(W.grad), ctypes.byref(geom), rt.stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# one fused layer: [mirror pad] -> conv -> dropout -> [BN] -> [+skip] -> [act]
+# ------------------------------------------------------------------------------------------------
+class BNVars:
+    """handles of one tf.contrib.layers.batch_norm scope (layers.py:95-100)"""
+    __slots__ = ("gamma", "beta", "moving_mean", "moving_var")
+
+    def __init__(self, gamma, beta, moving_mean, moving_var):
+        self.gamma, self.beta, self.moving_mean, self.moving_var = gamma, beta, moving_mean, moving_var
+
+
+class LayerCfg:
+    __slots__ = ("stride", "dil", "padding", "keep_prob", "bn", "bn_training", "act", "skip_off")
+
+    def __init__(self, stride=1, dil=1, padding="SAME", keep_prob=1.0, bn=None, bn_training=True, act=ACT_NONE, skip_off=0):
+        self.stride, self.dil, self.padding, self.keep_prob = stride, dil, padding, keep_prob
+        self.bn, self.bn_training, self.act, self.skip_off = bn, bool(bn_training), act, skip_off
+
+
+def _geometry(x_shape, w_shape, cfg):
+    B, H, Wd, C = x_shape
+    kh, kw, cin, cout = w_shape
+    if C != cin:
+        raise ValueError("conv: input has %d channels, filter expects %d" % (C, cin))
+    p = 0
+    if cfg.padding == "SYMMETRIC":
+        p = kh // 2
+        H, Wd = H + 2 * p, Wd + 2 * p
+        pt = pl = 0
+        Ho = (H - ((kh - 1) * cfg.dil + 1)) // cfg.stride + 1
+        Wo = (Wd - ((kw - 1) * cfg.dil + 1)) // cfg.stride + 1
+    elif cfg.padding == "SAME":
+        pt, _ = same_pad(H, kh, cfg.stride, cfg.dil)
+        pl, _ = same_pad(Wd, kw, cfg.stride, cfg.dil)
+        Ho, Wo = -(-H // cfg.stride), -(-Wd // cfg.stride)
+    elif cfg.padding == "VALID":
+        pt = pl = 0
+        Ho = (H - ((kh - 1) * cfg.dil + 1)) // cfg.stride + 1
+        Wo = (Wd - ((kw - 1) * cfg.dil + 1)) // cfg.stride + 1
+    else:
+        # the reference leaves conv_2d unbound for unknown strings (layers.py:17-25) -> UnboundLocalError
+        raise UnboundLocalError("local variable 'conv_2d' referenced before assignment (padding=%r)" % (cfg.padding,))
+    return p, ConvGeom(B, H, Wd, cin, Ho, Wo, cout, kh, kw, cfg.stride, cfg.dil, pt, pl)
+
+
+def layer_forward(x, W, cfg, skip=None, save=True):
+    """returns (y, saved) -- `saved` is None when save is False (inference / frozen sub-graph)"""
+    x = x.contiguous()
+    dev = x.device
+    p, geom = _geometry(x.shape, W.shape, cfg)
+    if p:
+        xp = torch.empty(geom.B, geom.H, geom.W, geom.Cin, dtype=torch.float32, device=dev)
+        call("pnp_mirror_pad_fwd", ptr(x), ptr(xp), x.shape[0], x.shape[1], x.shape[2], x.shape[3], p, rt.stream())
+    else:
+        xp = x
+    drop, drop_info = _drop_cfg(cfg.keep_prob)
+    C = geom.Cout
+    M = geom.B * geom.Ho * geom.Wo
+    bn = cfg.bn
+    stats = None
+    if bn is not None and cfg.bn_training:
+        s = _zeros_f64(2 * C, dev)
+        stats = (s[:C], s[C:])
+    z, stats_done = conv_fwd_raw(xp, W, geom, drop, stats)
+    mean = invstd = None
+    if bn is not None:
+        vec = torch.empty(4, C, dtype=torch.float32, device=dev)
+        scale, shift, mean, invstd = vec[0], vec[1], vec[2], vec[3]
+        if cfg.bn_training and not stats_done:
+            call("pnp_bn_stats", ptr(z), M, C, ptr(stats[0]), ptr(stats[1]), rt.stream())
+        call("pnp_bn_finalize", ptr(stats[0]) if stats else None, ptr(stats[1]) if stats else None, M, C, ptr(bn.gamma),
+             ptr(bn.beta), ptr(bn.moving_mean), ptr(bn.moving_var), 1 if cfg.bn_training else 0, ptr(scale), ptr(shift),
+             ptr(mean), ptr(invstd), rt.stream())
+        if cfg.bn_training:
+            bn.moving_mean.pnp_version = getattr(bn.moving_mean, "pnp_version", 0) + 1
+        y = torch.empty_like(z)
+        cs = skip.shape[-1] if skip is not None else 0
+        call("pnp_bn_act_apply", ptr(z), ptr(scale), ptr(shift), ptr(skip), cs, cfg.skip_off, cfg.act, ptr(y), M, C, rt.stream())
+    elif cfg.act != ACT_NONE or skip is not None:
+        y = torch.empty_like(z)
+        cs = skip.shape[-1] if skip is not None else 0
+        call("pnp_bn_act_apply", ptr(z), None, None, ptr(skip), cs, cfg.skip_off, cfg.act, ptr(y), M, C, rt.stream())
+    else:
+        y = z
+    if not save:
+        return y, None
+    saved = {
+        "cfg": cfg, "geom": geom, "p": p, "x_shape": tuple(x.shape), "xp": xp, "W": W, "drop": drop_info,
+        "z": z if (bn is not None) else None, "y": y if cfg.act != ACT_NONE else None,
+        "mean": mean, "invstd": invstd, "skip_c": skip.shape[-1] if skip is not None else 0,
+    }
+    return y, saved
+
+
+def layer_backward(sv, dy, need_dx=True, dx_into=None, want_dskip=False):
+    """returns (dx or None, dskip or None).  Parameter gradients are accumulated into var.grad."""
+    cfg, geom, W = sv["cfg"], sv["geom"], sv["W"]
+    dy = dy.contiguous()
+    dev = dy.device
+    C = geom.Cout
+    M = geom.B * geom.Ho * geom.Wo
+    bn = cfg.bn
+    drop = _drop_from(sv["drop"])
+    y = sv["y"]
+    g_owned = False
+    if bn is not None:
+        need_dparam = bn.gamma.requires_grad or bn.beta.requires_grad
+        coef = None
+        if cfg.bn_training or need_dparam:
+            g = torch.empty(dy.shape, dtype=torch.float32, device=dev)
+            g_owned = True
+            sums = _zeros_f64(2 * C, dev)
+            call("pnp_bn_bwd_reduce", ptr(dy), ptr(y), ptr(sv["z"]), ptr(sv["mean"]), ptr(sv["invstd"]), cfg.act, ptr(g),
+                 ptr(sums[:C]), ptr(sums[C:]), M, C, rt.stream())
+            coef = torch.empty(2 * C, dtype=torch.float32, device=dev)
+            dgamma = dbeta = None
+            if bn.gamma.requires_grad:
+                dgamma = _grad_slot(bn.gamma)
+            if bn.beta.requires_grad:
+                dbeta = _grad_slot(bn.beta)
+            call("pnp_bn_bwd_finalize", ptr(sums[:C]), ptr(sums[C:]), M, C, ptr(dgamma), ptr(dbeta), ptr(coef), rt.stream())
+        elif cfg.act != ACT_NONE:
+            g = torch.empty(dy.shape, dtype=torch.float32, device=dev)
+            g_owned = True
+            call("pnp_act_bwd", ptr(dy), ptr(y), cfg.act, ptr(g), dy.numel(), rt.stream())
+        else:
+            g = dy
+        dz = torch.empty(dy.shape, dtype=torch.float32, device=dev)
+        call("pnp_bn_bwd_apply", ptr(g), ptr(sv["z"]), ptr(sv["mean"]), ptr(sv["invstd"]), ptr(bn.gamma), ptr(coef),
+             1 if cfg.bn_training else 0, _byref(drop), ptr(dz), M, C, rt.stream())
+    else:
+        if cfg.act != ACT_NONE:
+            g = torch.empty(dy.shape, dtype=torch.float32, device=dev)
+            g_owned = True
+            call("pnp_act_bwd", ptr(dy), ptr(y), cfg.act, ptr(g), dy.numel(), rt.stream())
+        else:
+            g = dy
+        if drop is not None:
+            dz = torch.empty(dy.shape, dtype=torch.float32, device=dev)
+            call("pnp_dropout_apply", ptr(g), ptr(dz), g.numel(), ctypes.byref(drop), rt.stream())
+        else:
+            dz = g
+    dskip = None
+    if want_dskip and sv["skip_c"]:
+        cs = sv["skip_c"]
+        if cs == C and g_owned:
+            dskip = g            # safe to hand out / accumulate into: nothing reads g after this point
+        else:
+            dskip = torch.empty(dy.shape[:-1] + (cs,), dtype=torch.float32, device=dev)
+            call("pnp_channel_slice", ptr(g), C, cfg.skip_off if cs != C else 0, cs, ptr(dskip), M, 0, rt.stream())
+    if W.requires_grad:
+        conv_wgrad_raw(sv["xp"], dz, W, geom)
+    dx = None
+    if need_dx:
+        if sv["p"]:
+            dxp = conv_dgrad_raw(dz, W, geom)
+            B, H, Wd, Cin = sv["x_shape"]
+            dx = torch.empty(sv["x_shape"], dtype=torch.float32, device=dev)
+            call("pnp_mirror_pad_bwd", ptr(dxp), ptr(dx), B, H, Wd, Cin, sv["p"], rt.stream())
+            if dx_into is not None:
+                raise NotImplementedError("accumulating dgrad through a SYMMETRIC pad is not used by the hot path")
+        else:
+            dx = conv_dgrad_raw(dz, W, geom, into=dx_into)
+    return dx, dskip
+
+
+def _grad_slot(v):
+    if v.grad is None:
+        v.grad = torch.empty_like(v)
+        call("pnp_fill", ptr(v.grad), 0.0, v.numel(), rt.stream())
+    return v.grad
+
+
+def _bn_params(cfg):
+    return [] if cfg.bn is None else [cfg.bn.gamma, cfg.bn.beta]
+
+
+class _ConvLayerFn(torch.autograd.Function):
+    """conv2d / conv_bn_2d / conv_bn_relu2d / dilate_* of layers.py as ONE fused op (optionally + skip)."""
+
+    @staticmethod
+    def forward(ctx, x, skip, cfg, W, *bnp):
+        save = torch.is_grad_enabled() and (x.requires_grad or W.requires_grad or any(p.requires_grad for p in bnp) or
+                                            (skip is not None and skip.requires_grad))
+        y, sv = layer_forward(x, W, cfg, skip, save)
+        ctx.sv = sv
+        ctx.has_skip = skip is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        sv = ctx.sv
+        need_dx = ctx.needs_input_grad[0]
+        want_ds = ctx.has_skip and ctx.needs_input_grad[1]
+        dx, dskip = layer_backward(sv, dy, need_dx, None, want_ds)
+        ctx.sv = None
+        return (dx, dskip, None, None) + (None,) * (len(ctx.needs_input_grad) - 4)
+
+
+def conv_layer(x, W, cfg, skip=None):
+    return _ConvLayerFn.apply(x, skip, cfg, W, *_bn_params(cfg))
+
+
+class _ResBlockFn(torch.autograd.Function):
+    """residual_block / DR_block of layers.py:145-189: act(x_s + BN(conv(act(BN(conv(x)))))) with the
+    skip-gradient and the first conv's dgrad merged by the dgrad epilogue (no separate add kernel)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg1, cfg2, W1, W2, *bnp):
+        save = torch.is_grad_enabled() and (x.requires_grad or W1.requires_grad or W2.requires_grad or
+                                            any(p.requires_grad for p in bnp))
+        h, s1 = layer_forward(x, W1, cfg1, None, save)
+        y, s2 = layer_forward(h, W2, cfg2, x, save)
+        ctx.s1, ctx.s2 = s1, s2
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        need_dx = ctx.needs_input_grad[0]
+        dh, dskip = layer_backward(ctx.s2, dy, True, None, need_dx)
+        dx, _ = layer_backward(ctx.s1, dh, need_dx, dskip if need_dx else None, False)
+        ctx.s1 = ctx.s2 = None
+        return (dx, None, None, None, None) + (None,) * (len(ctx.needs_input_grad) - 5)
+
+
+def res_block(x, W1, W2, cfg1, cfg2):
+    return _ResBlockFn.apply(x, cfg1, cfg2, W1, W2, *(_bn_params(cfg1) + _bn_params(cfg2)))
+
+
+# ------------------------------------------------------------------------------------------------
+# pooling / phase shift / discriminator input
+# ------------------------------------------------------------------------------------------------
+class _MaxPool2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        B, H, W, C = x.shape
+        y = torch.empty(B, H // 2, W // 2, C, dtype=x.dtype, device=x.device)
+        call("pnp_maxpool2_fwd", ptr(x), ptr(y), B, H, W, C, rt.stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        B, H, W, C = x.shape
+        dx = torch.empty_like(x)
+        call("pnp_maxpool2_bwd", ptr(x), ptr(dy.contiguous()), ptr(dx), B, H, W, C, rt.stream())
+        return dx
+
+
+def max_pool2(x):
+    return _MaxPool2Fn.apply(x)
+
+
+class _PhaseShiftFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, r, G, order_b1):
+        X = X.contiguous()
+        B, a, b, C = X.shape
+        if C != G * r * r:
+            raise ValueError("PS: %d channels cannot be split into %d groups of %d" % (C, G, r * r))
+        out = torch.empty(B, a * r, b * r, G, dtype=X.dtype, device=X.device)
+        call("pnp_phase_shift_fwd", ptr(X), ptr(out), B, a, b, G, r, G, 0, 1, order_b1, rt.stream())
+        ctx.meta = (B, a, b, G, r, order_b1)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, a, b, G, r, o = ctx.meta
+        dX = torch.empty(B, a, b, G * r * r, dtype=dout.dtype, device=dout.device)
+        call("pnp_phase_shift_bwd", ptr(dout.contiguous()), ptr(dX), B, a, b, G, r, G, 0, 1, o, rt.stream())
+        return dX, None, None, None
+
+
+def phase_shift(X, r, n_channel, batch_size):
+    return _PhaseShiftFn.apply(X, r, n_channel, 1 if batch_size == 1 else 0)
+
+
+class _DiscInputFn(torch.autograd.Function):
+    """adversarial.py:325-335 in one gather: [PS(c4,2) x3 | PS(c6,4) | PS(b7,8) | PS(c9,8) | logits | argmax]"""
+
+    @staticmethod
+    def forward(ctx, c4, c6, b7, c9, logits, r, order_b1):
+        srcs = [c4.contiguous(), c6.contiguous(), b7.contiguous(), c9.contiguous()]
+        logits = logits.contiguous()
+        B, H, W, NC = logits.shape
+        plan = []
+        off = 0
+        for t, ntile in zip(srcs, (3, 1, 1, 1)):
+            G = t.shape[-1] // (r * r)
+            plan.append((t.shape[1], t.shape[2], G, off, ntile))
+            off += G * ntile
+        ctot = off + NC + 1
+        out = torch.empty(B, H, W, ctot, dtype=logits.dtype, device=logits.device)
+        for t, (a, b, G, coff, ntile) in zip(srcs, plan):
+            call("pnp_phase_shift_fwd", ptr(t), ptr(out), B, a, b, G, r, ctot, coff, ntile, order_b1, rt.stream())
+        call("pnp_logits_argmax_concat", ptr(logits), ptr(out), B * H * W, NC, ctot, off, rt.stream())
+        ctx.meta = (B, H, W, NC, r, order_b1, plan, ctot, off)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, H, W, NC, r, o, plan, ctot, off = ctx.meta
+        dout = dout.contiguous()
+        grads = []
+        for i, (a, b, G, coff, ntile) in enumerate(plan):
+            if ctx.needs_input_grad[i]:
+                dX = torch.empty(B, a, b, G * r * r, dtype=dout.dtype, device=dout.device)
+                call("pnp_phase_shift_bwd", ptr(dout), ptr(dX), B, a, b, G, r, ctot, coff, ntile, o, rt.stream())
+                grads.append(dX)
+            else:
+                grads.append(None)
+        dl = None
+        if ctx.needs_input_grad[4]:
+            dl = torch.empty(B, H, W, NC, dtype=dout.dtype, device=dout.device)
+            call("pnp_channel_slice", ptr(dout), ctot, off, NC, ptr(dl), B * H * W, 0, rt.stream())
+        return tuple(grads) + (dl, None, None)
+
+
+def disc_input(c4, c6, b7, c9, logits, batch_size, r=8):
+    return _DiscInputFn.apply(c4, c6, b7, c9, logits, r, 1 if batch_size == 1 else 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# losses / metrics
+# ------------------------------------------------------------------------------------------------
+class _SegLossFn(torch.autograd.Function):
+    """(weighted CE, soft Dice) of source_segmenter.py:241-273 from one reduction pass."""
+
+    @staticmethod
+    def forward(ctx, logits, y):
+        logits, y = logits.contiguous(), y.contiguous()
+        C = logits.shape[-1]
+        P = logits.numel() // C
+        acc = _zeros_f64(4 * C, logits.device)
+        call("pnp_segloss_reduce", ptr(logits), ptr(y), P, C, ptr(acc), rt.stream())
+        out = torch.empty(2, dtype=torch.float32, device=logits.device)
+        coef = torch.empty(3 * C, dtype=torch.float32, device=logits.device)
+        call("pnp_segloss_finalize", ptr(acc), P, C, ptr(out), ptr(coef), rt.stream())
+        ctx.save_for_backward(logits, y, coef)
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g_wce, g_dice):
+        logits, y, coef = ctx.saved_tensors
+        C = logits.shape[-1]
+        P = logits.numel() // C
+        dl = torch.empty_like(logits)
+        call("pnp_segloss_bwd", ptr(logits), ptr(y), ptr(coef), ptr(g_wce.contiguous()), ptr(g_dice.contiguous()), ptr(dl), P, C,
+             rt.stream())
+        return dl, None
+
+
+def seg_losses(logits, y):
+    return _SegLossFn.apply(logits, y)
+
+
+def pixel_softmax2(logits):
+    logits = logits.contiguous()
+    C = logits.shape[-1]
+    out = torch.empty_like(logits)
+    call("pnp_pixel_softmax2", ptr(logits), ptr(out), logits.numel() // C, C, rt.stream())
+    return out
+
+
+def one_hot(labels, num_cls):
+    """device-side lib._label_decomp (lib.py:75-92): int64 [..] -> fp32 [.., num_cls]"""
+    labels = labels.contiguous().to(torch.int64)
+    out = torch.empty(labels.shape + (num_cls,), dtype=torch.float32, device=labels.device)
+    call("pnp_one_hot", ptr(labels), ptr(out), labels.numel(), num_cls, rt.stream())
+    return out
+
+
+def confusion_counts(logits, y):
+    """[C,C] int64 confusion matrix (rows = truth) of argmax(logits) vs one-hot y (lib.py:96-110)."""
+    logits, y = logits.contiguous(), y.contiguous()
+    C = logits.shape[-1]
+    cnt = torch.empty(C * C, dtype=torch.int64, device=logits.device)
+    call("pnp_fill", ptr(cnt), 0.0, 2 * C * C, rt.stream())
+    call("pnp_confusion", ptr(logits), ptr(y), logits.numel() // C, C, ptr(cnt), rt.stream())
+    return cnt.view(C, C)
+
+
+class _FCFn(torch.autograd.Function):
+    """tf.matmul([B,F],[F,1]) (adversarial.py:397,440)"""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x = x.contiguous()
+        B, F = x.shape
+        out = torch.empty(B, 1, dtype=x.dtype, device=x.device)
+        call("pnp_fc_fwd", ptr(x), ptr(w), ptr(out), B, F, rt.stream())
+        ctx.save_for_backward(x)
+        ctx.w = w
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        w = ctx.w
+        B, F = x.shape
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = _grad_slot(w) if w.requires_grad else None
+        if dx is not None or dw is not None:
+            call("pnp_fc_bwd", ptr(x), ptr(w), ptr(dout.contiguous()), ptr(dx), ptr(dw), B, F, rt.stream())
+        return dx, None
+
+
+def fc(x, w):
+    return _FCFn.apply(x, w)
+
+
+class _MeanComboFn(torch.autograd.Function):
+    """ca*mean(a) + cb*mean(b): the WGAN loss terms of adversarial.py:455-459"""
+
+    @staticmethod
+    def forward(ctx, a, ca, b, cb):
+        a = a.contiguous()
+        n = a.numel()
+        out = torch.empty(1, dtype=a.dtype, device=a.device)
+        call("pnp_mean_combo", ptr(a), float(ca), ptr(b.contiguous()) if b is not None else None, float(cb), n, ptr(out), rt.stream())
+        ctx.meta = (ca, cb, n, a.shape, b is not None)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        ca, cb, n, shape, has_b = ctx.meta
+        def mk(c):
+            t = torch.empty(shape, dtype=g.dtype, device=g.device)
+            _bcast(t, g, float(c) / n)
+            return t
+        da = mk(ca) if ctx.needs_input_grad[0] else None
+        db = mk(cb) if (has_b and ctx.needs_input_grad[2]) else None
+        return da, None, db, None
+
+
+def _bcast(t, g, c):
+    """t[:] = c * g for a device scalar g: the FC backward kernel with B = 1 (dx[0, f] = dout[0] * w[f])."""
+    F = t.numel()
+    w = torch.empty(F, dtype=t.dtype, device=t.device)
+    call("pnp_fill", ptr(w), float(c), F, rt.stream())
+    call("pnp_fc_bwd", ptr(w), ptr(w), ptr(g.reshape(1).contiguous()), ptr(t), None, 1, F, rt.stream())
+
+
+def mean_combo(a, ca, b=None, cb=0.0):
+    return _MeanComboFn.apply(a, ca, b, cb)
+
+
+def l2_loss_sum(tensors):
+    """sum_i tf.nn.l2_loss(w_i) as a python float-on-device tensor (monitoring only)."""
+    dev = tensors[0].device
+    acc = _zeros_f64(1, dev)
+    for t in tensors:
+        call("pnp_l2_loss_acc", ptr(t), t.numel(), ptr(acc), rt.stream())
+    return acc

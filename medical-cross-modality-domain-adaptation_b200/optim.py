@@ -1,0 +1,113 @@
+"""Flat parameter / gradient arenas and the fused optimizers of the hot path.
+
+All variables of one optimizer live in ONE contiguous fp32 arena (each padded to 1024 floats), their
+gradients in a second arena of the same layout; `var.data` / `var.grad` are views.  One kernel launch
+updates everything (TF Adam, source_segmenter.py:378; TF RMSProp + WGAN weight clip,
+adversarial.py:643-654), folding in the L2-regulariser gradient (wd * theta) and the 1/N data-parallel
+average; one NCCL all-reduce over the gradient arena is all the communication DP needs (parallel.py).
+"""
+import torch
+
+from . import runtime as rt
+from ._C import call, ptr
+
+CHUNK = 1024
+
+
+class Arena:
+    def __init__(self, variables):
+        variables = list(variables)
+        if not variables:
+            raise ValueError("empty variable list")
+        dev = variables[0].device
+        self.vars = variables
+        self.offsets = []
+        off = 0
+        seg_of_chunk = []
+        for i, v in enumerate(variables):
+            if getattr(v, "_pnp_arena", None) is not None:
+                raise ValueError("variable %s already belongs to an arena" % getattr(v, "pnp_name", "?"))
+            n = v.numel()
+            padded = -(-n // CHUNK) * CHUNK
+            self.offsets.append((off, n))
+            seg_of_chunk += [i] * (padded // CHUNK)
+            off += padded
+        self.total = off
+        self.theta = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.chunk_seg = torch.tensor(seg_of_chunk, dtype=torch.int32, device=dev)
+        with torch.no_grad():
+            for v, (o, n) in zip(variables, self.offsets):
+                view = self.theta[o:o + n].view(v.shape)
+                view.copy_(v)
+                v.data = view
+                v.grad = self.grad[o:o + n].view(v.shape)
+                v._pnp_arena = self
+
+    def zero_grad(self):
+        call("pnp_fill", ptr(self.grad), 0.0, self.total, rt.stream())
+
+    def bump_versions(self):
+        for v in self.vars:
+            v.pnp_version = getattr(v, "pnp_version", 0) + 1
+
+    def seg_table(self, values):
+        return torch.tensor([float(x) for x in values], dtype=torch.float32, device=self.theta.device)
+
+
+class Adam:
+    """tf.train.AdamOptimizer(learning_rate, beta1=.9, beta2=.999, epsilon=1e-8) over an Arena."""
+
+    def __init__(self, arena, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=None):
+        self.arena = arena
+        self.b1, self.b2, self.eps = beta1, beta2, eps
+        dev = arena.theta.device
+        self.m = torch.zeros_like(arena.theta)
+        self.v = torch.zeros_like(arena.theta)
+        self.state = torch.tensor([1.0, 1.0, float(lr), 0.0], dtype=torch.float64, device=dev)
+        self.seg_wd = arena.seg_table(weight_decay if weight_decay is not None else [0.0] * len(arena.vars))
+        self.t = 0
+
+    def set_lr(self, lr):
+        self.state[2] = float(lr)
+
+    def get_lr(self):
+        return float(self.state[2].item())
+
+    def step(self, grad_scale=1.0):
+        a = self.arena
+        self.t += 1
+        call("pnp_adam_advance", ptr(self.state), self.b1, self.b2, rt.stream())
+        call("pnp_adam_step", ptr(a.theta), ptr(a.grad), ptr(self.m), ptr(self.v), a.total, ptr(a.chunk_seg), ptr(self.seg_wd),
+             ptr(self.state), self.b1, self.b2, self.eps, float(grad_scale), rt.stream())
+        a.bump_versions()
+
+
+class RMSProp:
+    """tf.train.RMSPropOptimizer(learning_rate, decay=.9, momentum=0, epsilon=1e-10) over an Arena,
+    `ms` initialised to ONE, epsilon inside the sqrt; optional per-variable clip (WGAN clip_op)."""
+
+    def __init__(self, arena, lr=3e-4, decay=0.9, momentum=0.0, eps=1e-10, weight_decay=None, clip=None):
+        self.arena = arena
+        self.decay, self.momentum, self.eps = decay, momentum, eps
+        dev = arena.theta.device
+        self.ms = torch.ones_like(arena.theta)
+        self.mom = torch.zeros_like(arena.theta)
+        self.lr_t = torch.tensor([float(lr)], dtype=torch.float32, device=dev)
+        self.seg_wd = arena.seg_table(weight_decay if weight_decay is not None else [0.0] * len(arena.vars))
+        self.seg_clip = arena.seg_table(clip if clip is not None else [0.0] * len(arena.vars))
+
+    def set_lr(self, lr):
+        self.lr_t[0] = float(lr)
+
+    def get_lr(self):
+        return float(self.lr_t.item())
+
+    def set_weight_decay(self, values):
+        self.seg_wd.copy_(self.arena.seg_table(values))
+
+    def step(self, grad_scale=1.0):
+        a = self.arena
+        call("pnp_rmsprop_step", ptr(a.theta), ptr(a.grad), ptr(self.ms), ptr(self.mom), a.total, ptr(a.chunk_seg), ptr(self.seg_wd),
+             ptr(self.seg_clip), ptr(self.lr_t), self.decay, self.momentum, self.eps, float(grad_scale), rt.stream())
+        a.bump_versions()

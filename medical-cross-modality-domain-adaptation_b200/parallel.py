@@ -1,0 +1,48 @@
+"""Data parallelism for the hot path: one process per GPU, parameters and optimizer state replicated,
+the per-slice minibatch sharded across ranks, and ONE all-reduce (NCCL over NVLink/NVSwitch, or gloo in
+the CPU tests) over the flat gradient arena per optimizer step.  The 1/N average is folded into the
+optimizer kernel (`grad_scale`), so no extra pass touches the gradients.
+
+The reference is single-GPU (train_segmenter.py:20, train_gan.py:18); parity under DP is defined as:
+an N-rank step == the average of N single-GPU reference steps at the per-rank batch (batch-norm
+statistics, the CE class weights and the Dice sums stay per rank -- SURVEY 8e).
+"""
+import os
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from the torchrun environment (RANK / WORLD_SIZE / MASTER_*)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1 or dist.is_initialized():
+        return
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if torch.cuda.is_available():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group(backend=backend)
+
+
+class DataParallel:
+    def __init__(self):
+        self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.world = dist.get_world_size() if self.on else 1
+        self.rank = dist.get_rank() if self.on else 0
+
+    def allreduce(self, grad_arena):
+        """sum-all-reduce the flat gradient arena in place; returns the grad_scale (1/world) to hand to
+        the optimizer kernel."""
+        if self.on:
+            dist.all_reduce(grad_arena, op=dist.ReduceOp.SUM)
+        return 1.0 / self.world
+
+    def broadcast_params(self, theta_arena):
+        """make every replica start from rank 0's parameters"""
+        if self.on:
+            dist.broadcast(theta_arena, src=0)
+
+    def barrier(self):
+        if self.on:
+            dist.barrier()

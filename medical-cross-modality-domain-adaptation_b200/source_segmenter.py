@@ -1,0 +1,222 @@
+"""Source-only dilated-residual segmenter and its Adam training step -- the B200-native counterpart of
+the reference's source_segmenter.py (Full_DRN :48-301, Trainer :303-675), eager instead of TF-1 graph.
+
+Mapping of the reference's graph attributes (evaluated there through sess.run + feed_dict):
+    net.x / net.y / net.keep_prob / net.main_bn / net.adapt_bn  -> arguments of net.forward()/net.losses()
+    net.predicter, net.compact_pred, net.cost, net.regularizer_loss, net.weighted_loss, net.dice_loss,
+    net.dice_eval[_arr], net.confusion_matrix                   -> methods of the same name
+Out of scope: TFRecord queues, TensorBoard summaries, NIfTI test_eval (which does not
+even parse in the reference, source_segmenter.py:611).
+"""
+import logging
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import functional as F
+from . import layers as L
+from . import runtime as rt
+from . import optim
+from . import parallel
+from .data import SyntheticSource, to_device
+from .lib import _label_decomp, _save
+from .networks import FRONT, BACK, SegmenterHalf, SegmenterTail
+
+raw_size = [256, 256, 3]
+volume_size = [256, 256, 3]
+label_size = [256, 256, 1]
+
+
+class Full_DRN(object):
+    """source_segmenter.py:48-273.  cost_kwargs: dice_flag, cross_flag, miu_dice, miu_cross, regularizer."""
+
+    def __init__(self, channels, n_class, batch_size, adapt_module=True, main_trainable=True, adapt_trainable=True,
+                 cost_kwargs={}, **kwargs):
+        rt.reset_default_graph()
+        self.n_class = n_class
+        self.batch_size = batch_size
+        self.main_trainable = main_trainable
+        self.adapt_trainable = adapt_trainable
+        stddev = kwargs.get("stddev", 0.01)                     # layers.py:47
+        counter = [0]
+
+        def anon(gi, blk, kind):
+            # tf.contrib.layers.batch_norm(scope=None): top-level BatchNorm, BatchNorm_1, ... in creation order
+            def one():
+                k = counter[0]
+                counter[0] += 1
+                return "/BatchNorm" if k == 0 else "/BatchNorm_%d" % k
+            return one() if kind == "b" else (one(), one())
+
+        # groups 1-4 use adapt_trainable, 5+ main_trainable (source_segmenter.py:91-161)
+        self.front_a = SegmenterHalf({g: FRONT[g] for g in (1, 2, 3, 4)}, "group_%d", channels, anon, adapt_trainable, stddev)
+        self.front_b = SegmenterHalf({g: FRONT[g] for g in (5, 6)}, "group_%d", self.front_a.out_channels, anon, main_trainable, stddev)
+        self.back = SegmenterHalf(BACK, "group_%d", self.front_b.out_channels, anon, main_trainable, stddev)
+        self.tail = SegmenterTail(n_class, main_trainable, stddev)
+        ws = self.front_a.weights + self.front_b.weights + self.back.weights + self.tail.weights
+        # conv_weights with the reference's quirk (source_segmenter.py:132-135): wr4_4 twice, wr4_3 never
+        wr4_3 = rt.graph.vars["group_4/Variable_2"]
+        wr4_4 = rt.graph.vars["group_4/Variable_3"]
+        self.conv_weights = []
+        for w in ws:
+            if w is wr4_3:
+                continue
+            self.conv_weights.append(w)
+            if w is wr4_4:
+                self.conv_weights.append(w)
+        self.all_weights = ws
+
+        ck = dict(cost_kwargs)
+        self.dice_flag = ck.pop("dice_flag", True)
+        self.cross_flag = ck.pop("cross_flag", False)
+        self.miu_dice = ck.pop("miu_dice", None)
+        self.miu_cross = ck.pop("miu_cross", None)
+        self.reg_coeff = ck.pop("regularizer", 1e-4)
+
+    # ---- graph ---------------------------------------------------------------------------------------
+    def forward(self, x, keep_prob=1.0, main_bn=True, adapt_bn=True, return_taps=False):
+        """create_network (source_segmenter.py:88-209) -> logits [B,256,256,n_class]"""
+        h, t1 = self.front_a.run(x, keep_prob, adapt_bn, self.adapt_trainable)
+        h, t2 = self.front_b.run(h, keep_prob, main_bn, self.main_trainable)
+        h, t3 = self.back.run(h, keep_prob, main_bn, self.main_trainable)
+        logits = self.tail.run(h, keep_prob, self.batch_size)
+        if return_taps:
+            return logits, {"c4_2": t1[4], "c6_2": t2[6], "b7": t3[7], "b8": t3[8], "c9_2": t3[9]}
+        return logits
+
+    __call__ = forward
+
+    def predicter(self, logits):
+        return L.pixel_wise_softmax_2(logits)
+
+    def compact_pred(self, logits):
+        return torch.argmax(self.predicter(logits), 3)
+
+    def losses(self, logits, y):
+        """(cost, weighted_loss, dice_loss) -- source_segmenter.py:211-273"""
+        wce, dice = F.seg_losses(logits, y)
+        self.weighted_loss, self.dice_loss = wce, dice
+        return wce, dice
+
+    def cost_value(self, wce, dice):
+        c = 0.0
+        if self.cross_flag is True:
+            c = c + self.miu_cross * float(wce)
+        if self.dice_flag is True:
+            c = c + self.miu_dice * float(dice)
+        return c
+
+    def regularizer_loss(self):
+        return self.reg_coeff * float(F.l2_loss_sum(self.conv_weights).item())
+
+    def dice_eval(self, logits, y):
+        from .lib import _dice_eval
+        return _dice_eval(logits, y, self.n_class)
+
+    def confusion_matrix(self, logits, y):
+        return F.confusion_counts(logits, y)
+
+    def weight_decay_table(self, variables):
+        """per-variable coefficient of the L2 term's gradient: reg_coeff * multiplicity in conv_weights"""
+        mult = {}
+        for w in self.conv_weights:
+            mult[id(w)] = mult.get(id(w), 0) + 1
+        return [self.reg_coeff * mult.get(id(v), 0) for v in variables]
+
+    def restore(self, model_path):
+        """source_segmenter.py:275-300 with relaxation: load every stored variable whose name we know."""
+        d = dict(np.load(model_path))
+        missing = rt.load_state_dict(d, strict=False)
+        logging.info("Model restored from file: %s (%d unknown names skipped)" % (model_path, len(missing)))
+
+
+class Trainer(object):
+    """source_segmenter.py:303-675, re-hosted: same constructor / train() arguments; inputs come from a
+    synthetic source unless `source` is given (anything with .next() -> (images, int labels))."""
+
+    def __init__(self, net, train_list, val_list, num_cls, batch_size, test_nii_list=None, test_label_list=None,
+                 optimizer="momentum", opt_kwargs={}, num_epochs=100, checkpoint_space=500, lr_update_flag=False, source=None):
+        self.net = net
+        self.batch_size = batch_size
+        self.num_cls = num_cls
+        self.checkpoint_space = checkpoint_space
+        self.opt_kwargs = dict(opt_kwargs)
+        self.lr_update_flag = lr_update_flag
+        self.train_list, self.val_list = train_list, val_list
+        if optimizer != "adam":
+            raise NotImplementedError("only the reference's configured optimizer (adam, train_segmenter.py:38) is on the hot path")
+        self.source = source
+        self.global_step = 0
+        self.dp = parallel.DataParallel()
+        self._build_optimizer()
+
+    def _build_optimizer(self):
+        """source_segmenter.py:357-381: Adam over every trainable variable, loss = cost + regularizer"""
+        tv = [v for v in rt.global_variables() if v.pnp_trainable]
+        self.trainables = tv
+        self.arena = optim.Arena(tv)
+        lr = self.opt_kwargs.pop("learning_rate", 1e-3)
+        self._new_LR = lr
+        self.optimizer = optim.Adam(self.arena, lr=lr, weight_decay=self.net.weight_decay_table(tv), **self.opt_kwargs)
+        dev = self.arena.theta.device
+        self._g_cross = torch.tensor(float(self.net.miu_cross or 0.0) if self.net.cross_flag else 0.0, device=dev)
+        self._g_dice = torch.tensor(float(self.net.miu_dice or 0.0) if self.net.dice_flag else 0.0, device=dev)
+
+    def train_step(self, batch_x, batch_y, keep_prob=0.75):
+        """one sess.run((optimizer, cost, lr)) of source_segmenter.py:484-489 (both BN switches True).
+        batch_x [B,256,256,3] fp32, batch_y [B,256,256,num_cls] one-hot fp32, both on the device."""
+        self.arena.zero_grad()
+        rt.rng.advance()
+        logits = self.net.forward(batch_x, keep_prob=keep_prob, main_bn=True, adapt_bn=True)
+        wce, dice = self.net.losses(logits, batch_y)
+        torch.autograd.backward([wce, dice], [self._g_cross, self._g_dice])
+        scale = self.dp.allreduce(self.arena.grad)
+        self.optimizer.step(grad_scale=scale)
+        self.global_step += 1
+        return wce, dice
+
+    def feed(self, images, raw_labels):
+        """host batch -> device tensors (the feed_dict copy) + on-device one-hot (lib._label_decomp)"""
+        dev = rt.device()
+        x = to_device(images, dev)
+        y = _label_decomp(self.num_cls, to_device(raw_labels, dev))
+        return x, y
+
+    def train(self, output_path, restored_path=None, restore=False, training_iters=100, epochs=100, display_step=5, dropout=0.75):
+        """source_segmenter.py:429-525 without queues/summaries: Adam steps, periodic stats, checkpoint + LR*0.9."""
+        save_path = os.path.join(output_path, "model.cpkt")
+        if epochs == 0:
+            return save_path
+        os.makedirs(output_path, exist_ok=True)
+        if restore and restored_path and os.path.exists(os.path.join(restored_path, "latest.npz")):
+            self.net.restore(os.path.join(restored_path, "latest.npz"))
+            if self.lr_update_flag:
+                self.optimizer.set_lr(self._new_LR)
+        elif restore:
+            print("Unable to restore, start from beginning")
+        src = self.source or SyntheticSource(self.batch_size, seed=1234 + self.dp.rank, num_cls=self.num_cls)
+        for epoch in range(epochs):
+            for step in range(epoch * training_iters, (epoch + 1) * training_iters):
+                start = time.time()
+                images, raw_y = src.next()
+                x, y = self.feed(images, raw_y)
+                wce, dice = self.train_step(x, y, dropout)
+                if step % display_step == 0:
+                    loss = self.net.cost_value(wce, dice)
+                    logging.info("Training at step %s epoch %s , loss is %0.4f" % (step, epoch, loss))
+                    logging.info("Time elapsed %s seconds" % (time.time() - start))
+                if step % self.checkpoint_space == 0 and step > 10000:
+                    _save(rt.state_dict(), save_path, global_step=self.global_step)
+                    _save(rt.state_dict(), os.path.join(output_path, "latest"))
+                    self.optimizer.set_lr(self.optimizer.get_lr() * 0.9)
+        return save_path
+
+    def val_stats(self, batch_x, batch_y):
+        """source_segmenter.py:541-570: inference-mode forward (BN moving stats, keep_prob 1)"""
+        with torch.no_grad():
+            logits = self.net.forward(batch_x, keep_prob=1.0, main_bn=False, adapt_bn=False)
+            wce, dice = self.net.losses(logits, batch_y)
+            d, arr = self.net.dice_eval(logits, batch_y)
+        return {"loss": self.net.cost_value(wce, dice), "dice_eval": float(d), "dice_arr": [float(a) for a in arr]}

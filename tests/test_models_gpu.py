@@ -1,0 +1,187 @@
+"""GPU parity of the whole hot path against the CPU oracle (oracle/pnp_graphs.py) on identical seeded
+synthetic 256x256x3 inputs and identical initial variables (loaded by TF variable name):
+  config 1: segmenter forward, B=2              -> logits / softmax / argmax / Dice
+  config 2: segmenter Adam train step           -> losses, updated variables, BN moving statistics
+  config 3: D step (pre-train, lambda=0) + clip -> dis_loss, critic logits, updated variables
+  config 4: D step + G step (train-gan, lambda=0.3)
+Tolerance (BASELINE.json north_star): 1e-3 relative fp32, stated per check; dropout off (keep_prob=1,
+critic_keep_prob=1) because TF's Philox stream cannot be reproduced.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import check, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+B = 2
+
+
+def _seg_pair(backend, dtype=torch.float32):
+    import pnp_b200
+    from pnp_b200 import runtime as rt, source_segmenter as seg
+    from oracle.pnp_graphs import OracleSegmenter, init_numpy_params
+    rt.set_conv_backend(backend)
+    ws, bns = OracleSegmenter.layout()
+    P = init_numpy_params(ws, bns, 0, 0.05)
+    rng = np.random.RandomState(5)
+    for n, c in bns:   # non-trivial BN state so that inference-mode BN is really exercised
+        P[n + "/gamma"] = (1 + 0.2 * rng.randn(c)).astype(np.float32)
+        P[n + "/beta"] = (0.1 * rng.randn(c)).astype(np.float32)
+        P[n + "/moving_mean"] = (0.05 * rng.randn(c)).astype(np.float32)
+        P[n + "/moving_variance"] = (1 + 0.2 * rng.rand(c)).astype(np.float32)
+    ck = {"cross_flag": True, "miu_cross": 1.0, "dice_flag": True, "miu_dice": 1.0, "regularizer": 1e-4}
+    net = seg.Full_DRN(channels=3, n_class=5, batch_size=B, cost_kwargs=dict(ck))
+    rt.load_state_dict(P)
+    oracle = OracleSegmenter(P, B, dtype=dtype)
+    return net, oracle, P
+
+
+def _inputs():
+    from oracle.pnp_graphs import synthetic_images, synthetic_labels
+    from oracle.tf14_numpy import label_decomp
+    x = synthetic_images(B, 1234)
+    lab = synthetic_labels(B, 99)
+    y = torch.from_numpy(label_decomp(5, lab))
+    return x, lab, y
+
+
+@pytest.mark.parametrize("backend", ["simt", "auto"])
+@pytest.mark.parametrize("bn_train", [True, False])
+def test_config1_segmenter_forward(backend, bn_train):
+    from pnp_b200 import runtime as rt
+    net, oracle, _ = _seg_pair(backend)
+    x, lab, y = _inputs()
+    with torch.no_grad():
+        ref = oracle.forward(x, 1.0, bn_train)
+        logits, taps = net.forward(x.to(DEV), keep_prob=1.0, main_bn=bn_train, adapt_bn=bn_train, return_taps=True)
+    for k in ("c4_2", "c6_2", "b7", "c9_2"):
+        check(k, taps[k], ref[k], 1e-3)
+    check("logits", logits, ref["logits"], 1e-3)
+    from oracle import tf14_torch as T
+    check("softmax", net.predicter(logits), T.pixel_wise_softmax_2(ref["logits"]), 1e-3)
+    agree = float((logits.argmax(3).cpu() == ref["logits"].argmax(3)).float().mean())
+    print("  argmax agreement %.6f" % agree)
+    assert agree > 0.999
+    d, arr = net.dice_eval(logits, y.to(DEV))
+    do, _ = T.dice_eval(ref["logits"].argmax(3), y, 5)
+    assert abs(float(d) - float(do)) <= 1e-3, (float(d), float(do))
+    rt.set_conv_backend("auto")
+
+
+@pytest.mark.parametrize("backend", ["simt", "auto"])
+def test_config2_segmenter_train_step(backend):
+    from pnp_b200 import runtime as rt, source_segmenter as seg
+    net, oracle, P = _seg_pair(backend)
+    x, lab, y = _inputs()
+    trainer = seg.Trainer(net, [], [], num_cls=5, batch_size=B, optimizer="adam", opt_kwargs={"learning_rate": 1e-3})
+    xg, yg = trainer.feed(x, torch.from_numpy(lab))
+    assert torch.equal(yg.cpu(), y)
+    for step in range(2):
+        ro = oracle.train_step(x, y, keep_prob=1.0)
+        wce, dice = trainer.train_step(xg, yg, keep_prob=1.0)
+        check("step%d wce" % step, wce.reshape(1), torch.tensor([ro["wce"]]), 1e-3)
+        check("step%d dice" % step, dice.reshape(1), torch.tensor([ro["dice"]]), 1e-3)
+        if step == 0:
+            # first-step gradients, name by name (the arena holds them until the next zero_grad)
+            names = [n for n, _ in type(oracle).layout()[0]]
+            worst = 0.0
+            for n, g in zip(names, ro["grads"][:len(names)]):
+                # oracle grads include the L2 term; ours folds it into the optimizer (wd * theta)
+                v = rt.graph.vars[n]
+                mult = sum(1 for w in net.conv_weights if w is v)
+                ours = v.grad.cpu().double() + 1e-4 * mult * torch.tensor(P[n]).double()
+                worst = max(worst, rel_err(ours, g))
+            print("  worst weight-gradient rel err %.3e" % worst)
+            assert worst <= 2e-3
+    ref = oracle.ps.to_numpy()
+    got = rt.state_dict()
+    worst, wname = 0.0, None
+    for n in ref:
+        e = rel_err(torch.tensor(got[n]), torch.tensor(ref[n]))
+        if e > worst:
+            worst, wname = e, n
+    print("  worst variable after 2 Adam steps: %s rel err %.3e" % (wname, worst))
+    assert worst <= 1e-3
+    reg = net.regularizer_loss()
+    assert abs(reg - float(oracle.losses(oracle.forward(x, 1.0, False)["logits"], y)[1])) <= 1e-3 * abs(reg)
+    rt.set_conv_backend("auto")
+
+
+def _adv_pair(backend, lam, phase):
+    import pnp_b200
+    from pnp_b200 import runtime as rt, adversarial as adv
+    from pnp_b200.train_gan import configure
+    from oracle.pnp_graphs import OracleAdversarial, init_numpy_params
+    rt.set_conv_backend(backend)
+    ws, bns = OracleAdversarial.layout()
+    P = init_numpy_params(ws, bns, 0, 0.05)
+    rng = np.random.RandomState(6)
+    for n, c in bns:
+        P[n + "/gamma"] = (1 + 0.2 * rng.randn(c)).astype(np.float32)
+        P[n + "/beta"] = (0.1 * rng.randn(c)).astype(np.float32)
+        P[n + "/moving_mean"] = (0.05 * rng.randn(c)).astype(np.float32)
+        P[n + "/moving_variance"] = (1 + 0.2 * rng.rand(c)).astype(np.float32)
+    for n, s in ws:   # keep the critic weights inside the clip range so the clip is exercised but not dominant
+        if "cls" in n:
+            P[n] = np.clip(P[n] * 0.5, -0.05, 0.05).astype(np.float32)
+    ck, nc, tc = configure(phase)
+    ck["lambda_mask_loss"] = lam
+    tc["dis_sub_iter"] = 3
+    net = adv.Full_DRN(channels=3, n_class=5, batch_size=B, cost_kwargs=ck, network_config=nc, critic_keep_prob=1.0)
+    rt.load_state_dict(P)
+    trainer = adv.Trainer(net, num_cls=5, batch_size=B, opt_kwargs={"learning_rate": 3e-4}, train_config=tc)
+    oracle = OracleAdversarial(P, B, lambda_mask_loss=lam, dis_sub_iter=3, gen_sub_iter=1, critic_keep_prob=1.0)
+    return net, trainer, oracle
+
+
+def _compare_state(rt, oracle, tol, only=None):
+    ref = oracle.ps.to_numpy()
+    got = rt.state_dict()
+    worst, wname = 0.0, None
+    for n in ref:
+        if only and not only(n):
+            continue
+        e = rel_err(torch.tensor(got[n]), torch.tensor(ref[n]))
+        if e > worst:
+            worst, wname = e, n
+    print("  worst variable: %s rel err %.3e" % (wname, worst))
+    assert worst <= tol, (wname, worst)
+
+
+@pytest.mark.parametrize("backend", ["simt", "auto"])
+def test_config3_discriminator_pretrain_step(backend):
+    from pnp_b200 import runtime as rt
+    from oracle.pnp_graphs import synthetic_images
+    net, trainer, oracle = _adv_pair(backend, 0, "pre-train")
+    mr, ct = synthetic_images(B, 1234), synthetic_images(B, 4321, 0.3, 0.8)
+    for step in range(2):
+        ro = oracle.d_step(mr, ct, keep_prob=1.0)
+        terms = trainer.d_step(mr.to(DEV), ct.to(DEV), keep_prob=1.0)
+        got = trainer.loss_value(terms)
+        print("  step %d dis_loss %.6e (oracle %.6e)" % (step, got, ro["dis_loss"]))
+        assert abs(got - ro["dis_loss"]) <= 1e-3 * max(abs(ro["dis_loss"]), 2e-3 * float(ro["mr_cls"].abs().max()))
+    _compare_state(rt, oracle, 1e-3)
+    check("dis_reg", torch.tensor([net.dis_reg()]), torch.tensor([float(oracle.dis_losses(ro["ct_cls"], ro["mr_cls"], None, None)[1])]), 1e-3)
+    rt.set_conv_backend("auto")
+
+
+@pytest.mark.parametrize("backend", ["simt", "auto"])
+def test_config4_joint_adversarial_step(backend):
+    from pnp_b200 import runtime as rt
+    from oracle.pnp_graphs import synthetic_images
+    net, trainer, oracle = _adv_pair(backend, 0.3, "train-gan")
+    mr, ct = synthetic_images(B, 1234), synthetic_images(B, 4321, 0.3, 0.8)
+    ro = oracle.d_step(mr, ct, keep_prob=1.0)
+    terms = trainer.d_step(mr.to(DEV), ct.to(DEV), keep_prob=1.0)
+    got = trainer.loss_value(terms)
+    print("  dis_loss %.6e (oracle %.6e)" % (got, ro["dis_loss"]))
+    assert abs(got - ro["dis_loss"]) <= 1e-3 * max(abs(ro["dis_loss"]), 2e-3 * float(ro["mr_cls"].abs().max()))
+    rg = oracle.g_step(ct, keep_prob=1.0)
+    terms = trainer.g_step(ct.to(DEV), keep_prob=1.0)
+    got = trainer.loss_value(terms)
+    print("  gen_loss %.6e (oracle %.6e)" % (got, rg["gen_loss"]))
+    assert abs(got - rg["gen_loss"]) <= 1e-3 * max(abs(rg["gen_loss"]), 2e-3 * float(rg["ct_cls"].abs().max()))
+    _compare_state(rt, oracle, 1e-3)
+    rt.set_conv_backend("auto")

@@ -1,0 +1,408 @@
+"""GPU parity of every operator of the hot path: CUDA product (through layers.py / ops.py -> ctypes ->
+C-ABI) vs the CPU oracle (oracle/tf14_torch.py, fp64) on identical seeded inputs.  fp32 kernels: tolerance
+1e-4 relative to the largest reference magnitude; the 3-term bf16-split tensor-core path: 2e-4; stated per test.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import check, randn
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _prod():
+    import pnp_b200
+    from pnp_b200 import layers, ops, functional, runtime
+    return layers, ops, functional, runtime
+
+
+def _oracle():
+    from oracle import tf14_torch as T
+    return T
+
+
+def _var(t, grad=True):
+    v = t.to(DEV).contiguous()
+    v.requires_grad_(grad)
+    return v
+
+
+# (B, H, W, Cin, Cout, k, stride, dil, padding) -- every conv flavour the graphs contain, at reduced spatial size
+CONV_CASES = [
+    (2, 16, 16, 3, 16, 3, 1, 1, "SAME"),       # conv1_1: Cin=3 scalar gather
+    (2, 16, 16, 16, 16, 3, 1, 1, "SAME"),      # g1 res
+    (2, 16, 16, 16, 32, 3, 1, 1, "SAME"),      # g2 inc
+    (2, 8, 8, 64, 128, 3, 1, 1, "SAME"),       # g4
+    (2, 8, 8, 128, 128, 3, 1, 2, "SAME"),      # dilated
+    (2, 8, 8, 64, 320, 3, 1, 1, "SYMMETRIC"),  # g10-like (mirror pad)
+    (2, 16, 16, 40, 5, 5, 1, 1, "SYMMETRIC"),  # output conv: Cin=40, Cout=5
+    (2, 16, 16, 64, 64, 3, 2, 1, "SAME"),      # cls_1_3 down: stride 2, pad (0,1)
+    (2, 16, 16, 32, 32, 5, 2, 1, "SAME"),      # cls_2_3: 5x5 stride 2, pad (1,2)
+    (2, 16, 16, 16, 32, 5, 4, 1, "SAME"),      # m_cls_2_3: 5x5 stride 4
+    (2, 4, 4, 64, 64, 3, 2, 1, "SYMMETRIC"),   # cls_6
+    (2, 8, 8, 32, 64, 5, 4, 1, "SYMMETRIC"),   # m_cls_4
+    (2, 16, 16, 5, 16, 3, 2, 1, "SAME"),       # mask_cls_1: Cin=5
+    (3, 12, 20, 24, 40, 3, 1, 1, "SAME"),      # odd sizes / ragged tiles
+    (1, 7, 9, 8, 12, 3, 2, 1, "SAME"),         # odd spatial, stride 2
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "B%d_%dx%d_%d-%d_k%d_s%d_d%d_%s" % c)
+@pytest.mark.parametrize("backend", ["simt", "auto"])
+def test_conv_fwd_bwd(case, backend):
+    """conv2d / dilate_conv2d forward, dgrad and wgrad vs oracle autograd"""
+    L, ops, F, rt = _prod()
+    T = _oracle()
+    rt.set_conv_backend(backend)
+    B, H, W, Cin, Cout, k, s, d, pad = case
+    x = randn((B, H, W, Cin), 1)
+    w = randn((k, k, Cin, Cout), 2, 0.2)
+    xo, wo = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    yo = T.conv2d_raw(xo, wo, stride=s, dilation=d, padding=pad)
+    r = randn(tuple(yo.shape), 3)
+    (yo * r.double()).sum().backward()
+    xg, wg = _var(x), _var(w)
+    if d == 1:
+        y = L.conv2d(xg, wg, 1.0, strides=[1, s, s, 1], padding=pad)
+    else:
+        y = L.dilate_conv2d(xg, wg, 1.0, rate=d, padding=pad)
+    tol = 1e-4 if backend == "simt" else 2e-4
+    check("y", y, yo, tol)
+    y.backward(r.to(DEV))
+    check("dx", xg.grad, xo.grad, tol)
+    check("dw", wg.grad, wo.grad, tol)
+    rt.set_conv_backend("auto")
+
+
+TC_CASES = [
+    (2, 32, 32, 64, 64, 3, 1, 1, "SAME"),
+    (2, 32, 32, 128, 256, 3, 1, 1, "SAME"),
+    (3, 32, 32, 512, 512, 3, 1, 2, "SAME"),     # DR block conv, B not a multiple of the image tile
+    (2, 32, 32, 64, 320, 3, 1, 1, "SYMMETRIC"), # g10-like: 34x34 padded input, dgrad on a 34-wide grid
+    (2, 64, 64, 64, 64, 3, 1, 1, "SAME"),
+    (1, 128, 128, 64, 128, 3, 1, 1, "SAME"),
+    (1, 256, 256, 64, 64, 3, 1, 1, "SAME"),     # cls_1 res b: two 128-wide tiles per row
+    (5, 16, 16, 512, 512, 3, 1, 1, "SAME"),     # cls_5: 16x16 images, 8 rows per tile
+    (9, 4, 4, 128, 64, 3, 1, 1, "SAME"),        # tiny images: 8 images per tile, ragged batch
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "B%d_%dx%d_%d-%d_k%d_s%d_d%d_%s" % c)
+@pytest.mark.parametrize("backend,tol", [("tc3", 2e-4), ("tc1", 3e-2)])
+def test_conv_tensor_core(case, backend, tol):
+    """tcgen05 path (3-term split = fp32-grade, 1-term = plain bf16) forward + dgrad vs oracle"""
+    L, ops, F, rt = _prod()
+    T = _oracle()
+    if not rt.tc_available():
+        pytest.fail("tcgen05 path unavailable on this device -- it must be the one that runs on B200")
+    rt.set_conv_backend(backend)
+    B, H, W, Cin, Cout, k, s, d, pad = case
+    x = randn((B, H, W, Cin), 11)
+    w = randn((k, k, Cin, Cout), 12, 0.05)
+    xo, wo = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    yo = T.conv2d_raw(xo, wo, stride=s, dilation=d, padding=pad)
+    r = randn(tuple(yo.shape), 13)
+    (yo * r.double()).sum().backward()
+    xg, wg = _var(x), _var(w)
+    y = L.conv2d(xg, wg, 1.0, padding=pad) if d == 1 else L.dilate_conv2d(xg, wg, 1.0, rate=d, padding=pad)
+    check("y", y, yo, tol)
+    y.backward(r.to(DEV))
+    check("dx", xg.grad, xo.grad, tol)
+    check("dw", wg.grad, wo.grad, 2e-4 if backend == "tc3" else 1e-3)
+    rt.set_conv_backend("auto")
+
+
+def _bn_pair(T, C, seed):
+    """oracle BNState + matching product variables with non-trivial gamma/beta/moving stats"""
+    bn = T.BNState(C, torch.float64)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        bn.gamma.copy_(1 + 0.3 * torch.randn(C, generator=g, dtype=torch.float64))
+        bn.beta.copy_(0.2 * torch.randn(C, generator=g, dtype=torch.float64))
+        bn.moving_mean = 0.1 * torch.randn(C, generator=g, dtype=torch.float64)
+        bn.moving_var = 1 + 0.2 * torch.rand(C, generator=g, dtype=torch.float64)
+    return bn
+
+
+def _load_bn(rt, scope, bn):
+    rt.load_state_dict({scope + "/gamma": bn.gamma.detach().numpy(), scope + "/beta": bn.beta.detach().numpy(),
+                        scope + "/moving_mean": bn.moving_mean.numpy(), scope + "/moving_variance": bn.moving_var.numpy()})
+
+
+@pytest.mark.parametrize("is_train", [True, False])
+@pytest.mark.parametrize("leak", [True, False])
+@pytest.mark.parametrize("backend", ["simt", "auto"])
+def test_conv_bn_relu(is_train, leak, backend):
+    """conv_bn_relu2d: conv -> BN(train|infer) -> (l)relu, forward, all gradients, moving statistics"""
+    L, ops, F, rt = _prod()
+    T = _oracle()
+    rt.reset_default_graph()
+    rt.set_conv_backend(backend)
+    B, H, W, Cin, Cout = 3, 16, 16, 64, 64
+    x, w = randn((B, H, W, Cin), 21), randn((3, 3, Cin, Cout), 22, 0.1)
+    bn = _bn_pair(T, Cout, 23)
+    xo, wo = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    mm0, mv0 = bn.moving_mean.clone(), bn.moving_var.clone()
+    st = 1 if backend == "auto" else 2          # stride 1 rides the tcgen05 path (+ fused BN statistics)
+    yo = T.conv_bn_relu2d(xo, wo, 1.0, bn, strides=(1, st, st, 1), is_train=is_train, leak=leak)
+    r = randn(tuple(yo.shape), 24)
+    (yo * r.double()).sum().backward()
+    L.bn_variables("t", Cout)
+    bn0 = _bn_pair(T, Cout, 23)
+    _load_bn(rt, "t", bn0)
+    xg, wg = _var(x), _var(w)
+    y = L.conv_bn_relu2d(xg, wg, 1.0, strides=[1, st, st, 1], is_train=is_train, scope="t", leak=leak)
+    check("y", y, yo, 2e-4)
+    y.backward(r.to(DEV))
+    check("dx", xg.grad, xo.grad, 3e-4)
+    check("dw", wg.grad, wo.grad, 3e-4)
+    v = rt.graph.vars
+    check("dgamma", v["t/gamma"].grad, bn.gamma.grad, 3e-4)
+    check("dbeta", v["t/beta"].grad, bn.beta.grad, 3e-4)
+    check("moving_mean", v["t/moving_mean"], bn.moving_mean, 1e-5)
+    check("moving_var", v["t/moving_variance"], bn.moving_var, 1e-5)
+    if not is_train:
+        assert torch.equal(bn.moving_mean, mm0) and torch.equal(bn.moving_var, mv0)
+    rt.set_conv_backend("auto")
+
+
+@pytest.mark.parametrize("inc_dim", [False, True])
+@pytest.mark.parametrize("kind", ["res", "dr"])
+@pytest.mark.parametrize("is_train", [True, False])
+@pytest.mark.parametrize("backend", ["simt", "auto"])
+def test_residual_blocks(inc_dim, kind, is_train, backend):
+    """residual_block / DR_block incl. the channel-pad skip; dgrad of the first conv merged with the skip grad"""
+    L, ops, F, rt = _prod()
+    T = _oracle()
+    rt.reset_default_graph()
+    rt.set_conv_backend(backend)
+    B, H, W, Cin = 2, 16, 16, 64
+    Cout = 2 * Cin if inc_dim else Cin
+    x = randn((B, H, W, Cin), 31)
+    w1, w2 = randn((3, 3, Cin, Cout), 32, 0.1), randn((3, 3, Cout, Cout), 33, 0.1)
+    b1, b2 = _bn_pair(T, Cout, 34), _bn_pair(T, Cout, 35)
+    xo = x.double().requires_grad_(True)
+    w1o, w2o = w1.double().requires_grad_(True), w2.double().requires_grad_(True)
+    if kind == "res":
+        yo = T.residual_block(xo, w1o, w2o, 1.0, b1, b2, inc_dim=inc_dim, is_train=is_train, leak=True)
+    else:
+        yo = T.DR_block(xo, w1o, w2o, 2, 1.0, b1, b2, inc_dim=inc_dim, is_train=is_train, leak=True)
+    r = randn(tuple(yo.shape), 36)
+    (yo * r.double()).sum().backward()
+    L.bn_variables("s_1", Cout)
+    L.bn_variables("s_2", Cout)
+    _load_bn(rt, "s_1", _bn_pair(T, Cout, 34))
+    _load_bn(rt, "s_2", _bn_pair(T, Cout, 35))
+    xg, w1g, w2g = _var(x), _var(w1), _var(w2)
+    if kind == "res":
+        y = L.residual_block(xg, w1g, w2g, 1.0, inc_dim=inc_dim, is_train=is_train, scope="s", leak=True)
+    else:
+        y = L.DR_block(xg, w1g, w2g, 2, 1.0, inc_dim=inc_dim, is_train=is_train, scope="s", leak=True)
+    check("y", y, yo, 2e-4)
+    y.backward(r.to(DEV))
+    check("dx", xg.grad, xo.grad, 5e-4)
+    check("dw1", w1g.grad, w1o.grad, 5e-4)
+    check("dw2", w2g.grad, w2o.grad, 5e-4)
+    v = rt.graph.vars
+    check("dgamma1", v["s_1/gamma"].grad, b1.gamma.grad, 5e-4)
+    check("dbeta2", v["s_2/beta"].grad, b2.beta.grad, 5e-4)
+    check("mm2", v["s_2/moving_mean"], b2.moving_mean, 1e-5)
+    check("mv1", v["s_1/moving_variance"], b1.moving_var, 1e-5)
+    rt.set_conv_backend("auto")
+
+
+def test_fused_bn_stats_match_separate_pass():
+    """BN statistics reduced in the tcgen05 epilogue == the standalone pnp_bn_stats pass"""
+    L, ops, F, rt = _prod()
+    rt.reset_default_graph()
+    rt.set_conv_backend("tc3")
+    x, w = randn((3, 32, 32, 64), 41), randn((3, 3, 64, 128), 42, 0.1)
+    outs = []
+    for fuse in (True, False):
+        rt.reset_default_graph()
+        F.FUSE_BN_STATS = fuse
+        y = L.conv_bn_relu2d(_var(x, False), _var(w, False), 1.0, is_train=True, scope="q", leak=True)
+        outs.append((y, rt.graph.vars["q/moving_mean"].clone(), rt.graph.vars["q/moving_variance"].clone()))
+    F.FUSE_BN_STATS = True
+    check("y", outs[0][0], outs[1][0], 1e-5)
+    check("moving_mean", outs[0][1], outs[1][1], 1e-5)
+    check("moving_var", outs[0][2], outs[1][2], 1e-5)
+    rt.set_conv_backend("auto")
+
+
+def test_maxpool():
+    L, ops, F, rt = _prod()
+    T = _oracle()
+    for C in (16, 6):
+        x = randn((2, 8, 12, C), 51)
+        xo = x.double().requires_grad_(True)
+        yo = T.max_pool2d(xo, 2)
+        r = randn(tuple(yo.shape), 52)
+        (yo * r.double()).sum().backward()
+        xg = _var(x)
+        y = L.max_pool2d(xg, 2)
+        check("y", y, yo, 1e-7)
+        y.backward(r.to(DEV))
+        check("dx", xg.grad, xo.grad, 1e-7)
+
+
+@pytest.mark.parametrize("B", [1, 2, 3])
+@pytest.mark.parametrize("G", [1, 5])
+def test_phase_shift(B, G):
+    """PS: bit-exact data movement vs the LITERAL numpy emulation of ops.py (both batch regimes)"""
+    L, ops, F, rt = _prod()
+    from oracle.tf14_numpy import PS_literal
+    r = 4
+    x = randn((B, 3, 5, G * r * r), 61)
+    ref = torch.from_numpy(PS_literal(x.numpy(), r, G, B))
+    xg = _var(x)
+    y = ops.PS(xg, r, n_channel=G, batch_size=B)
+    assert torch.equal(y.cpu(), ref), "PS forward is pure data movement and must be bit-exact"
+    g = randn(tuple(ref.shape), 62)
+    y.backward(g.to(DEV))
+    # adjoint of a permutation = inverse permutation: check <PS(x), g> == <x, PS^T(g)>
+    lhs = float((ref.double() * g.double()).sum())
+    rhs = float((x.double() * xg.grad.cpu().double()).sum())
+    assert abs(lhs - rhs) <= 1e-6 * max(1.0, abs(lhs))
+    with pytest.raises(ValueError):
+        ops.PS(xg, r, n_channel=G, batch_size=B + 1)
+
+
+def test_disc_input_gather():
+    """adversarial.py:325-335 channel order + gradients (argmax channel carries none)"""
+    L, ops, F, rt = _prod()
+    T = _oracle()
+    B, a = 2, 4
+    c4, c6 = randn((B, a, a, 128), 71), randn((B, a, a, 256), 72)
+    b7, c9 = randn((B, a, a, 512), 73), randn((B, a, a, 512), 74)
+    lg = randn((B, a * 8, a * 8, 5), 75)
+    ins_o = [t.double().requires_grad_(True) for t in (c4, c6, b7, c9, lg)]
+    f4 = T.PS(ins_o[0], 8, 2, B).repeat(1, 1, 1, 3)
+    ref = torch.cat([f4, T.PS(ins_o[1], 8, 4, B), T.PS(ins_o[2], 8, 8, B), T.PS(ins_o[3], 8, 8, B), ins_o[4],
+                     ins_o[4].argmax(3).double().unsqueeze(3)], 3)
+    r = randn(tuple(ref.shape), 76)
+    (ref * r.double()).sum().backward()
+    ins = [_var(t) for t in (c4, c6, b7, c9, lg)]
+    out = F.disc_input(*ins, batch_size=B)
+    assert out.shape[-1] == 32
+    check("d_input", out, ref, 1e-7)
+    out.backward(r.to(DEV))
+    for n, a_, b_ in zip(("c4", "c6", "b7", "c9", "logits"), ins, ins_o):
+        check("d" + n, a_.grad, b_.grad, 1e-6)
+
+
+def test_seg_losses_and_metrics():
+    """weighted CE + soft Dice (forward, gradient), pixel_wise_softmax_2, hard Dice / confusion matrix"""
+    L, ops, F, rt = _prod()
+    T = _oracle()
+    from oracle.pnp_graphs import synthetic_labels
+    from oracle.tf14_numpy import label_decomp
+    B, S = 2, 64
+    logits = randn((B, S, S, 5), 81, 2.0)
+    lab = synthetic_labels(B, 5, size=S)
+    y = torch.from_numpy(label_decomp(5, lab))
+    lo = logits.double().requires_grad_(True)
+    wce_o, dice_o = T.softmax_weighted_loss(lo, y.double()), T.dice_loss(lo, y.double())
+    (0.7 * wce_o + 1.3 * dice_o).backward()
+    lg = _var(logits)
+    yg = F.one_hot(torch.from_numpy(lab).to(DEV), 5)
+    assert torch.equal(yg.cpu(), y)
+    wce, dice = F.seg_losses(lg, yg)
+    check("wce", wce.reshape(1), wce_o.reshape(1), 1e-5)
+    check("dice", dice.reshape(1), dice_o.reshape(1), 1e-5)
+    torch.autograd.backward([wce, dice], [torch.tensor(0.7, device=DEV), torch.tensor(1.3, device=DEV)])
+    check("dlogits", lg.grad, lo.grad, 1e-4)
+    check("softmax2", L.pixel_wise_softmax_2(lg.detach()), T.pixel_wise_softmax_2(logits.double()), 1e-6)
+    from pnp_b200.lib import _dice_eval
+    d, arr = _dice_eval(lg.detach(), yg, 5)
+    do, arro = T.dice_eval(logits.double().argmax(3), y.double(), 5)
+    check("dice_eval", d.reshape(1), do.reshape(1), 1e-6)
+    cm = F.confusion_counts(lg.detach(), yg).cpu().numpy()
+    pred = logits.argmax(3).numpy()
+    ref_cm = np.zeros((5, 5), np.int64)
+    np.add.at(ref_cm, (lab.reshape(-1), pred.reshape(-1)), 1)
+    assert (cm == ref_cm).all()
+
+
+def test_fc_and_wgan_means():
+    L, ops, F, rt = _prod()
+    B, Fd = 6, 2048
+    x, w = randn((B, Fd), 91), randn((Fd, 1), 92, 0.1)
+    x2 = randn((B, Fd), 93)
+    xo, x2o, wo = x.double().requires_grad_(True), x2.double().requires_grad_(True), w.double().requires_grad_(True)
+    mr, ct = xo @ wo, x2o @ wo
+    loss_o = -0.002 * (mr - ct).mean()
+    loss_o.backward()
+    xg, x2g, wg = _var(x), _var(x2), _var(w)
+    mrg, ctg = F.fc(xg, wg), F.fc(x2g, wg)
+    check("fc", mrg, mr, 1e-5)
+    loss = F.mean_combo(mrg, -0.002, ctg, 0.002)
+    check("dis_loss", loss.reshape(1), loss_o.reshape(1), 1e-5)
+    loss.backward()
+    check("dx_mr", xg.grad, xo.grad, 1e-5)
+    check("dx_ct", x2g.grad, x2o.grad, 1e-5)
+    check("dw", wg.grad, wo.grad, 1e-5)
+
+
+def test_optimizers_match_tf_semantics():
+    """fused Adam (epsilon-hat) and RMSProp (ms0 = 1, eps inside sqrt, wd, clip) vs the oracle, 3 steps"""
+    L, ops, F, rt = _prod()
+    T = _oracle()
+    from pnp_b200 import optim
+    shapes = [(3, 3, 8, 16), (16,), (5, 5, 16, 7), (2048, 1)]
+    for kind in ("adam", "rms"):
+        ps = [randn(s, 100 + i, 0.05) for i, s in enumerate(shapes)]
+        po = [p.double().clone() for p in ps]
+        pg = [_var(p) for p in ps]
+        arena = optim.Arena(pg)
+        wd = [1e-4, 0.0, 2e-4, 1e-4]
+        if kind == "adam":
+            opt = optim.Adam(arena, lr=1e-3, weight_decay=wd)
+            oo = T.TFAdam(po, lr=1e-3)
+        else:
+            opt = optim.RMSProp(arena, lr=3e-4, weight_decay=wd, clip=[0.03, 0.0, 0.03, 0.03])
+            oo = T.TFRMSProp(po, lr=3e-4)
+        for step in range(3):
+            gs = [randn(s, 200 + 10 * step + i, 0.1) for i, s in enumerate(shapes)]
+            arena.zero_grad()
+            for p, g in zip(pg, gs):
+                p.grad.copy_(g.to(DEV) * 2.0)          # pretend 2 ranks summed their gradients
+            opt.step(grad_scale=0.5)
+            oo.step([g.double() + c * p for g, c, p in zip(gs, wd, po)])
+            if kind == "rms":
+                for p, c in zip(po, [0.03, 0.0, 0.03, 0.03]):
+                    if c > 0:
+                        p.clamp_(-c, c)
+        for i, (p, q) in enumerate(zip(pg, po)):
+            check("%s theta[%d]" % (kind, i), p.detach(), q, 1e-5)
+
+
+def test_dropout_statistics_and_backward_consistency():
+    """tf.nn.dropout semantics: keep fraction ~ keep_prob, kept values scaled by 1/keep, the backward pass
+    regenerates the same mask; distinct call sites / steps draw distinct masks."""
+    L, ops, F, rt = _prod()
+    rt.manual_seed(123)
+    x = torch.ones(2, 32, 32, 64)
+    w = torch.zeros(1, 1, 64, 64)
+    w[0, 0] = torch.eye(64)
+    xg, wg = _var(x), _var(w, False)
+    rt.set_conv_backend("simt")
+    y = L.conv2d(xg, wg, 0.75)
+    frac = float((y != 0).float().mean())
+    assert abs(frac - 0.75) < 0.01, frac
+    vals = torch.unique(y.detach())
+    assert set(round(float(v), 5) for v in vals) <= {0.0, round(1 / 0.75, 5)}
+    y.backward(torch.ones_like(y))
+    assert torch.equal((xg.grad != 0), (y.detach() != 0)), "backward must regenerate the forward mask"
+    y2 = L.conv2d(xg.detach(), wg, 0.75)
+    assert not torch.equal(y2 != 0, y.detach() != 0)
+    rt.set_conv_backend("tc3")
+    rt.manual_seed(123)
+    y3 = L.conv2d(xg.detach(), wg, 0.75)        # same seed + first call site => same mask through the TC epilogue
+    assert torch.equal(y3 != 0, y.detach() != 0)
+    rt.set_conv_backend("auto")
