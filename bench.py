@@ -199,7 +199,7 @@ def run_ours(a):
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cpu = cpu_baseline_sample(1, 1)
+        cpu = cpu_baseline_sample(2, 1)
 
     if rank == 0:
         gf_step = B * (GF_D_STEP_PER_PAIR + GF_G_STEP_PER_SLICE) * world
@@ -223,7 +223,8 @@ def run_ours(a):
 def cpu_baseline_sample(B, reps):
     """the oracle's joint adversarial step (same math, torch-CPU/oneDNN) on the host cores -- bounded sample"""
     from oracle.pnp_graphs import OracleAdversarial, init_numpy_params, synthetic_images
-    torch.set_num_threads(os.cpu_count() or 1)
+    # torch's default intra-op pool (= physical cores it detects); forcing os.cpu_count() logical threads
+    # oversubscribes oneDNN on the GPU host and is >10x slower
     ws, bns = OracleAdversarial.layout()
     P = init_numpy_params(ws, bns, 0, 0.05)
     o = OracleAdversarial(P, B, lambda_mask_loss=0.3, dis_sub_iter=1, gen_sub_iter=1, critic_keep_prob=0.75)
@@ -246,7 +247,6 @@ def run_reference(a):
     if rank != 0:
         return
     from oracle.pnp_graphs import OracleAdversarial, init_numpy_params, synthetic_images
-    torch.set_num_threads(os.cpu_count() or 1)
     B = 1
     ws, bns = OracleAdversarial.layout()
     P = init_numpy_params(ws, bns, 0, 0.05)

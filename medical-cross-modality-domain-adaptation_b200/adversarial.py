@@ -403,7 +403,7 @@ class Trainer(object):
 
     @staticmethod
     def loss_value(terms):
-        return sum(float(t) * w for t, w in terms)
+        return sum(float(t.detach()) * w for t, w in terms)
 
     # ---- schedule (adversarial.py:767-940) ---------------------------------------------------------------------------------
     def train(self, output_path, restore=True, restored_path=None, training_iters=200, epochs=1000, dropout=0.75, display_step=5):

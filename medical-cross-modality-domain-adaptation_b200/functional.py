@@ -20,6 +20,8 @@ ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 FUSE_BN_STATS = True
 # bench.py sets this to a list to time every tcgen05 launch with CUDA events: (start, end, flops, tag)
 PROFILE = None
+# debugging aid: callable(sv, dy, g, dz, dx) invoked at the end of every layer_backward
+DEBUG_HOOK = None
 
 
 def _tc_launch(tag, flops, *args):
@@ -317,6 +319,8 @@ def layer_backward(sv, dy, need_dx=True, dx_into=None, want_dskip=False):
                 raise NotImplementedError("accumulating dgrad through a SYMMETRIC pad is not used by the hot path")
         else:
             dx = conv_dgrad_raw(dz, W, geom, into=dx_into)
+    if DEBUG_HOOK is not None:
+        DEBUG_HOOK(sv, dy, g, dz, dx)
     return dx, dskip
 
 
@@ -336,8 +340,9 @@ class _ConvLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, skip, cfg, W, *bnp):
-        save = torch.is_grad_enabled() and (x.requires_grad or W.requires_grad or any(p.requires_grad for p in bnp) or
-                                            (skip is not None and skip.requires_grad))
+        # autograd.Function.forward always runs with grad mode off; needs_input_grad already folds in the caller's
+        # grad mode (all False under torch.no_grad()) and the inputs' requires_grad flags
+        save = any(ctx.needs_input_grad)
         y, sv = layer_forward(x, W, cfg, skip, save)
         ctx.sv = sv
         ctx.has_skip = skip is not None
@@ -363,8 +368,7 @@ class _ResBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, cfg1, cfg2, W1, W2, *bnp):
-        save = torch.is_grad_enabled() and (x.requires_grad or W1.requires_grad or W2.requires_grad or
-                                            any(p.requires_grad for p in bnp))
+        save = any(ctx.needs_input_grad)
         h, s1 = layer_forward(x, W1, cfg1, None, save)
         y, s2 = layer_forward(h, W2, cfg2, x, save)
         ctx.s1, ctx.s2 = s1, s2

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import check, rel_err
+from tests.util import check, rel_err, l2_err
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -60,7 +60,9 @@ def test_config1_segmenter_forward(backend, bn_train):
         check(k, taps[k], ref[k], 1e-3)
     check("logits", logits, ref["logits"], 1e-3)
     from oracle import tf14_torch as T
-    check("softmax", net.predicter(logits), T.pixel_wise_softmax_2(ref["logits"]), 1e-3)
+    sm_ref = T.pixel_wise_softmax_2(ref["logits"])
+    if bool(torch.isfinite(sm_ref).all()):      # layers.py:135 has no max subtraction: exp() overflows for large logits
+        check("softmax", net.predicter(logits), sm_ref, 1e-3)
     agree = float((logits.argmax(3).cpu() == ref["logits"].argmax(3)).float().mean())
     print("  argmax agreement %.6f" % agree)
     assert agree > 0.999
@@ -78,23 +80,25 @@ def test_config2_segmenter_train_step(backend):
     trainer = seg.Trainer(net, [], [], num_cls=5, batch_size=B, optimizer="adam", opt_kwargs={"learning_rate": 1e-3})
     xg, yg = trainer.feed(x, torch.from_numpy(lab))
     assert torch.equal(yg.cpu(), y)
+    from oracle.pnp_graphs import OracleSegmenter
+    g64 = OracleSegmenter(P, B, dtype=torch.float64).train_step(x.double(), y.double(), keep_prob=1.0)["grads"]
     for step in range(2):
         ro = oracle.train_step(x, y, keep_prob=1.0)
         wce, dice = trainer.train_step(xg, yg, keep_prob=1.0)
         check("step%d wce" % step, wce.reshape(1), torch.tensor([ro["wce"]]), 1e-3)
         check("step%d dice" % step, dice.reshape(1), torch.tensor([ro["dice"]]), 1e-3)
         if step == 0:
-            # first-step gradients, name by name (the arena holds them until the next zero_grad)
+            # first-step gradients, variable by variable, against the fp64 oracle; bound calibrated by how far an fp32
+            # reference implementation (the fp32 oracle) itself sits from fp64 on this ill-conditioned backward pass
             names = [n for n, _ in type(oracle).layout()[0]]
-            worst = 0.0
-            for n, g in zip(names, ro["grads"][:len(names)]):
-                # oracle grads include the L2 term; ours folds it into the optimizer (wd * theta)
+            bn_names = [n for n, _ in type(oracle).layout()[1]]
+            all_names = names + [n + "/" + l for n in bn_names for l in ("gamma", "beta")]
+            ours = []
+            for n in all_names:
                 v = rt.graph.vars[n]
                 mult = sum(1 for w in net.conv_weights if w is v)
-                ours = v.grad.cpu().double() + 1e-4 * mult * torch.tensor(P[n]).double()
-                worst = max(worst, rel_err(ours, g))
-            print("  worst weight-gradient rel err %.3e" % worst)
-            assert worst <= 2e-3
+                ours.append(v.grad.cpu().double() + 1e-4 * mult * torch.tensor(P[n]).double())
+            _grad_report(all_names, ours, ro["grads"], g64)
     ref = oracle.ps.to_numpy()
     got = rt.state_dict()
     worst, wname = 0.0, None
@@ -107,6 +111,20 @@ def test_config2_segmenter_train_step(backend):
     reg = net.regularizer_loss()
     assert abs(reg - float(oracle.losses(oracle.forward(x, 1.0, False)["logits"], y)[1])) <= 1e-3 * abs(reg)
     rt.set_conv_backend("auto")
+
+
+def _grad_report(names, ours, g32, g64, slack=4.0, floor=2e-3):
+    wp = wo = 0.0
+    for n, a, b32, b64 in zip(names, ours, g32, g64):
+        if float(b64.abs().max()) == 0.0:
+            assert float(a.abs().max()) == 0.0, n
+            continue
+        ep, eo = l2_err(a, b64), l2_err(b32, b64)
+        if ep > max(floor, slack * eo):
+            print("  grad %-40s l2 err %.3e (fp32 oracle %.3e)" % (n, ep, eo))
+        wp, wo = max(wp, ep), max(wo, eo)
+    print("  worst gradient l2 err vs fp64 oracle: ours %.3e, fp32 oracle %.3e" % (wp, wo))
+    assert wp <= slack * wo + floor, (wp, wo)
 
 
 def _adv_pair(backend, lam, phase):
@@ -133,7 +151,36 @@ def _adv_pair(backend, lam, phase):
     rt.load_state_dict(P)
     trainer = adv.Trainer(net, num_cls=5, batch_size=B, opt_kwargs={"learning_rate": 3e-4}, train_config=tc)
     oracle = OracleAdversarial(P, B, lambda_mask_loss=lam, dis_sub_iter=3, gen_sub_iter=1, critic_keep_prob=1.0)
+    oracle.o64 = OracleAdversarial(P, B, dtype=torch.float64, lambda_mask_loss=lam, dis_sub_iter=3, gen_sub_iter=1, critic_keep_prob=1.0)
     return net, trainer, oracle
+
+
+def _compare_grads(rt, oracle, which, g32, g64):
+    """first-step gradients of an adversarial step, variable by variable (the optimizer's L2 term is folded into its
+    kernel on our side: add wd*theta before comparing)"""
+    if which == "d":
+        names = oracle.cls_w + [n + "/" + l for n in oracle.cls_bn for l in ("gamma", "beta")]
+        wd = {n: oracle.gan_reg * oracle.miu_dis * 2.0 / oracle.dis_sub_iter * (1.0 if n.startswith("cls_scope") else oracle.lam)
+              for n in oracle.cls_w}
+    else:
+        names = oracle.adapt_w + [n + "/" + l for n in oracle.adapt_bn for l in ("gamma", "beta")]
+        wd = {n: oracle.gan_reg * oracle.miu_gen / oracle.gen_sub_iter for n in oracle.adapt_w}
+    ours = []
+    for n in names:
+        a = rt.graph.vars[n].grad.cpu().double()
+        if n in wd:
+            a = a + wd[n] * PRE[n].double()
+        ours.append(a)
+    _grad_report(names, ours, g32, g64)
+
+
+PRE = {}
+
+
+def _snapshot(rt):
+    PRE.clear()
+    for n in rt.graph.order:
+        PRE[n] = rt.graph.vars[n].detach().cpu().clone()
 
 
 def _compare_state(rt, oracle, tol, only=None):
@@ -157,8 +204,11 @@ def test_config3_discriminator_pretrain_step(backend):
     net, trainer, oracle = _adv_pair(backend, 0, "pre-train")
     mr, ct = synthetic_images(B, 1234), synthetic_images(B, 4321, 0.3, 0.8)
     for step in range(2):
+        _snapshot(rt)
         ro = oracle.d_step(mr, ct, keep_prob=1.0)
         terms = trainer.d_step(mr.to(DEV), ct.to(DEV), keep_prob=1.0)
+        if step == 0:
+            _compare_grads(rt, oracle, "d", ro["grads"], oracle.o64.d_step(mr.double(), ct.double(), keep_prob=1.0)["grads"])
         got = trainer.loss_value(terms)
         print("  step %d dis_loss %.6e (oracle %.6e)" % (step, got, ro["dis_loss"]))
         assert abs(got - ro["dis_loss"]) <= 1e-3 * max(abs(ro["dis_loss"]), 2e-3 * float(ro["mr_cls"].abs().max()))
@@ -173,13 +223,17 @@ def test_config4_joint_adversarial_step(backend):
     from oracle.pnp_graphs import synthetic_images
     net, trainer, oracle = _adv_pair(backend, 0.3, "train-gan")
     mr, ct = synthetic_images(B, 1234), synthetic_images(B, 4321, 0.3, 0.8)
+    _snapshot(rt)
     ro = oracle.d_step(mr, ct, keep_prob=1.0)
     terms = trainer.d_step(mr.to(DEV), ct.to(DEV), keep_prob=1.0)
+    _compare_grads(rt, oracle, "d", ro["grads"], oracle.o64.d_step(mr.double(), ct.double(), keep_prob=1.0)["grads"])
     got = trainer.loss_value(terms)
     print("  dis_loss %.6e (oracle %.6e)" % (got, ro["dis_loss"]))
     assert abs(got - ro["dis_loss"]) <= 1e-3 * max(abs(ro["dis_loss"]), 2e-3 * float(ro["mr_cls"].abs().max()))
+    _snapshot(rt)
     rg = oracle.g_step(ct, keep_prob=1.0)
     terms = trainer.g_step(ct.to(DEV), keep_prob=1.0)
+    _compare_grads(rt, oracle, "g", rg["grads"], oracle.o64.g_step(ct.double(), keep_prob=1.0)["grads"])
     got = trainer.loss_value(terms)
     print("  gen_loss %.6e (oracle %.6e)" % (got, rg["gen_loss"]))
     assert abs(got - rg["gen_loss"]) <= 1e-3 * max(abs(rg["gen_loss"]), 2e-3 * float(rg["ct_cls"].abs().max()))
