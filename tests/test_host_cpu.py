@@ -1,0 +1,181 @@
+"""CPU-only tests of the host layer: the C-ABI library loads and exports every symbol include/pnp_b200.h declares
+(no compute calls -- there is no GPU here), the TF-style variable registry reproduces the reference's checkpoint
+naming contract, entry-point configuration mirrors train_gan.py, error behaviour of the layers.py surface, arena layout,
+and the world_size-2 data-parallel path over gloo."""
+import ctypes
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import pnp_b200
+    from pnp_b200 import _C
+    hdr = open(os.path.join(ROOT, "include", "pnp_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(pnp_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 40
+    lib = ctypes.CDLL(_C.LIB_PATH)
+    missing = [n for n in declared if not hasattr(lib, n)]
+    assert not missing, missing
+    # the ctypes table mirrors the header one to one
+    bound = set(_C.SIGNATURES) | {"pnp_error_string", "pnp_version", "pnp_tc_available"}
+    assert set(declared) == bound, (set(declared) ^ bound)
+    assert _C.lib.pnp_version() >= 100
+    assert _C.lib.pnp_error_string(100002).decode().startswith("pnp: unsupported")
+    assert _C.lib.pnp_tc_available() == 0          # no device in this container
+
+
+def test_no_cpu_fallback_product_does_not_import_oracle():
+    """the product path must never route through the oracle (or any CPU fallback)"""
+    pkg = os.path.join(ROOT, "medical-cross-modality-domain-adaptation_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+            assert "oracle." not in src, fn
+
+
+def test_variable_names_follow_reference_checkpoint_contract():
+    import pnp_b200
+    from pnp_b200 import runtime as rt, source_segmenter as seg, adversarial as adv
+    from pnp_b200.train_gan import configure
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_var_names.json")))
+    net = seg.Full_DRN(channels=3, n_class=5, batch_size=2, cost_kwargs={"cross_flag": True, "miu_cross": 1.0, "miu_dice": 1.0})
+    names = set(rt.graph.order)
+    assert set(gold["old_bn_list"]) <= names
+    assert len(names) == 33 + 120
+    # L2 list quirk of source_segmenter.py:132-135: wr4_4 twice, wr4_3 never
+    v = rt.graph.vars
+    assert sum(1 for w in net.conv_weights if w is v["group_4/Variable_3"]) == 2
+    assert sum(1 for w in net.conv_weights if w is v["group_4/Variable_2"]) == 0
+    ck, nc, tc = configure("train-gan")
+    anet = adv.Full_DRN(channels=3, n_class=5, batch_size=2, cost_kwargs=ck, network_config=nc)
+    names = set(rt.graph.order)
+    for key in ("half_zip_mri_vars", "half_zip_ct_vars"):
+        assert not [n for n in gold[key] if n not in names], key
+    leafs = set(n.split("/", 1)[1] for n in names if "/" in n)
+    assert not [n for n in gold["pred_bn_list"] if n not in leafs]
+    # adversarial.py:478-501: membership by name substring
+    assert all("cls" in x.pnp_name for x in anet.cls_vars) and len(anet.cls_vars) == 26 + 24 * 4
+    assert all("adapt" in x.pnp_name for x in anet.adapt_vars) and len(anet.adapt_vars) == 21 + 20 * 4
+    assert len(anet.cls_weights) == 2 * len(anet.cls_weights_unique)     # appended on both create_classifier calls
+    tr = adv.Trainer(anet, num_cls=5, batch_size=2, opt_kwargs={"learning_rate": 3e-4}, train_config=tc)
+    # clip_op: exactly the cls vars whose name contains "Variable"
+    clipped = [x.pnp_name for x, c in zip(tr.d_vars, tr.dis_optimizer.seg_clip.tolist()) if c > 0]
+    assert clipped and all("Variable" in n for n in clipped) and len(clipped) == 26
+    assert all(abs(c - 0.03) < 1e-9 for c in tr.dis_optimizer.seg_clip.tolist() if c > 0)
+    # arena: every variable is a view of the flat arena, 1024-float aligned
+    for x, (o, n) in zip(tr.d_vars, tr.d_arena.offsets):
+        assert o % 1024 == 0 and x.data_ptr() == tr.d_arena.theta.data_ptr() + 4 * o and x.grad.data_ptr() == tr.d_arena.grad.data_ptr() + 4 * o
+    # weight decay = gradient of dis_reg / dis_sub_iter (critic weights counted twice), lambda-scaled for the mask critic
+    wd = dict(zip([x.pnp_name for x in tr.d_vars], tr.dis_optimizer.seg_wd.tolist()))
+    base = 1e-4 * 0.002 * 2 / tc["dis_sub_iter"]
+    assert abs(wd["cls_scope/cls_1/Variable"] - base) < 1e-12 and abs(wd["mask_cls_scope/mask_cls_1/Variable"] - 0.3 * base) < 1e-12
+    assert wd["cls_scope/cls_1/cls_1_1/gamma"] == 0.0
+
+
+def test_scope_registry_semantics():
+    import pnp_b200
+    from pnp_b200 import runtime as rt, layers as L
+    rt.reset_default_graph()
+    with rt.variable_scope("group_1"):
+        a = L.weight_variable([3, 3, 3, 16])
+        b = L.weight_variable([3, 3, 16, 16])
+        c = L.sharable_weight_variable([3, 3, 16, 16], name="Variable_7")
+        c2 = L.sharable_weight_variable([3, 3, 16, 16], name="Variable_7")
+    assert (a.pnp_name, b.pnp_name, c.pnp_name) == ("group_1/Variable", "group_1/Variable_1", "group_1/Variable_7") and c is c2
+    bn1 = L.bn_variables(None, 8)
+    bn2 = L.bn_variables(None, 8)
+    assert bn1.gamma.pnp_name == "BatchNorm/gamma" and bn2.gamma.pnp_name == "BatchNorm_1/gamma"
+    assert float(bn1.gamma.sum()) == 8 and float(bn1.moving_var.sum()) == 8 and float(bn1.beta.abs().sum()) == 0
+    w = L.weight_variable([1000], stddev=0.01)
+    assert float(w.abs().max()) <= 0.02 + 1e-7        # truncated normal: |z| <= 2 sigma
+    assert float(L.bias_variable([4]).sum()) == pytest.approx(0.4)
+
+
+def test_train_gan_phase_configuration():
+    from pnp_b200.train_gan import configure
+    ck, nc, tc = configure("pre-train")
+    assert ck["lambda_mask_loss"] == 0 and nc["ct_front_trainable"] is False and tc["gen_interval"] == 0 and tc["dis_sub_iter"] == 1
+    assert tc["restore_from_baseline"] and tc["training_iters"] == 201 and tc["epochs"] == 100
+    ck, nc, tc = configure("train-gan")
+    assert ck["lambda_mask_loss"] == 0.3 and nc["ct_front_trainable"] is True and tc["dis_sub_iter"] == 20 and tc["gen_sub_iter"] == 1
+    assert tc["iter_upd_interval"] == 300 and tc["dis_sub_iter_inc"] == 1 and tc["lr_decay_factor"] == 0.98
+    ck, nc, tc = configure("fine-tune")
+    assert tc["dis_sub_iter"] == 30 and tc["lr_update"] is False
+    with pytest.raises(Exception, match="Please set a training phase!"):
+        configure(None)
+
+
+def test_layers_error_behaviour_without_a_gpu():
+    import pnp_b200
+    from pnp_b200 import layers as L, ops, functional as F
+    x = torch.zeros(2, 8, 8, 4)
+    w = torch.zeros(3, 3, 4, 4)
+    with pytest.raises(UnboundLocalError):          # layers.py:17-25 leaves conv_2d unbound for unknown padding strings
+        L.conv2d(x, w, 1.0, padding="REFLECT")
+    with pytest.raises(ValueError):
+        L.conv2d(x, w, 1.0, strides=[1, 2, 1, 1])
+    with pytest.raises(ValueError):
+        L.simple_concat2d(torch.zeros(2, 8, 8, 1), torch.zeros(2, 4, 8, 1))
+    assert L.simple_concat2d(torch.zeros(2, 8, 8, 1), torch.zeros(2, 8, 8, 3)).shape == (2, 8, 8, 4)
+    with pytest.raises(ValueError):
+        ops.PS(torch.zeros(2, 4, 4, 64), 8, n_channel=1, batch_size=3)
+    with pytest.raises(ValueError):
+        ops.PS(torch.zeros(1, 4, 5, 64), 8, n_channel=1, batch_size=1)
+    assert F.same_pad(256, 3, 2) == (0, 1) and F.same_pad(128, 5, 2) == (1, 2) and F.same_pad(16, 5, 4) == (0, 1)
+    g = F._geometry((2, 4, 4, 4), (3, 3, 4, 4), F.LayerCfg(stride=2, padding="SYMMETRIC"))
+    assert g[0] == 1 and (g[1].H, g[1].Ho, g[1].pad_t) == (6, 2, 0)
+
+
+def test_confusion_matrix_metrics_match_oracle():
+    from pnp_b200.lib import _dice, _jaccard, _label_decomp
+    from oracle import tf14_numpy as N
+    rng = np.random.RandomState(0)
+    lab, pred = rng.randint(0, 5, (2, 16, 16)), rng.randint(0, 5, (2, 16, 16))
+    cm = np.zeros((5, 5), np.int64)
+    np.add.at(cm, (lab.ravel(), pred.ravel()), 1)
+    y = N.label_decomp(5, lab)
+    assert np.array_equal(_label_decomp(5, lab), y)
+    d, arr = N.dice_eval(pred, y.astype(np.float64), 5)
+    assert np.allclose(_dice(cm), arr, atol=1e-6)
+    inter = np.diag(cm).astype(np.float64)
+    assert np.allclose(_jaccard(cm), inter / (cm.sum(0) + cm.sum(1) - inter))
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    import pnp_b200  # noqa: F401
+    from pnp_b200 import parallel
+    parallel.init_from_env(backend="gloo")
+    dp = parallel.DataParallel()
+    g = torch.full((2048,), float(rank + 1))
+    scale = dp.allreduce(g)
+    theta = torch.full((8,), float(rank))
+    dp.broadcast_params(theta)
+    out[rank] = (dp.world, dp.rank, scale, float(g[0]), float(theta[0]))
+    dp.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_data_parallel_gloo_world_size_2():
+    """one all-reduce over the flat gradient arena; the optimizer's grad_scale = 1/N turns the sum into the average of the
+    per-rank reference steps (SURVEY 8e parity definition)"""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+    for r in (0, 1):
+        world, rank, scale, gsum, th = out[r]
+        assert world == 2 and rank == r and scale == 0.5
+        assert gsum == 3.0 and gsum * scale == 1.5      # (1 + 2) / 2
+        assert th == 0.0                                # rank 0's parameters everywhere
