@@ -71,17 +71,26 @@ int pnp_conv2d_wgrad(const float* x, const float* dy, float* dw, const pnp_conv_
 int pnp_weight_transpose(const float* w, float* wT, int taps, int Cin, int Cout, void* stream);
 
 /* ---- convolution, tcgen05 + TMA tensor-core path (conv_tc.cu) ----------------------------------
- * Same math as pnp_conv2d_fwd for stride-1 convolutions with Cin % 64 == 0 and Cout % 64 == 0,
+ * Same math as pnp_conv2d_fwd for convolutions with Cin % 64 == 0 and Cout % 64 == 0 (any stride / dilation / kernel <= 5x5),
  * operands pre-split into bf16 planes (pnp_split_bf16); nterms = 3 gives fp32-grade results
  * (hi*hi + hi*lo + lo*hi), nterms = 1 is the plain bf16 path of BASELINE config 5. */
 int pnp_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long long n, void* stream);
-/* w HWIO fp32 -> planes [taps][Cout][Cin] bf16 (K-major B operand), optionally with the
- * taps flipped and Cin/Cout swapped (operand of the stride-1 dgrad) */
+/* w HWIO fp32 -> bf16 planes: for_dgrad == 0: [tap][Cout][Cin] (K-major B operand of the forward conv);
+ * for_dgrad != 0: [tap][Cin][Cout] (K-major B operand of the data gradient) */
 int pnp_split_weight_bf16(const float* w, uint16_t* hi, uint16_t* lo, int kh, int kw, int Cin, int Cout,
                           int for_dgrad, void* stream);
 int pnp_conv2d_tc_fwd(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo,
                       float* y, const pnp_conv_geom* g, int nterms, const pnp_dropout_cfg* drop,
                       int accumulate, double* bn_sum, double* bn_sumsq, void* stream);
+
+/* dx[B,H,W,Cin] (+)= conv^T(dy, w) on tcgen05.  g is the FORWARD geometry; stride s > 1 is decomposed into s*s
+ * stride-1 phase convolutions (no multiplications by the zeros a transposed convolution would insert). */
+int pnp_conv2d_tc_dgrad(const uint16_t* dy_hi, const uint16_t* dy_lo, const uint16_t* w_hi, const uint16_t* w_lo,
+                        float* dx, const pnp_conv_geom* g, int nterms, int accumulate, void* stream);
+/* dw[kh][kw][Cin][Cout] += x (*) dy on tcgen05 (both operands MN-major straight from the NHWC planes; pixel range split
+ * across CTAs, fp32 vector atomics into dw).  x planes are the (mirror-padded) forward input. */
+int pnp_conv2d_tc_wgrad(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dy_hi, const uint16_t* dy_lo,
+                        float* dw, const pnp_conv_geom* g, int nterms, void* stream);
 
 /* ---- batch norm + activation (+ residual skip) (elementwise.cu) ----------------------------------
  * replaces tf.contrib.layers.batch_norm(decay .9, eps 1e-3) (layers.py:95-100), the activation

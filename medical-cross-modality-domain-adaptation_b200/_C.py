@@ -44,6 +44,8 @@ SIGNATURES = {
     "pnp_split_bf16": [P, P, P, c_ll, P],
     "pnp_split_weight_bf16": [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     "pnp_conv2d_tc_fwd": [P, P, P, P, P, _GEOM, c_int, _DROP, c_int, P, P, P],
+    "pnp_conv2d_tc_dgrad": [P, P, P, P, P, _GEOM, c_int, c_int, P],
+    "pnp_conv2d_tc_wgrad": [P, P, P, P, P, _GEOM, c_int, P],
     "pnp_bn_stats": [P, c_ll, c_int, P, P, P],
     "pnp_bn_finalize": [P, P, c_ll, c_int, P, P, P, P, c_int, P, P, P, P, P],
     "pnp_bn_act_apply": [P, P, P, P, c_int, c_int, c_int, P, c_ll, c_int, P],
@@ -90,11 +92,21 @@ lib.pnp_tc_available.restype = c_int
 launch_count = 0
 
 
+ERR_UNSUPPORTED = 100002
+
+
+class Unsupported(RuntimeError):
+    """the launcher declined this shape (PNP_ERR_UNSUPPORTED): callers pick the general kernel instead"""
+
+
 def call(name, *args):
     global launch_count
     rc = getattr(lib, name)(*args)
     if rc != 0:
-        raise RuntimeError("%s failed: [%d] %s" % (name, rc, lib.pnp_error_string(rc).decode()))
+        msg = "%s failed: [%d] %s" % (name, rc, lib.pnp_error_string(rc).decode())
+        if rc == ERR_UNSUPPORTED:
+            raise Unsupported(msg)
+        raise RuntimeError(msg)
     launch_count += 1
 
 

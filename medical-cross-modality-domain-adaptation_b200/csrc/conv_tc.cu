@@ -142,10 +142,16 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+constexpr int MAX_TAPS = 25;
 struct TcArgs {
-  int B, Ho, Wo, Cout;        // output tensor
+  int B, OH, OW, Cout;        // full output tensor [B, OH, OW, Cout]
+  int U, V;                   // extent of the tiled grid: output pixel (u, v) -> (u*out_mul + out_py, v*out_mul + out_px)
+  int out_mul, out_py, out_px;
+  int in_mul;                 // TMA coordinate of tile origin = origin * in_mul + tap offset (stride of a strided forward conv)
   int Cin;                    // GEMM K per tap
-  int kh, kw, dil, pad_t, pad_l;
+  int ntaps;
+  short tap_oy[MAX_TAPS], tap_ox[MAX_TAPS];
+  int tap_wrow[MAX_TAPS];     // first row of the tap's [N][K] slab in the weight plane
   int tw, th, tn;             // pixel tile
   int tiles_x, tiles_y, tiles_n;
   int accumulate;
@@ -192,7 +198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int n0 = blockIdx.y * BLOCK_N;
 
   const int kchunks = a.Cin / BLOCK_K;
-  const int num_kb = a.kh * a.kw * kchunks;
+  const int num_kb = a.ntaps * kchunks;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a_hi);
@@ -221,19 +227,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       for (int kb = 0; kb < num_kb; ++kb) {
         const int tap = kb / kchunks;
         const int kc = kb - tap * kchunks;
-        const int ky = tap / a.kw;
-        const int kx = tap - ky * a.kw;
         mbar_wait(smem_u32(&bars[STAGES + stage]), phase ^ 1);
         const uint32_t full = smem_u32(&bars[stage]);
         mbar_expect_tx(full, tx_bytes);
         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
-        const int cx = x0 + kx * a.dil - a.pad_l;
-        const int cy = y0 + ky * a.dil - a.pad_t;
+        const int cx = x0 * a.in_mul + a.tap_ox[tap];
+        const int cy = y0 * a.in_mul + a.tap_oy[tap];
+        const int wrow = a.tap_wrow[tap] + n0;
         tma_load_4d(smem_u32(st), &map_a_hi, full, kc * BLOCK_K, cx, cy, img0);
-        tma_load_2d(smem_u32(st + Cfg::NPLANES * A_TILE_BYTES), &map_b_hi, full, kc * BLOCK_K, tap * a.Cout + n0);
+        tma_load_2d(smem_u32(st + Cfg::NPLANES * A_TILE_BYTES), &map_b_hi, full, kc * BLOCK_K, wrow);
         if (NTERMS > 1) {
           tma_load_4d(smem_u32(st + A_TILE_BYTES), &map_a_lo, full, kc * BLOCK_K, cx, cy, img0);
-          tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES), &map_b_lo, full, kc * BLOCK_K, tap * a.Cout + n0);
+          tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES), &map_b_lo, full, kc * BLOCK_K, wrow);
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -282,9 +287,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int rem = m - ni * per_img;
     const int yy = rem / a.tw;
     const int xx = rem - yy * a.tw;
-    const int img = img0 + ni, oy = y0 + yy, ox = x0 + xx;
-    const bool valid = (ni < a.tn) && (img < a.B) && (oy < a.Ho) && (ox < a.Wo);
-    const long long pix = ((long long)img * a.Ho + oy) * a.Wo + ox;
+    const int img = img0 + ni, u = y0 + yy, v_ = x0 + xx;
+    const bool valid = (ni < a.tn) && (img < a.B) && (u < a.U) && (v_ < a.V);
+    const int oy = u * a.out_mul + a.out_py, ox = v_ * a.out_mul + a.out_px;
+    const long long pix = ((long long)img * a.OH + oy) * a.OW + ox;
     float* orow = out + pix * a.Cout + n0;
     const bool drop_on = a.drop.seed_ptr != nullptr;
     unsigned long long seed = 0ull;
@@ -387,7 +393,7 @@ split_bf16_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16
 }
 
 // w HWIO [taps][Cin][Cout] -> fwd : out[tap][co][ci]          (B operand rows = co, K = ci)
-//                             dgrad: out[taps-1-tap][ci][co]   (B operand rows = ci, K = co)
+//                             dgrad: out[tap][ci][co]          (B operand rows = ci, K = co)
 __global__ void __launch_bounds__(256)
 split_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int taps, int Cin,
                     int Cout, int for_dgrad) {
@@ -395,7 +401,7 @@ split_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi, uint
   const int tap = blockIdx.z;
   const float* src = w + (long long)tap * Cin * Cout;
   if (for_dgrad) {
-    long long obase = (long long)(taps - 1 - tap) * Cin * Cout;
+    long long obase = (long long)tap * Cin * Cout;
     int ci = blockIdx.y * 32 + threadIdx.y * 4;
     int co = blockIdx.x * 32 + threadIdx.x;
     for (int r = 0; r < 4; ++r) {
@@ -447,13 +453,197 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_act_map(CUtensorMap* m, const uint16_t* ptr, int B, int H, int W, int C, int tw, int th, int tn) {
+// ---------------------------------------------------------------------------------------------
+// wgrad on tcgen05:  dW[tap][ci][co] += sum_pixels x[pixel + tap offset][ci] * dy[pixel][co]
+//   GEMM per tap: M = ci (128 per CTA), N = co (BLOCK_N), K = pixels.  Both operands are *MN-major*: the very same NHWC
+//   TMA boxes {64 ch, tw, th, tn} as the forward pass (one 128-byte row per pixel = one K index, 64 channels = 64 M/N
+//   indices), two/four boxes side by side for 128/BLOCK_N channels (LBO = box size), 8-pixel swizzle atoms 1024 B apart (SBO).
+//   The pixel range is split across CTAs (gridDim.y); partial tiles are added to the fp32 gradient arena with vector atomics.
+// ---------------------------------------------------------------------------------------------
+constexpr int WG_PB = 64;                                  // pixels per pipeline stage
+constexpr int WG_BOX_BYTES = WG_PB * BLOCK_K * 2;          // one {64 ch x 64 px} box = 8 KB
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;       // distance between 64-element groups along M/N
+  d |= (uint64_t)(1024 >> 4) << 32;                        // distance between 8-row groups along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct WgArgs {
+  int B, Cin, Cout;
+  int ntaps;
+  short tap_oy[MAX_TAPS], tap_ox[MAX_TAPS];
+  int in_mul;
+  int tw, th, tn, tiles_x, tiles_y, tiles_n;
+  int num_pb, pb_per_split;
+  int mt, nt;
+  float* dw;
+};
+
+template <int BLOCK_N, int NTERMS>
+struct WgCfg {
+  static constexpr int NPLANES = (NTERMS == 1) ? 1 : 2;
+  static constexpr int A_BYTES = 2 * WG_BOX_BYTES;                       // 128 ci
+  static constexpr int B_BYTES = (BLOCK_N / 64) * WG_BOX_BYTES;
+  static constexpr int STAGE_BYTES = NPLANES * (A_BYTES + B_BYTES);
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+};
+
+template <int BLOCK_N, int NTERMS>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                     const __grid_constant__ CUtensorMap map_dy_hi, const __grid_constant__ CUtensorMap map_dy_lo, WgArgs a) {
+  using Cfg = WgCfg<BLOCK_N, NTERMS>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  int t = blockIdx.x;
+  const int ni = t % a.nt;
+  t /= a.nt;
+  const int mi = t % a.mt;
+  const int tap = t / a.mt;
+  const int ci0 = mi * 128, co0 = ni * BLOCK_N;
+  const int pb_begin = blockIdx.y * a.pb_per_split;
+  const int pb_end = min(a.num_pb, pb_begin + a.pb_per_split);
+  const int num_kb = pb_end - pb_begin;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_x_hi);
+    tma_prefetch_desc(&map_dy_hi);
+    if (NTERMS > 1) { tma_prefetch_desc(&map_x_lo); tma_prefetch_desc(&map_dy_lo); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&bars[s]), 1);
+      mbar_init(smem_u32(&bars[STAGES + s]), 1);
+    }
+    mbar_init(smem_u32(&bars[2 * STAGES]), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tcgen05_alloc(smem_u32(tmem_holder), Cfg::TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (num_kb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const int oy = a.tap_oy[tap], ox = a.tap_ox[tap];
+        for (int kb = 0; kb < num_kb; ++kb) {
+          int pb = pb_begin + kb;
+          const int txi = pb % a.tiles_x;
+          pb /= a.tiles_x;
+          const int tyi = pb % a.tiles_y;
+          const int tni = pb / a.tiles_y;
+          const int x0 = txi * a.tw, y0 = tyi * a.th, img0 = tni * a.tn;
+          mbar_wait(smem_u32(&bars[STAGES + stage]), phase ^ 1);
+          const uint32_t full = smem_u32(&bars[stage]);
+          mbar_expect_tx(full, Cfg::STAGE_BYTES);
+          uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+          const int cx = x0 * a.in_mul + ox, cy = y0 * a.in_mul + oy;
+#pragma unroll
+          for (int p = 0; p < Cfg::NPLANES; ++p) {
+            const CUtensorMap* mx = p ? &map_x_lo : &map_x_hi;
+            const CUtensorMap* md = p ? &map_dy_lo : &map_dy_hi;
+            uint8_t* sa = st + p * Cfg::A_BYTES;
+            uint8_t* sb = st + Cfg::NPLANES * Cfg::A_BYTES + p * Cfg::B_BYTES;
+            tma_load_4d(smem_u32(sa), mx, full, ci0, cx, cy, img0);
+            tma_load_4d(smem_u32(sa + WG_BOX_BYTES), mx, full, ci0 + 64, cx, cy, img0);   // beyond Cin: zero filled
+#pragma unroll
+            for (int g = 0; g < BLOCK_N / 64; ++g) tma_load_4d(smem_u32(sb + g * WG_BOX_BYTES), md, full, co0 + g * 64, x0, y0, img0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N) | (1u << 15) | (1u << 16);   // A and B MN-major
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&bars[stage]), phase);
+          tcgen05_fence_after();
+          const uint32_t st = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t a_hi = st, a_lo = st + Cfg::A_BYTES;
+          const uint32_t b_hi = st + Cfg::NPLANES * Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+#pragma unroll
+          for (int k = 0; k < WG_PB / UMMA_K; ++k) {
+            const uint32_t koff = k * (UMMA_K / 8) * 1024;       // 16 pixels = two 8-row swizzle atoms
+            const uint64_t da_hi = make_mnmajor_sw128_desc(a_hi + koff, WG_BOX_BYTES);
+            const uint64_t db_hi = make_mnmajor_sw128_desc(b_hi + koff, WG_BOX_BYTES);
+            if (NTERMS > 1) {
+              const uint64_t da_lo = make_mnmajor_sw128_desc(a_lo + koff, WG_BOX_BYTES);
+              const uint64_t db_lo = make_mnmajor_sw128_desc(b_lo + koff, WG_BOX_BYTES);
+              tcgen05_mma_bf16(tmem_base, da_lo, db_hi, idesc, (kb | k) != 0);
+              tcgen05_mma_bf16(tmem_base, da_hi, db_lo, idesc, 1);
+              tcgen05_mma_bf16(tmem_base, da_hi, db_hi, idesc, 1);
+            } else {
+              tcgen05_mma_bf16(tmem_base, da_hi, db_hi, idesc, (kb | k) != 0);
+            }
+          }
+          tcgen05_commit(smem_u32(&bars[STAGES + stage]));
+          if (kb == num_kb - 1) tcgen05_commit(smem_u32(&bars[2 * STAGES]));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else {
+      const int q = warp & 3;
+      const int m = q * 32 + lane;
+      const int ci = ci0 + m;
+      const bool valid = ci < a.Cin;
+      float* orow = a.dw + ((long long)tap * a.Cin + ci) * a.Cout + co0;
+      mbar_wait(smem_u32(&bars[2 * STAGES]), 0);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tcgen05_wait_ld();
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 v = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                   __uint_as_float(r[4 * i + 3]));
+            atomicAdd(reinterpret_cast<float4*>(orow + c0) + i, v);
+          }
+        }
+      }
+      tcgen05_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tcgen05_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps, tile selection, launches
+// ---------------------------------------------------------------------------------------------
+int make_act_map(CUtensorMap* m, const uint16_t* ptr, int B, int H, int W, int C, int tw, int th, int tn, int stride) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return PNP_ERR_DRIVER;
+  if (tw * stride > 256 || th * stride > 256 || tn > 256) return PNP_ERR_UNSUPPORTED;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // traversal stride: TMA loads ceil(box/stride) elements per dimension, i.e. every stride-th pixel (strided convolutions)
+  cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(tw * stride), (cuuint32_t)(th * stride), (cuuint32_t)tn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? PNP_OK : PNP_ERR_DRIVER;
@@ -471,6 +661,26 @@ int make_w_map(CUtensorMap* m, const uint16_t* ptr, long long rows, int K, int b
   return r == CUDA_SUCCESS ? PNP_OK : PNP_ERR_DRIVER;
 }
 
+// pixel tile of `rows` (128 for conv, 64 for wgrad) over a U x V grid; exact != 0 demands tw*th*tn == rows (reduction dim)
+int choose_tile(int U, int V, int B, int rows, int exact, int* tw, int* th, int* tn) {
+  if (V >= rows) {
+    if (V % rows != 0) return PNP_ERR_UNSUPPORTED;
+    *tw = rows; *th = 1; *tn = 1;
+    return PNP_OK;
+  }
+  *tw = V;
+  *th = rows / V;
+  if (*th > U) *th = U;
+  *tn = (*th == U) ? (rows / (*tw * *th)) : 1;
+  if (*tn < 1) *tn = 1;
+  if (exact) {
+    if ((*tw) * (*th) * (*tn) != rows || (U % *th) != 0) return PNP_ERR_UNSUPPORTED;
+  } else if (*tn > B) {
+    *tn = B;
+  }
+  return PNP_OK;
+}
+
 template <int BLOCK_N, int NTERMS>
 int launch_tc(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi, const CUtensorMap& mb_lo,
               float* y, const TcArgs& a, cudaStream_t s) {
@@ -486,6 +696,21 @@ int launch_tc(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensor
   return PNP_OK;
 }
 
+template <int BLOCK_N, int NTERMS>
+int launch_wg(const CUtensorMap& mx_hi, const CUtensorMap& mx_lo, const CUtensorMap& md_hi, const CUtensorMap& md_lo,
+              const WgArgs& a, int splits, cudaStream_t s) {
+  using Cfg = WgCfg<BLOCK_N, NTERMS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PNP_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BLOCK_N, NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(a.ntaps * a.mt * a.nt, splits);
+  conv_wgrad_tc_kernel<BLOCK_N, NTERMS><<<grid, 192, Cfg::SMEM_BYTES, s>>>(mx_hi, mx_lo, md_hi, md_lo, a);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
 PnpDropout make_drop(const pnp_dropout_cfg* d) {
   PnpDropout r;
   r.seed_ptr = nullptr; r.stream = 0; r.keep = 1.f; r.inv_keep = 1.f;
@@ -493,6 +718,43 @@ PnpDropout make_drop(const pnp_dropout_cfg* d) {
     r.seed_ptr = d->seed_ptr; r.stream = d->stream; r.keep = d->keep; r.inv_keep = 1.0f / d->keep;
   }
   return r;
+}
+
+// one launch of the generalized tap-table convolution: A planes [B, AH, AW, Cin] -> out [B, OH, OW, Cout]
+int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_stride, const uint16_t* w_hi, const uint16_t* w_lo,
+           long long w_rows, float* out, TcArgs& a, int nterms, cudaStream_t s) {
+  int rc = choose_tile(a.U, a.V, a.B, BLOCK_M, 0, &a.tw, &a.th, &a.tn);
+  if (rc) return rc;
+  a.tiles_x = a.V / a.tw;
+  if (a.V % a.tw != 0) return PNP_ERR_UNSUPPORTED;
+  a.tiles_y = pnp_cdiv(a.U, a.th);
+  a.tiles_n = pnp_cdiv(a.B, a.tn);
+  const int block_n = (a.Cout % 128 == 0) ? 128 : 64;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  rc = make_act_map(&ma_hi, a_hi, a.B, AH, AW, a.Cin, a.tw, a.th, a.tn, a_stride);
+  if (rc) return rc;
+  rc = make_w_map(&mb_hi, w_hi, w_rows, a.Cin, block_n);
+  if (rc) return rc;
+  if (nterms == 3) {
+    rc = make_act_map(&ma_lo, a_lo, a.B, AH, AW, a.Cin, a.tw, a.th, a.tn, a_stride);
+    if (rc) return rc;
+    rc = make_w_map(&mb_lo, w_lo, w_rows, a.Cin, block_n);
+    if (rc) return rc;
+  } else {
+    ma_lo = ma_hi;
+    mb_lo = mb_hi;
+  }
+  if (block_n == 128) {
+    if (nterms == 3) return launch_tc<128, 3>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
+    return launch_tc<128, 1>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
+  }
+  if (nterms == 3) return launch_tc<64, 3>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
+  return launch_tc<64, 1>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
+}
+
+bool tc_geom_ok(const pnp_conv_geom* g) {
+  return g && g->B > 0 && g->H > 0 && g->W > 0 && g->Ho > 0 && g->Wo > 0 && g->kh > 0 && g->kw > 0 && g->dil > 0 && g->stride > 0 &&
+         g->kh * g->kw <= MAX_TAPS && g->Cin % 64 == 0 && g->Cout % 64 == 0;
 }
 
 }  // namespace
@@ -531,50 +793,125 @@ extern "C" int pnp_conv2d_tc_fwd(const uint16_t* x_hi, const uint16_t* x_lo, con
   if (nterms != 1 && nterms != 3) return PNP_ERR_BAD_ARG;
   if (nterms == 3 && (!x_lo || !w_lo)) return PNP_ERR_BAD_ARG;
   if ((bn_sum == nullptr) != (bn_sumsq == nullptr)) return PNP_ERR_BAD_ARG;
-  if (g->stride != 1 || g->Cin % 64 != 0 || g->Cout % 64 != 0) return PNP_ERR_UNSUPPORTED;
-  if (g->B <= 0 || g->H <= 0 || g->W <= 0 || g->Ho <= 0 || g->Wo <= 0 || g->kh <= 0 || g->kw <= 0 || g->dil <= 0)
-    return PNP_ERR_BAD_ARG;
+  if (!tc_geom_ok(g)) return PNP_ERR_UNSUPPORTED;
   TcArgs a;
-  a.B = g->B; a.Ho = g->Ho; a.Wo = g->Wo; a.Cout = g->Cout; a.Cin = g->Cin;
-  a.kh = g->kh; a.kw = g->kw; a.dil = g->dil; a.pad_t = g->pad_t; a.pad_l = g->pad_l;
-  if (g->Wo >= 128) {
-    if (g->Wo % 128 != 0) return PNP_ERR_UNSUPPORTED;
-    a.tw = 128; a.th = 1; a.tn = 1;
-  } else {
-    a.tw = g->Wo;
-    a.th = 128 / a.tw;
-    if (a.th > g->Ho) a.th = g->Ho;
-    a.tn = (a.th == g->Ho) ? (128 / (a.tw * a.th)) : 1;
-    if (a.tn < 1) a.tn = 1;
-    if (a.tn > g->B) a.tn = g->B;
-  }
-  a.tiles_x = g->Wo / a.tw;
-  a.tiles_y = pnp_cdiv(g->Ho, a.th);
-  a.tiles_n = pnp_cdiv(g->B, a.tn);
+  a.B = g->B; a.OH = g->Ho; a.OW = g->Wo; a.Cout = g->Cout; a.Cin = g->Cin;
+  a.U = g->Ho; a.V = g->Wo; a.out_mul = 1; a.out_py = 0; a.out_px = 0; a.in_mul = g->stride;
+  a.ntaps = g->kh * g->kw;
+  for (int ky = 0; ky < g->kh; ++ky)
+    for (int kx = 0; kx < g->kw; ++kx) {
+      int t = ky * g->kw + kx;
+      a.tap_oy[t] = (short)(ky * g->dil - g->pad_t);
+      a.tap_ox[t] = (short)(kx * g->dil - g->pad_l);
+      a.tap_wrow[t] = t * g->Cout;
+    }
   a.accumulate = accumulate;
   a.drop = make_drop(drop);
   a.bn_sum = bn_sum;
   a.bn_sumsq = bn_sumsq;
-  const int block_n = (g->Cout % 128 == 0) ? 128 : 64;
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  int rc = make_act_map(&ma_hi, x_hi, g->B, g->H, g->W, g->Cin, a.tw, a.th, a.tn);
+  return run_tc(x_hi, x_lo, g->H, g->W, g->stride, w_hi, w_lo, (long long)g->kh * g->kw * g->Cout, y, a, nterms, (cudaStream_t)stream);
+}
+
+// dx[B,H,W,Cin] (+)= conv^T(dy, w): `g` is the FORWARD geometry, dy planes [B,Ho,Wo,Cout], weight planes from
+// pnp_split_weight_bf16(for_dgrad = 1) = [tap][Cin][Cout].  stride 1: one launch; stride s: s*s phase launches, each a
+// stride-1 convolution over dy with the taps whose offset is divisible by s, writing every s-th pixel of dx.
+extern "C" int pnp_conv2d_tc_dgrad(const uint16_t* dy_hi, const uint16_t* dy_lo, const uint16_t* w_hi, const uint16_t* w_lo,
+                                   float* dx, const pnp_conv_geom* g, int nterms, int accumulate, void* stream) {
+  if (!g || !dy_hi || !w_hi || !dx) return PNP_ERR_BAD_ARG;
+  if (nterms != 1 && nterms != 3) return PNP_ERR_BAD_ARG;
+  if (nterms == 3 && (!dy_lo || !w_lo)) return PNP_ERR_BAD_ARG;
+  if (!tc_geom_ok(g)) return PNP_ERR_UNSUPPORTED;
+  const int s = g->stride;
+  // every phase needs at least one tap per axis, otherwise part of dx would stay unwritten
+  for (int p = 0; p < s; ++p) {
+    bool hy = false, hx = false;
+    for (int k = 0; k < g->kh; ++k) hy = hy || ((p + g->pad_t - k * g->dil) % s == 0);
+    for (int k = 0; k < g->kw; ++k) hx = hx || ((p + g->pad_l - k * g->dil) % s == 0);
+    if (!hy || !hx) return PNP_ERR_UNSUPPORTED;
+  }
+  for (int py = 0; py < s; ++py)
+    for (int px = 0; px < s; ++px) {
+      TcArgs a;
+      a.B = g->B; a.OH = g->H; a.OW = g->W; a.Cout = g->Cin; a.Cin = g->Cout;
+      a.U = (g->H - py + s - 1) / s;
+      a.V = (g->W - px + s - 1) / s;
+      if (a.U <= 0 || a.V <= 0) continue;
+      a.out_mul = s; a.out_py = py; a.out_px = px; a.in_mul = 1;
+      int nt = 0;
+      for (int ky = 0; ky < g->kh; ++ky) {
+        int ny = py + g->pad_t - ky * g->dil;
+        if (ny % s != 0) continue;
+        for (int kx = 0; kx < g->kw; ++kx) {
+          int nx = px + g->pad_l - kx * g->dil;
+          if (nx % s != 0) continue;
+          a.tap_oy[nt] = (short)(ny / s);
+          a.tap_ox[nt] = (short)(nx / s);
+          a.tap_wrow[nt] = (ky * g->kw + kx) * g->Cin;
+          ++nt;
+        }
+      }
+      a.ntaps = nt;
+      a.accumulate = accumulate;
+      a.drop = make_drop(nullptr);
+      a.bn_sum = nullptr;
+      a.bn_sumsq = nullptr;
+      int rc = run_tc(dy_hi, dy_lo, g->Ho, g->Wo, 1, w_hi, w_lo, (long long)g->kh * g->kw * g->Cin, dx, a, nterms, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+  return PNP_OK;
+}
+
+// dw[kh][kw][Cin][Cout] += x (*) dy on tcgen05 (x planes [B,H,W,Cin] -- the mirror-padded input for SYMMETRIC convs)
+extern "C" int pnp_conv2d_tc_wgrad(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dy_hi, const uint16_t* dy_lo,
+                                   float* dw, const pnp_conv_geom* g, int nterms, void* stream) {
+  if (!g || !x_hi || !dy_hi || !dw) return PNP_ERR_BAD_ARG;
+  if (nterms != 1 && nterms != 3) return PNP_ERR_BAD_ARG;
+  if (nterms == 3 && (!x_lo || !dy_lo)) return PNP_ERR_BAD_ARG;
+  if (!tc_geom_ok(g)) return PNP_ERR_UNSUPPORTED;
+  WgArgs a;
+  a.B = g->B; a.Cin = g->Cin; a.Cout = g->Cout; a.in_mul = g->stride; a.dw = dw;
+  a.ntaps = g->kh * g->kw;
+  for (int ky = 0; ky < g->kh; ++ky)
+    for (int kx = 0; kx < g->kw; ++kx) {
+      a.tap_oy[ky * g->kw + kx] = (short)(ky * g->dil - g->pad_t);
+      a.tap_ox[ky * g->kw + kx] = (short)(kx * g->dil - g->pad_l);
+    }
+  int rc = choose_tile(g->Ho, g->Wo, g->B, WG_PB, 1, &a.tw, &a.th, &a.tn);
   if (rc) return rc;
-  rc = make_w_map(&mb_hi, w_hi, (long long)g->kh * g->kw * g->Cout, g->Cin, block_n);
+  a.tiles_x = g->Wo / a.tw;
+  a.tiles_y = g->Ho / a.th;
+  a.tiles_n = pnp_cdiv(g->B, a.tn);
+  a.num_pb = a.tiles_x * a.tiles_y * a.tiles_n;
+  const int block_n = (g->Cout % 128 == 0) ? 128 : 64;
+  a.mt = pnp_cdiv(g->Cin, 128);
+  a.nt = g->Cout / block_n;
+  const int tiles = a.ntaps * a.mt * a.nt;
+  int splits = (2 * 148 + tiles - 1) / tiles;
+  int max_splits = a.num_pb / 4;
+  if (max_splits < 1) max_splits = 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  a.pb_per_split = pnp_cdiv(a.num_pb, splits);
+  splits = pnp_cdiv(a.num_pb, a.pb_per_split);
+  CUtensorMap mx_hi, mx_lo, md_hi, md_lo;
+  rc = make_act_map(&mx_hi, x_hi, g->B, g->H, g->W, g->Cin, a.tw, a.th, a.tn, g->stride);
+  if (rc) return rc;
+  rc = make_act_map(&md_hi, dy_hi, g->B, g->Ho, g->Wo, g->Cout, a.tw, a.th, a.tn, 1);
   if (rc) return rc;
   if (nterms == 3) {
-    rc = make_act_map(&ma_lo, x_lo, g->B, g->H, g->W, g->Cin, a.tw, a.th, a.tn);
+    rc = make_act_map(&mx_lo, x_lo, g->B, g->H, g->W, g->Cin, a.tw, a.th, a.tn, g->stride);
     if (rc) return rc;
-    rc = make_w_map(&mb_lo, w_lo, (long long)g->kh * g->kw * g->Cout, g->Cin, block_n);
+    rc = make_act_map(&md_lo, dy_lo, g->B, g->Ho, g->Wo, g->Cout, a.tw, a.th, a.tn, 1);
     if (rc) return rc;
   } else {
-    ma_lo = ma_hi;
-    mb_lo = mb_hi;
+    mx_lo = mx_hi;
+    md_lo = md_hi;
   }
   cudaStream_t s = (cudaStream_t)stream;
   if (block_n == 128) {
-    if (nterms == 3) return launch_tc<128, 3>(ma_hi, ma_lo, mb_hi, mb_lo, y, a, s);
-    return launch_tc<128, 1>(ma_hi, ma_lo, mb_hi, mb_lo, y, a, s);
+    if (nterms == 3) return launch_wg<128, 3>(mx_hi, mx_lo, md_hi, md_lo, a, splits, s);
+    return launch_wg<128, 1>(mx_hi, mx_lo, md_hi, md_lo, a, splits, s);
   }
-  if (nterms == 3) return launch_tc<64, 3>(ma_hi, ma_lo, mb_hi, mb_lo, y, a, s);
-  return launch_tc<64, 1>(ma_hi, ma_lo, mb_hi, mb_lo, y, a, s);
+  if (nterms == 3) return launch_wg<64, 3>(mx_hi, mx_lo, md_hi, md_lo, a, splits, s);
+  return launch_wg<64, 1>(mx_hi, mx_lo, md_hi, md_lo, a, splits, s);
 }

@@ -8,6 +8,7 @@ of a flat gradient arena, see optim.py); the Functions return None for them so a
 """
 import ctypes
 import math
+import os
 import torch
 
 from . import _C
@@ -24,13 +25,13 @@ PROFILE = None
 DEBUG_HOOK = None
 
 
-def _tc_launch(tag, flops, *args):
+def _tc_launch(tag, flops, name, *args):
     if PROFILE is None:
-        call("pnp_conv2d_tc_fwd", *args)
+        call(name, *args)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    call("pnp_conv2d_tc_fwd", *args)
+    call(name, *args)
     e1.record()
     PROFILE.append((e0, e1, flops, tag))
 
@@ -76,8 +77,17 @@ def _tc_mode():
     return 1 if b == "tc1" else 3
 
 
-def _tc_ok(cin, cout, stride, wo):
-    return stride == 1 and cin % 64 == 0 and cout % 64 == 0 and (wo < 128 or wo % 128 == 0)
+# tcgen05 wgrad can be switched off separately (PNP_TC_WGRAD=0) for A/B measurements
+TC_WGRAD = os.environ.get("PNP_TC_WGRAD", "1") != "0"
+_tc_declined = set()     # (kind, geometry) the tcgen05 launchers returned PNP_ERR_UNSUPPORTED for -> general SIMT kernel
+
+
+def _gkey(kind, g):
+    return (kind, g.B, g.H, g.W, g.Cin, g.Ho, g.Wo, g.Cout, g.kh, g.kw, g.stride, g.dil, g.pad_t, g.pad_l)
+
+
+def _tc_candidate(kind, g):
+    return g.Cin % 64 == 0 and g.Cout % 64 == 0 and g.kh * g.kw <= 25 and _gkey(kind, g) not in _tc_declined
 
 
 def split_bf16(x, nterms):
@@ -114,46 +124,67 @@ def _weight_T(W):
     return wT
 
 
-def conv_fwd_raw(xp, W, geom, drop=None, stats=None):
-    """z = conv(xp, W) [* dropout]; xp already mirror-padded if needed.  stats=(sum,sumsq) f64 buffers
-    are filled only when the tcgen05 path can fuse them; returns (z, stats_done)."""
+def _conv_flops(g):
+    return 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.kh * g.kw * g.Cin
+
+
+def conv_fwd_raw(xp, W, geom, drop=None, stats=None, keep_planes=False):
+    """z = conv(xp, W) [* dropout]; xp already mirror-padded if needed.  stats=(sum,sumsq) f64 buffers are filled only
+    when the tcgen05 path can fuse them.  Returns (z, stats_done, (hi, lo) bf16 planes of xp or None)."""
     z = torch.empty(geom.B, geom.Ho, geom.Wo, geom.Cout, dtype=torch.float32, device=xp.device)
     nt = _tc_mode()
-    if nt and _tc_ok(geom.Cin, geom.Cout, geom.stride, geom.Wo):
-        hi, lo = split_bf16(xp, nt)
+    if nt and _tc_candidate("fwd", geom):
+        planes = split_bf16(xp, nt)
         whi, wlo = _weight_planes(W, False, nt)
         fuse = stats is not None and FUSE_BN_STATS
-        flops = 2.0 * geom.B * geom.Ho * geom.Wo * geom.Cout * geom.kh * geom.kw * geom.Cin
-        _tc_launch("fwd", flops, ptr(hi), ptr(lo), ptr(whi), ptr(wlo), ptr(z), ctypes.byref(geom), nt, _byref(drop), 0,
-                   ptr(stats[0]) if fuse else None, ptr(stats[1]) if fuse else None, rt.stream())
-        return z, fuse
+        try:
+            _tc_launch("fwd", _conv_flops(geom), "pnp_conv2d_tc_fwd", ptr(planes[0]), ptr(planes[1]), ptr(whi), ptr(wlo), ptr(z),
+                       ctypes.byref(geom), nt, _byref(drop), 0, ptr(stats[0]) if fuse else None, ptr(stats[1]) if fuse else None,
+                       rt.stream())
+            return z, fuse, (planes if keep_planes else None)
+        except _C.Unsupported:
+            _tc_declined.add(_gkey("fwd", geom))
     call("pnp_conv2d_fwd", ptr(xp), ptr(W), ptr(z), ctypes.byref(geom), _byref(drop), 0, rt.stream())
-    return z, False
+    return z, False, None
 
 
-def conv_dgrad_raw(dz, W, geom, into=None):
+def conv_dgrad_raw(dz, W, geom, into=None, dz_planes=None):
     """dx[B,H,W,Cin] = conv^T(dz, W); if `into` is given the result is accumulated into it."""
     acc = 1 if into is not None else 0
     dx = into if into is not None else torch.empty(geom.B, geom.H, geom.W, geom.Cin, dtype=torch.float32, device=dz.device)
     nt = _tc_mode()
-    if nt and _tc_ok(geom.Cout, geom.Cin, geom.stride, geom.W):
-        g2 = ConvGeom(geom.B, geom.Ho, geom.Wo, geom.Cout, geom.H, geom.W, geom.Cin, geom.kh, geom.kw, 1, geom.dil,
-                      (geom.kh - 1) * geom.dil - geom.pad_t, (geom.kw - 1) * geom.dil - geom.pad_l)
-        hi, lo = split_bf16(dz, nt)
+    if nt and _tc_candidate("dgrad", geom):
+        hi, lo = dz_planes if dz_planes is not None else split_bf16(dz, nt)
         whi, wlo = _weight_planes(W, True, nt)
-        flops = 2.0 * geom.B * geom.Ho * geom.Wo * geom.Cout * geom.kh * geom.kw * geom.Cin
-        _tc_launch("dgrad", flops, ptr(hi), ptr(lo), ptr(whi), ptr(wlo), ptr(dx), ctypes.byref(g2), nt, None, acc, None, None,
-                   rt.stream())
-        return dx
+        try:
+            _tc_launch("dgrad", _conv_flops(geom), "pnp_conv2d_tc_dgrad", ptr(hi), ptr(lo), ptr(whi), ptr(wlo), ptr(dx),
+                       ctypes.byref(geom), nt, acc, rt.stream())
+            return dx
+        except _C.Unsupported:
+            _tc_declined.add(_gkey("dgrad", geom))
     call("pnp_conv2d_dgrad", ptr(dz), ptr(_weight_T(W)), ptr(dx), ctypes.byref(geom), acc, rt.stream())
     return dx
 
 
-def conv_wgrad_raw(xp, dz, W, geom):
+def conv_wgrad_raw(xp, dz, W, geom, x_planes=None, dz_planes=None):
     if W.grad is None:
         W.grad = torch.empty_like(W)
         call("pnp_fill", ptr(W.grad), 0.0, W.numel(), rt.stream())
+    nt = _tc_mode()
+    if nt and TC_WGRAD and _tc_candidate("wgrad", geom):
+        xh, xl = x_planes if x_planes is not None else split_bf16(xp, nt)
+        dh, dl = dz_planes if dz_planes is not None else split_bf16(dz, nt)
+        try:
+            _tc_launch("wgrad", _conv_flops(geom), "pnp_conv2d_tc_wgrad", ptr(xh), ptr(xl), ptr(dh), ptr(dl), ptr(W.grad),
+                       ctypes.byref(geom), nt, rt.stream())
+            return
+        except _C.Unsupported:
+            _tc_declined.add(_gkey("wgrad", geom))
     call("pnp_conv2d_wgrad", ptr(xp), ptr(dz), ptr(W.grad), ctypes.byref(geom), rt.stream())
+
+
+def _tc_will_run(kind, geom):
+    return bool(_tc_mode()) and _tc_candidate(kind, geom) and (kind != "wgrad" or TC_WGRAD)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -219,7 +250,7 @@ def layer_forward(x, W, cfg, skip=None, save=True):
     if bn is not None and cfg.bn_training:
         s = _zeros_f64(2 * C, dev)
         stats = (s[:C], s[C:])
-    z, stats_done = conv_fwd_raw(xp, W, geom, drop, stats)
+    z, stats_done, x_planes = conv_fwd_raw(xp, W, geom, drop, stats, keep_planes=save and W.requires_grad)
     mean = invstd = None
     if bn is not None:
         vec = torch.empty(4, C, dtype=torch.float32, device=dev)
@@ -243,7 +274,7 @@ def layer_forward(x, W, cfg, skip=None, save=True):
     if not save:
         return y, None
     saved = {
-        "cfg": cfg, "geom": geom, "p": p, "x_shape": tuple(x.shape), "xp": xp, "W": W, "drop": drop_info,
+        "cfg": cfg, "geom": geom, "p": p, "x_shape": tuple(x.shape), "xp": xp, "xs": x_planes, "W": W, "drop": drop_info,
         "z": z if (bn is not None) else None, "y": y if cfg.act != ACT_NONE else None,
         "mean": mean, "invstd": invstd, "skip_c": skip.shape[-1] if skip is not None else 0,
     }
@@ -306,19 +337,22 @@ def layer_backward(sv, dy, need_dx=True, dx_into=None, want_dskip=False):
         else:
             dskip = torch.empty(dy.shape[:-1] + (cs,), dtype=torch.float32, device=dev)
             call("pnp_channel_slice", ptr(g), C, cfg.skip_off if cs != C else 0, cs, ptr(dskip), M, 0, rt.stream())
+    dz_planes = None
+    if (W.requires_grad and _tc_will_run("wgrad", geom)) or (need_dx and _tc_will_run("dgrad", geom)):
+        dz_planes = split_bf16(dz, _tc_mode())
     if W.requires_grad:
-        conv_wgrad_raw(sv["xp"], dz, W, geom)
+        conv_wgrad_raw(sv["xp"], dz, W, geom, sv.get("xs"), dz_planes)
     dx = None
     if need_dx:
         if sv["p"]:
-            dxp = conv_dgrad_raw(dz, W, geom)
+            dxp = conv_dgrad_raw(dz, W, geom, None, dz_planes)
             B, H, Wd, Cin = sv["x_shape"]
             dx = torch.empty(sv["x_shape"], dtype=torch.float32, device=dev)
             call("pnp_mirror_pad_bwd", ptr(dxp), ptr(dx), B, H, Wd, Cin, sv["p"], rt.stream())
             if dx_into is not None:
                 raise NotImplementedError("accumulating dgrad through a SYMMETRIC pad is not used by the hot path")
         else:
-            dx = conv_dgrad_raw(dz, W, geom, into=dx_into)
+            dx = conv_dgrad_raw(dz, W, geom, dx_into, dz_planes)
     if DEBUG_HOOK is not None:
         DEBUG_HOOK(sv, dy, g, dz, dx)
     return dx, dskip

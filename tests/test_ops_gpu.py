@@ -89,6 +89,13 @@ TC_CASES = [
     (1, 256, 256, 64, 64, 3, 1, 1, "SAME"),     # cls_1 res b: two 128-wide tiles per row
     (5, 16, 16, 512, 512, 3, 1, 1, "SAME"),     # cls_5: 16x16 images, 8 rows per tile
     (9, 4, 4, 128, 64, 3, 1, 1, "SAME"),        # tiny images: 8 images per tile, ragged batch
+    # strided layers: forward through TMA element strides, dgrad as s*s phase convolutions, wgrad with strided x boxes
+    (2, 32, 32, 64, 64, 3, 2, 1, "SAME"),       # cls_x_3 style 3x3 s2, pad (0,1)
+    (2, 32, 32, 128, 128, 5, 2, 1, "SAME"),     # cls_2_3: 5x5 s2, pad (1,2)
+    (3, 16, 16, 512, 512, 5, 4, 1, "SAME"),     # cls_5_3: 5x5 s4 16 -> 4
+    (2, 4, 4, 64, 64, 3, 2, 1, "SYMMETRIC"),    # cls_6: mirror pad + s2 -> 2x2
+    (1, 256, 256, 64, 64, 3, 2, 1, "SAME"),     # cls_1_3 at full size: 256-wide strided TMA box
+    (2, 8, 8, 128, 256, 5, 4, 1, "SYMMETRIC"),  # m_cls_4
 ]
 
 
@@ -109,11 +116,12 @@ def test_conv_tensor_core(case, backend, tol):
     r = randn(tuple(yo.shape), 13)
     (yo * r.double()).sum().backward()
     xg, wg = _var(x), _var(w)
-    y = L.conv2d(xg, wg, 1.0, padding=pad) if d == 1 else L.dilate_conv2d(xg, wg, 1.0, rate=d, padding=pad)
+    y = L.conv2d(xg, wg, 1.0, strides=[1, s, s, 1], padding=pad) if d == 1 else L.dilate_conv2d(xg, wg, 1.0, rate=d, padding=pad)
     check("y", y, yo, tol)
     y.backward(r.to(DEV))
     check("dx", xg.grad, xo.grad, tol)
-    check("dw", wg.grad, wo.grad, 2e-4 if backend == "tc3" else 1e-3)
+    check("dw", wg.grad, wo.grad, tol)
+    assert not F._tc_declined, "these shapes must run on tcgen05: %s" % (F._tc_declined,)
     rt.set_conv_backend("auto")
 
 
