@@ -101,19 +101,21 @@ int pnp_bn_stats(const float* z, long long M, int C, double* sum, double* sumsq,
 int pnp_bn_finalize(const double* sum, const double* sumsq, long long M, int C, const float* gamma,
                     const float* beta, float* moving_mean, float* moving_var, int training,
                     float* scale, float* shift, float* mean, float* invstd, void* stream);
-/* y = act(z*scale + shift + skip);  skip (optional) has Cs channels placed at channel offset skip_off */
+/* y = act(z*scale + shift + skip);  skip (optional) has Cs channels placed at channel offset skip_off.
+ * y_hi / y_lo (optional): also emit the bf16 (hi, lo) operand planes of y for the next tcgen05 convolution */
 int pnp_bn_act_apply(const float* z, const float* scale, const float* shift, const float* skip, int Cs,
-                     int skip_off, int act, float* y, long long M, int C, void* stream);
+                     int skip_off, int act, float* y, uint16_t* y_hi, uint16_t* y_lo, long long M, int C, void* stream);
 /* g = dy * act'(y);  sum_g[c] += g;  sum_gx[c] += g * xhat   (xhat = (z-mean)*invstd) */
 int pnp_bn_bwd_reduce(const float* dy, const float* y, const float* z, const float* mean, const float* invstd,
                       int act, float* g, double* sum_g, double* sum_gx, long long M, int C, void* stream);
 /* dgamma += sum_gx, dbeta += sum_g (if non-NULL); coef[0..C) = sum_g/M, coef[C..2C) = sum_gx/M */
 int pnp_bn_bwd_finalize(const double* sum_g, const double* sum_gx, long long M, int C, float* dgamma,
                         float* dbeta, float* coef, void* stream);
-/* training: dz = gamma*invstd*(g - c1 - xhat*c2) ; else dz = gamma*invstd*g ; then * dropout mult */
+/* training: dz = gamma*invstd*(g - c1 - xhat*c2) ; else dz = gamma*invstd*g ; then * dropout mult.
+ * dz_hi / dz_lo (optional): bf16 operand planes of dz for the tcgen05 dgrad / wgrad */
 int pnp_bn_bwd_apply(const float* g, const float* z, const float* mean, const float* invstd, const float* gamma,
-                     const float* coef, int training, const pnp_dropout_cfg* drop, float* dz, long long M, int C,
-                     void* stream);
+                     const float* coef, int training, const pnp_dropout_cfg* drop, float* dz, uint16_t* dz_hi, uint16_t* dz_lo,
+                     long long M, int C, void* stream);
 /* activation-only backward (no BN): g = dy * act'(y) */
 int pnp_act_bwd(const float* dy, const float* y, int act, float* g, long long n, void* stream);
 /* dskip[m, c] = g[m, skip_off + c], c < Cs   (gradient of the channel-pad skip) */

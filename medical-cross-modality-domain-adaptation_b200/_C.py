@@ -48,10 +48,10 @@ SIGNATURES = {
     "pnp_conv2d_tc_wgrad": [P, P, P, P, P, _GEOM, c_int, P],
     "pnp_bn_stats": [P, c_ll, c_int, P, P, P],
     "pnp_bn_finalize": [P, P, c_ll, c_int, P, P, P, P, c_int, P, P, P, P, P],
-    "pnp_bn_act_apply": [P, P, P, P, c_int, c_int, c_int, P, c_ll, c_int, P],
+    "pnp_bn_act_apply": [P, P, P, P, c_int, c_int, c_int, P, P, P, c_ll, c_int, P],
     "pnp_bn_bwd_reduce": [P, P, P, P, P, c_int, P, P, P, c_ll, c_int, P],
     "pnp_bn_bwd_finalize": [P, P, c_ll, c_int, P, P, P, P],
-    "pnp_bn_bwd_apply": [P, P, P, P, P, P, c_int, _DROP, P, c_ll, c_int, P],
+    "pnp_bn_bwd_apply": [P, P, P, P, P, P, c_int, _DROP, P, P, P, c_ll, c_int, P],
     "pnp_act_bwd": [P, P, c_int, P, c_ll, P],
     "pnp_channel_slice": [P, c_int, c_int, c_int, P, c_ll, c_int, P],
     "pnp_dropout_apply": [P, P, c_ll, _DROP, P],

@@ -6,9 +6,25 @@
 #include "common.cuh"
 #include "../../include/pnp_b200.h"
 
+#include <cuda_bf16.h>
+
 namespace {
 
 constexpr int kSMs = 148;
+
+// fp32 -> (hi, lo) bf16 pair with hi + lo ~ x to 2^-17 (operand planes of the tcgen05 convolution, conv_tc.cu)
+__device__ __forceinline__ void split_pair(float x, unsigned short& hi, unsigned short& lo) {
+  __nv_bfloat16 h = __float2bfloat16_rn(x);
+  __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = __bfloat16_as_ushort(h);
+  lo = __bfloat16_as_ushort(l);
+}
+__device__ __forceinline__ void store_planes(unsigned short* hi, unsigned short* lo, long long i4, float4 v) {
+  ushort4 h, l;
+  split_pair(v.x, h.x, l.x); split_pair(v.y, h.y, l.y); split_pair(v.z, h.z, l.z); split_pair(v.w, h.w, l.w);
+  reinterpret_cast<ushort4*>(hi)[i4] = h;
+  if (lo) reinterpret_cast<ushort4*>(lo)[i4] = l;
+}
 constexpr float kLeak = 0.2f;       // tf.nn.leaky_relu default alpha (layers.py:12)
 constexpr float kBnDecay = 0.90f;   // layers.py:100
 constexpr float kBnEps = 1e-3f;     // tf.contrib.layers.batch_norm default epsilon
@@ -50,10 +66,9 @@ bn_reduce_kernel(const float* __restrict__ z, const float* __restrict__ dy, cons
                  long long M, int C, int tpr, long long rows_per_block, double* __restrict__ out_a, double* __restrict__ out_b) {
   // WITH_G == false: out_a += sum z, out_b += sum z^2
   // WITH_G == true : g = dy*act'(y) (written to gout); out_a += sum g ; out_b += sum g*xhat
-  __shared__ double s_a[1024];
-  __shared__ double s_b[1024];
-  for (int i = threadIdx.x; i < C; i += 256) { s_a[i] = 0.0; s_b[i] = 0.0; }
-  __syncthreads();
+  // thread (q, rlane) owns channel quad q and every rstep-th row; block partials are combined through shared memory
+  // (no shared-memory fp64 atomics: those are CAS loops) and one fp64 global atomic per channel per block.
+  __shared__ double s_part[256][8];
   const int C4 = C >> 2;
   const int q = threadIdx.x % tpr;
   const int rlane = threadIdx.x / tpr;
@@ -61,19 +76,22 @@ bn_reduce_kernel(const float* __restrict__ z, const float* __restrict__ dy, cons
   long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > M) r1 = M;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+  double da[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) da[i] = 0.0;
   if (q < C4) {
     float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), is = make_float4(1.f, 1.f, 1.f, 1.f);
     if (WITH_G) {
       mu = __ldg(reinterpret_cast<const float4*>(mean) + q);
       is = __ldg(reinterpret_cast<const float4*>(invstd) + q);
     }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+    int cnt = 0;
     for (long long r = r0 + rlane; r < r1; r += rstep) {
       long long off = r * C4 + q;
       float4 zv = __ldg(reinterpret_cast<const float4*>(z) + off);
       if (WITH_G) {
-        float4 d = __ldg(reinterpret_cast<const float4*>(dy) + off);
-        float4 g = d;
+        float4 g = __ldg(reinterpret_cast<const float4*>(dy) + off);
         if (act != PNP_ACT_NONE) {
           float4 yv = __ldg(reinterpret_cast<const float4*>(yact) + off);
           g.x *= act_slope(yv.x, act); g.y *= act_slope(yv.y, act);
@@ -87,17 +105,25 @@ bn_reduce_kernel(const float* __restrict__ z, const float* __restrict__ dy, cons
         a0 += zv.x; a1 += zv.y; a2 += zv.z; a3 += zv.w;
         b0 += zv.x * zv.x; b1 += zv.y * zv.y; b2 += zv.z * zv.z; b3 += zv.w * zv.w;
       }
+      if (++cnt == 64) {   // keep fp32 partial sums short, promote to fp64
+        da[0] += a0; da[1] += a1; da[2] += a2; da[3] += a3; da[4] += b0; da[5] += b1; da[6] += b2; da[7] += b3;
+        a0 = a1 = a2 = a3 = b0 = b1 = b2 = b3 = 0.f;
+        cnt = 0;
+      }
     }
-    int c = q * 4;
-    atomicAdd(&s_a[c + 0], (double)a0); atomicAdd(&s_a[c + 1], (double)a1);
-    atomicAdd(&s_a[c + 2], (double)a2); atomicAdd(&s_a[c + 3], (double)a3);
-    atomicAdd(&s_b[c + 0], (double)b0); atomicAdd(&s_b[c + 1], (double)b1);
-    atomicAdd(&s_b[c + 2], (double)b2); atomicAdd(&s_b[c + 3], (double)b3);
+    da[0] += a0; da[1] += a1; da[2] += a2; da[3] += a3; da[4] += b0; da[5] += b1; da[6] += b2; da[7] += b3;
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_part[threadIdx.x][i] = da[i];
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += 256) {
-    atomicAdd(out_a + i, s_a[i]);
-    atomicAdd(out_b + i, s_b[i]);
+  // 2*C outputs, each the sum over the rstep row-lanes
+  for (int o = threadIdx.x; o < 2 * C; o += 256) {
+    const int which = o / C;            // 0: out_a, 1: out_b
+    const int c = o - which * C;
+    const int qq = c >> 2, j = (c & 3) + 4 * which;
+    double t = 0.0;
+    for (int r = 0; r < rstep; ++r) t += s_part[r * tpr + qq][j];
+    atomicAdd((which ? out_b : out_a) + c, t);
   }
 }
 
@@ -108,10 +134,9 @@ int reduce_launch_cfg(long long M, int C, int* tpr, long long* rpb, int* grid) {
   if (t > 256) return PNP_ERR_UNSUPPORTED;
   *tpr = t;
   int rstep = 256 / t;
-  // per-thread fp32 partial sums stay short (<= ~64 rows) before being promoted to double
-  long long rows = (long long)rstep * 64;
+  long long rows = (long long)rstep * 32;
   long long g = (M + rows - 1) / rows;
-  long long cap = (long long)kSMs * 16;
+  long long cap = (long long)kSMs * 8;     // 8 resident CTAs of 256 threads per SM, one wave
   if (g > cap) { g = cap; rows = (M + g - 1) / g; }
   *rpb = rows;
   *grid = (int)((M + rows - 1) / rows);
@@ -150,7 +175,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
 __global__ void __launch_bounds__(256)
 bn_act_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ skip, int Cs, int skip_off, int act, float* __restrict__ y,
-                    long long n4, int C4) {
+                    unsigned short* __restrict__ p_hi, unsigned short* __restrict__ p_lo, long long n4, int C4) {
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     int q = (int)(i % C4);
     float4 v = __ldg(reinterpret_cast<const float4*>(z) + i);
@@ -170,6 +195,7 @@ bn_act_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale
     }
     v.x = act_fwd(v.x, act); v.y = act_fwd(v.y, act); v.z = act_fwd(v.z, act); v.w = act_fwd(v.w, act);
     reinterpret_cast<float4*>(y)[i] = v;
+    if (p_hi) store_planes(p_hi, p_lo, i, v);
   }
 }
 
@@ -187,7 +213,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sum_g, const d
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ coef,
-                    int training, PnpDropout drop, float* __restrict__ dz, long long n4, int C4) {
+                    int training, PnpDropout drop, float* __restrict__ dz, unsigned short* __restrict__ p_hi,
+                    unsigned short* __restrict__ p_lo, long long n4, int C4) {
   unsigned long long seed = 0ull;
   const bool drop_on = drop.seed_ptr != nullptr;
   if (drop_on) seed = *drop.seed_ptr;
@@ -214,6 +241,7 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, co
       o.x *= mu.x; o.y *= mu.y; o.z *= mu.z; o.w *= mu.w;
     }
     reinterpret_cast<float4*>(dz)[i] = o;
+    if (p_hi) store_planes(p_hi, p_lo, i, o);
   }
 }
 
@@ -715,13 +743,13 @@ extern "C" int pnp_bn_finalize(const double* sum, const double* sumsq, long long
 }
 
 extern "C" int pnp_bn_act_apply(const float* z, const float* scale, const float* shift, const float* skip, int Cs,
-                                int skip_off, int act, float* y, long long M, int C, void* stream) {
+                                int skip_off, int act, float* y, uint16_t* y_hi, uint16_t* y_lo, long long M, int C, void* stream) {
   if (!z || !y || M <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
   if (C % 4 != 0) return PNP_ERR_UNSUPPORTED;
   if (skip && (Cs % 4 != 0 || skip_off % 4 != 0 || skip_off < 0 || skip_off + Cs > C)) return PNP_ERR_UNSUPPORTED;
   if ((scale == nullptr) != (shift == nullptr)) return PNP_ERR_BAD_ARG;
   long long n4 = M * (C / 4);
-  bn_act_apply_kernel<<<grid_for(n4, 256 * 4), 256, 0, S_>>>(z, scale, shift, skip, Cs, skip_off, act, y, n4, C / 4);
+  bn_act_apply_kernel<<<grid_for(n4, 256 * 4), 256, 0, S_>>>(z, scale, shift, skip, Cs, skip_off, act, y, y_hi, y_lo, n4, C / 4);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -747,13 +775,14 @@ extern "C" int pnp_bn_bwd_finalize(const double* sum_g, const double* sum_gx, lo
 }
 
 extern "C" int pnp_bn_bwd_apply(const float* g, const float* z, const float* mean, const float* invstd, const float* gamma,
-                                const float* coef, int training, const pnp_dropout_cfg* drop, float* dz, long long M, int C,
-                                void* stream) {
+                                const float* coef, int training, const pnp_dropout_cfg* drop, float* dz, uint16_t* dz_hi,
+                                uint16_t* dz_lo, long long M, int C, void* stream) {
   if (!g || !invstd || !gamma || !dz || M <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
   if (training && (!z || !mean || !coef)) return PNP_ERR_BAD_ARG;
   if (C % 4 != 0) return PNP_ERR_UNSUPPORTED;
   long long n4 = M * (C / 4);
-  bn_bwd_apply_kernel<<<grid_for(n4, 256 * 4), 256, 0, S_>>>(g, z, mean, invstd, gamma, coef, training, make_drop(drop), dz, n4, C / 4);
+  bn_bwd_apply_kernel<<<grid_for(n4, 256 * 4), 256, 0, S_>>>(g, z, mean, invstd, gamma, coef, training, make_drop(drop), dz, dz_hi, dz_lo,
+                                                            n4, C / 4);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }

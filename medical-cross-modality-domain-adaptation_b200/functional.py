@@ -19,6 +19,8 @@ ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 
 # fuse BN batch statistics into the tcgen05 conv epilogue (otherwise a separate pnp_bn_stats pass)
 FUSE_BN_STATS = True
+# emit the bf16 operand planes from the BN-apply / BN-backward kernels instead of a separate split pass
+FUSE_SPLIT = os.environ.get("PNP_FUSE_SPLIT", "1") != "0"
 # bench.py sets this to a list to time every tcgen05 launch with CUDA events: (start, end, flops, tag)
 PROFILE = None
 # debugging aid: callable(sv, dy, g, dz, dx) invoked at the end of every layer_backward
@@ -90,6 +92,26 @@ def _tc_candidate(kind, g):
     return g.Cin % 64 == 0 and g.Cout % 64 == 0 and g.kh * g.kw <= 25 and _gkey(kind, g) not in _tc_declined
 
 
+def _new_planes(shape, dev, nterms):
+    hi = torch.empty(shape, dtype=torch.bfloat16, device=dev)
+    lo = torch.empty(shape, dtype=torch.bfloat16, device=dev) if nterms == 3 else None
+    return hi, lo
+
+
+def _planes_of(x, nterms):
+    """bf16 operand planes of x: emitted by the producing kernel when available, else one split pass"""
+    p = getattr(x, "_pnp_planes", None)
+    if p is not None and p[0] == nterms:
+        return p[1], p[2]
+    return split_bf16(x, nterms)
+
+
+def _want_planes(C):
+    """producers emit planes for tensors a tcgen05 convolution is likely to consume (64-multiple channel counts)"""
+    nt = _tc_mode()
+    return nt if (nt and FUSE_SPLIT and C % 64 == 0) else 0
+
+
 def split_bf16(x, nterms):
     hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if nterms == 3 else None
@@ -134,7 +156,7 @@ def conv_fwd_raw(xp, W, geom, drop=None, stats=None, keep_planes=False):
     z = torch.empty(geom.B, geom.Ho, geom.Wo, geom.Cout, dtype=torch.float32, device=xp.device)
     nt = _tc_mode()
     if nt and _tc_candidate("fwd", geom):
-        planes = split_bf16(xp, nt)
+        planes = _planes_of(xp, nt)
         whi, wlo = _weight_planes(W, False, nt)
         fuse = stats is not None and FUSE_BN_STATS
         try:
@@ -264,11 +286,16 @@ def layer_forward(x, W, cfg, skip=None, save=True):
             bn.moving_mean.pnp_version = getattr(bn.moving_mean, "pnp_version", 0) + 1
         y = torch.empty_like(z)
         cs = skip.shape[-1] if skip is not None else 0
-        call("pnp_bn_act_apply", ptr(z), ptr(scale), ptr(shift), ptr(skip), cs, cfg.skip_off, cfg.act, ptr(y), M, C, rt.stream())
+        nt = _want_planes(C)
+        yh, yl = _new_planes(z.shape, dev, nt) if nt else (None, None)
+        call("pnp_bn_act_apply", ptr(z), ptr(scale), ptr(shift), ptr(skip), cs, cfg.skip_off, cfg.act, ptr(y), ptr(yh), ptr(yl), M, C,
+             rt.stream())
+        if nt:
+            y._pnp_planes = (nt, yh, yl)
     elif cfg.act != ACT_NONE or skip is not None:
         y = torch.empty_like(z)
         cs = skip.shape[-1] if skip is not None else 0
-        call("pnp_bn_act_apply", ptr(z), None, None, ptr(skip), cs, cfg.skip_off, cfg.act, ptr(y), M, C, rt.stream())
+        call("pnp_bn_act_apply", ptr(z), None, None, ptr(skip), cs, cfg.skip_off, cfg.act, ptr(y), None, None, M, C, rt.stream())
     else:
         y = z
     if not save:
@@ -315,8 +342,13 @@ def layer_backward(sv, dy, need_dx=True, dx_into=None, want_dskip=False):
         else:
             g = dy
         dz = torch.empty(dy.shape, dtype=torch.float32, device=dev)
+        nt = _tc_mode()
+        want = nt and FUSE_SPLIT and ((W.requires_grad and _tc_will_run("wgrad", geom)) or (need_dx and _tc_will_run("dgrad", geom)))
+        dzh, dzl = _new_planes(dy.shape, dev, nt) if want else (None, None)
         call("pnp_bn_bwd_apply", ptr(g), ptr(sv["z"]), ptr(sv["mean"]), ptr(sv["invstd"]), ptr(bn.gamma), ptr(coef),
-             1 if cfg.bn_training else 0, _byref(drop), ptr(dz), M, C, rt.stream())
+             1 if cfg.bn_training else 0, _byref(drop), ptr(dz), ptr(dzh), ptr(dzl), M, C, rt.stream())
+        if want:
+            dz._pnp_planes = (nt, dzh, dzl)
     else:
         if cfg.act != ACT_NONE:
             g = torch.empty(dy.shape, dtype=torch.float32, device=dev)
@@ -339,7 +371,7 @@ def layer_backward(sv, dy, need_dx=True, dx_into=None, want_dskip=False):
             call("pnp_channel_slice", ptr(g), C, cfg.skip_off if cs != C else 0, cs, ptr(dskip), M, 0, rt.stream())
     dz_planes = None
     if (W.requires_grad and _tc_will_run("wgrad", geom)) or (need_dx and _tc_will_run("dgrad", geom)):
-        dz_planes = split_bf16(dz, _tc_mode())
+        dz_planes = _planes_of(dz, _tc_mode())
     if W.requires_grad:
         conv_wgrad_raw(sv["xp"], dz, W, geom, sv.get("xs"), dz_planes)
     dx = None

@@ -157,7 +157,7 @@ class _BNOnly(torch.autograd.Function):
              ptr(bn.beta), ptr(bn.moving_mean), ptr(bn.moving_var), 1 if training else 0, ptr(vec[0]), ptr(vec[1]), ptr(vec[2]),
              ptr(vec[3]), rt.stream())
         y = torch.empty_like(x)
-        call("pnp_bn_act_apply", ptr(x), ptr(vec[0]), ptr(vec[1]), None, 0, 0, F.ACT_NONE, ptr(y), M, C, rt.stream())
+        call("pnp_bn_act_apply", ptr(x), ptr(vec[0]), ptr(vec[1]), None, 0, 0, F.ACT_NONE, ptr(y), None, None, M, C, rt.stream())
         ctx.save_for_backward(x)
         ctx.meta = (bn, training, vec, M, C)
         return y
@@ -179,7 +179,7 @@ class _BNOnly(torch.autograd.Function):
         call("pnp_bn_bwd_finalize", ptr(sums[:C]), ptr(sums[C:]), M, C, ptr(dgamma), ptr(dbeta), ptr(coef), rt.stream())
         dx = torch.empty_like(dy)
         call("pnp_bn_bwd_apply", ptr(g), ptr(x), ptr(vec[2]), ptr(vec[3]), ptr(bn.gamma), ptr(coef), 1 if training else 0, None,
-             ptr(dx), M, C, rt.stream())
+             ptr(dx), None, None, M, C, rt.stream())
         return dx, None, None, None, None
 
 
