@@ -180,6 +180,15 @@ def run_ours(a):
         torch.cuda.synchronize()
         recs = F.PROFILE
         F.PROFILE = None
+        by = {}
+        for s_, e_, fl_, tag_ in recs:
+            k_ = (tag_, round(fl_ / 1e9, 3))
+            c_ = by.setdefault(k_, [0, 0.0])
+            c_[0] += 1
+            c_[1] += s_.elapsed_time(e_)
+        top = sorted(by.items(), key=lambda kv: -kv[1][1])[:14]
+        for (tag_, gf_), (n_, ms_) in top:
+            print("[tc] %-18s %9.3f GF x%3d  %8.3f ms  %7.1f TF/s" % (tag_, gf_, n_, ms_, gf_ * n_ / ms_), file=sys.stderr)
         tc_ms = sum(s.elapsed_time(e) for s, e, _, _ in recs)
         tc_fl = sum(fl for _, _, fl, _ in recs)
         pk = _peaks()

@@ -78,7 +78,9 @@ int pnp_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long long n, void
 /* w HWIO fp32 -> bf16 planes: for_dgrad == 0: [tap][Cout][Cin] (K-major B operand of the forward conv);
  * for_dgrad != 0: [tap][Cin][Cout] (K-major B operand of the data gradient) */
 int pnp_split_weight_bf16(const float* w, uint16_t* hi, uint16_t* lo, int kh, int kw, int Cin, int Cout,
-                          int for_dgrad, void* stream);
+                          int for_dgrad, int cin_pad /* forward layout only: zero-pad Cin up to this (0 = none) */, void* stream);
+/* [rows, C] fp32 -> [rows, Cpad] bf16 planes with zero channels >= C: Cin = 32 layers ride the 64-channel K chunk */
+int pnp_split_bf16_pad(const float* x, uint16_t* hi, uint16_t* lo, long long rows, int C, int Cpad, void* stream);
 int pnp_conv2d_tc_fwd(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo,
                       float* y, const pnp_conv_geom* g, int nterms, const pnp_dropout_cfg* drop,
                       int accumulate, double* bn_sum, double* bn_sumsq, void* stream);
@@ -90,7 +92,8 @@ int pnp_conv2d_tc_dgrad(const uint16_t* dy_hi, const uint16_t* dy_lo, const uint
 /* dw[kh][kw][Cin][Cout] += x (*) dy on tcgen05 (both operands MN-major straight from the NHWC planes; pixel range split
  * across CTAs, fp32 vector atomics into dw).  x planes are the (mirror-padded) forward input. */
 int pnp_conv2d_tc_wgrad(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dy_hi, const uint16_t* dy_lo,
-                        float* dw, const pnp_conv_geom* g, int nterms, void* stream);
+                        float* dw, const pnp_conv_geom* g, int nterms, int x_channels /* channels of the x planes, 0 = Cin */,
+                        void* stream);
 
 /* ---- batch norm + activation (+ residual skip) (elementwise.cu) ----------------------------------
  * replaces tf.contrib.layers.batch_norm(decay .9, eps 1e-3) (layers.py:95-100), the activation

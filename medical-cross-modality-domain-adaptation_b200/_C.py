@@ -42,10 +42,11 @@ SIGNATURES = {
     "pnp_conv2d_wgrad": [P, P, P, _GEOM, P],
     "pnp_weight_transpose": [P, P, c_int, c_int, c_int, P],
     "pnp_split_bf16": [P, P, P, c_ll, P],
-    "pnp_split_weight_bf16": [P, P, P, c_int, c_int, c_int, c_int, c_int, P],
+    "pnp_split_weight_bf16": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "pnp_split_bf16_pad": [P, P, P, c_ll, c_int, c_int, P],
     "pnp_conv2d_tc_fwd": [P, P, P, P, P, _GEOM, c_int, _DROP, c_int, P, P, P],
     "pnp_conv2d_tc_dgrad": [P, P, P, P, P, _GEOM, c_int, c_int, P],
-    "pnp_conv2d_tc_wgrad": [P, P, P, P, P, _GEOM, c_int, P],
+    "pnp_conv2d_tc_wgrad": [P, P, P, P, P, _GEOM, c_int, c_int, P],
     "pnp_bn_stats": [P, c_ll, c_int, P, P, P],
     "pnp_bn_finalize": [P, P, c_ll, c_int, P, P, P, P, c_int, P, P, P, P, P],
     "pnp_bn_act_apply": [P, P, P, P, c_int, c_int, c_int, P, P, P, c_ll, c_int, P],

@@ -284,6 +284,75 @@ int dispatch_gather(const float* in, const float* wmat, float* out, const Gather
 }
 
 // ------------------------------------------------------------------------------------------------
+// direct convolution for very few output channels (the 5x5 40 -> 5 "output" conv on the 256x256 map,
+// source_segmenter.py:206 / adversarial.py:315): an implicit GEMM would waste most of an N tile.  One CTA = 32x32 output
+// pixels, 256 threads = 32 (x) x 8 (y), 4 rows per thread; 8-channel slabs of the haloed input tile and of the weights are
+// staged in shared memory ([c][y][x], x fastest => conflict-free reads, weights broadcast).
+// ------------------------------------------------------------------------------------------------
+template <int NO>
+__global__ void __launch_bounds__(256)
+conv_few_out_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int B, int H, int W, int Cin,
+                    int Ho, int Wo, int kh, int kw, int pad_t, int pad_l) {
+  constexpr int T = 32, CC = 8, HALO = T + 4;            // kernels up to 5x5
+  __shared__ float s_x[CC][HALO][HALO + 1];
+  __shared__ float s_w[25][CC][NO];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * T, y0 = blockIdx.y * T, b = blockIdx.z;
+  const int hh = T + kh - 1, hw = T + kw - 1;
+  float acc[4][NO];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int o = 0; o < NO; ++o) acc[j][o] = 0.f;
+  const float* xb = x + (long long)b * H * W * Cin;
+  for (int c0 = 0; c0 < Cin; c0 += CC) {
+    __syncthreads();
+    for (int p = threadIdx.x; p < hh * hw * 2; p += 256) {
+      const int half = p & 1, pix = p >> 1;
+      const int py = pix / hw, px = pix - py * hw;
+      const int iy = y0 + py - pad_t, ix = x0 + px - pad_l;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float4*>(xb + ((long long)iy * W + ix) * Cin + c0 + half * 4));
+      s_x[half * 4 + 0][py][px] = v.x; s_x[half * 4 + 1][py][px] = v.y;
+      s_x[half * 4 + 2][py][px] = v.z; s_x[half * 4 + 3][py][px] = v.w;
+    }
+    for (int p = threadIdx.x; p < kh * kw * CC * NO; p += 256) {
+      const int o = p % NO, c = (p / NO) % CC, t = p / (NO * CC);
+      s_w[t][c][o] = __ldg(w + ((long long)t * Cin + c0 + c) * NO + o);
+    }
+    __syncthreads();
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx) {
+        const int t = ky * kw + kx;
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+          float wv[NO];
+#pragma unroll
+          for (int o = 0; o < NO; ++o) wv[o] = s_w[t][c][o];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = s_x[c][ty + 8 * j + ky][tx + kx];
+#pragma unroll
+            for (int o = 0; o < NO; ++o) acc[j][o] = fmaf(a, wv[o], acc[j][o]);
+          }
+        }
+      }
+  }
+  const int ox = x0 + tx;
+  if (ox < Wo) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int oy = y0 + ty + 8 * j;
+      if (oy < Ho) {
+        float* dst = y + (((long long)b * Ho + oy) * Wo + ox) * NO;
+#pragma unroll
+        for (int o = 0; o < NO; ++o) dst[o] = acc[j][o];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // wgrad
 // ------------------------------------------------------------------------------------------------
 struct WgradArgs {
@@ -522,6 +591,18 @@ extern "C" int pnp_conv2d_fwd(const float* x, const float* w, float* y, const pn
   a.kh = g->kh; a.kw = g->kw; a.stride = g->stride; a.dil = g->dil; a.pad_t = g->pad_t; a.pad_l = g->pad_l;
   a.M = (int)M; a.K = g->kh * g->kw * g->Cin; a.accumulate = accumulate;
   a.drop = make_drop(drop);
+  if ((g->Cout == 5 || g->Cout == 8) && g->Cin % 8 == 0 && g->stride == 1 && g->dil == 1 && g->kh <= 5 && g->kw <= 5 && !accumulate &&
+      a.drop.seed_ptr == nullptr && g->B <= 65535) {
+    dim3 grid(pnp_cdiv(g->Wo, 32), pnp_cdiv(g->Ho, 32), g->B);
+    if (g->Cout == 5)
+      conv_few_out_kernel<5><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, y, g->B, g->H, g->W, g->Cin, g->Ho, g->Wo, g->kh, g->kw,
+                                                                     g->pad_t, g->pad_l);
+    else
+      conv_few_out_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, y, g->B, g->H, g->W, g->Cin, g->Ho, g->Wo, g->kh, g->kw,
+                                                                     g->pad_t, g->pad_l);
+    PNP_LAUNCH_CHECK();
+    return PNP_OK;
+  }
   return dispatch_gather<false>(x, w, y, a, (cudaStream_t)stream);
 }
 

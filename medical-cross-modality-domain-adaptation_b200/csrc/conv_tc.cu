@@ -392,11 +392,30 @@ split_bf16_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16
   }
 }
 
+// [rows, C] fp32 -> [rows, Cpad] bf16 planes, channels >= C zero (lets Cin = 32 layers ride the 64-channel tcgen05 K chunk)
+__global__ void __launch_bounds__(256)
+split_bf16_pad_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, long long rows, int C,
+                      int Cpad) {
+  const int q4 = Cpad >> 2;
+  long long total = rows * q4;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    long long r = i / q4;
+    int c = (int)(i - r * q4) * 4;
+    ushort4 h = make_ushort4(0, 0, 0, 0), l = make_ushort4(0, 0, 0, 0);
+    if (c < C) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C + c));
+      split1(v.x, h.x, l.x); split1(v.y, h.y, l.y); split1(v.z, h.z, l.z); split1(v.w, h.w, l.w);
+    }
+    reinterpret_cast<ushort4*>(hi)[i] = h;
+    if (lo) reinterpret_cast<ushort4*>(lo)[i] = l;
+  }
+}
+
 // w HWIO [taps][Cin][Cout] -> fwd : out[tap][co][ci]          (B operand rows = co, K = ci)
 //                             dgrad: out[tap][ci][co]          (B operand rows = ci, K = co)
 __global__ void __launch_bounds__(256)
 split_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int taps, int Cin,
-                    int Cout, int for_dgrad) {
+                    int Cout, int for_dgrad, int CinP) {
   __shared__ float tile[32][33];
   const int tap = blockIdx.z;
   const float* src = w + (long long)tap * Cin * Cout;
@@ -420,14 +439,14 @@ split_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi, uint
     tile[r][threadIdx.x] = (ci < Cin && co < Cout) ? src[(long long)ci * Cout + co] : 0.f;
   }
   __syncthreads();
-  long long obase = (long long)tap * Cin * Cout;
+  long long obase = (long long)tap * CinP * Cout;
   for (int r = threadIdx.y; r < 32; r += 8) {
     int co = co0 + r, ci = ci0 + threadIdx.x;
-    if (co < Cout && ci < Cin) {
+    if (co < Cout && ci < CinP) {       // ci in [Cin, CinP): zero padding (tile[] holds 0 there)
       uint16_t h, l;
       split1(tile[threadIdx.x][r], h, l);
-      hi[obase + (long long)co * Cin + ci] = h;
-      if (lo) lo[obase + (long long)co * Cin + ci] = l;
+      hi[obase + (long long)co * CinP + ci] = h;
+      if (lo) lo[obase + (long long)co * CinP + ci] = l;
     }
   }
 }
@@ -729,7 +748,14 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
   if (a.V % a.tw != 0) return PNP_ERR_UNSUPPORTED;
   a.tiles_y = pnp_cdiv(a.U, a.th);
   a.tiles_n = pnp_cdiv(a.B, a.tn);
-  const int block_n = (a.Cout % 128 == 0) ? 128 : 64;
+  // N = 256 tiles halve the shared-memory operand traffic per MMA (the 128x128 tile is shared-memory-bandwidth bound:
+  // 12 MMAs x 8 KB reads + 64 KB TMA fill per 768 tensor cycles) and take the 512-channel 32x32 layers from 1.73 waves
+  // of 256 CTAs to one wave of 128; used whenever enough tiles remain to fill the machine
+  int block_n = (a.Cout % 128 == 0) ? 128 : 64;
+  {
+    const long long mtiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n;
+    if (a.Cout % 256 == 0 && mtiles * (a.Cout / 256) >= 96) block_n = 256;
+  }
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   rc = make_act_map(&ma_hi, a_hi, a.B, AH, AW, a.Cin, a.tw, a.th, a.tn, a_stride);
   if (rc) return rc;
@@ -743,6 +769,10 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
   } else {
     ma_lo = ma_hi;
     mb_lo = mb_hi;
+  }
+  if (block_n == 256) {
+    if (nterms == 3) return launch_tc<256, 3>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
+    return launch_tc<256, 1>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
   }
   if (block_n == 128) {
     if (nterms == 3) return launch_tc<128, 3>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
@@ -777,11 +807,22 @@ extern "C" int pnp_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long l
   return PNP_OK;
 }
 
+extern "C" int pnp_split_bf16_pad(const float* x, uint16_t* hi, uint16_t* lo, long long rows, int C, int Cpad, void* stream) {
+  if (!x || !hi || rows <= 0 || C <= 0 || Cpad < C || (C % 4) != 0 || (Cpad % 4) != 0) return PNP_ERR_BAD_ARG;
+  long long blocks = (rows * (Cpad / 4) + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  split_bf16_pad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, hi, lo, rows, C, Cpad);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
 extern "C" int pnp_split_weight_bf16(const float* w, uint16_t* hi, uint16_t* lo, int kh, int kw, int Cin, int Cout,
-                                     int for_dgrad, void* stream) {
+                                     int for_dgrad, int cin_pad, void* stream) {
   if (!w || !hi || kh <= 0 || kw <= 0 || Cin <= 0 || Cout <= 0) return PNP_ERR_BAD_ARG;
-  dim3 grid(pnp_cdiv(Cout, 32), pnp_cdiv(Cin, 32), kh * kw);
-  split_weight_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(w, hi, lo, kh * kw, Cin, Cout, for_dgrad);
+  const int CinP = (cin_pad > Cin) ? cin_pad : Cin;
+  if (for_dgrad && CinP != Cin) return PNP_ERR_UNSUPPORTED;
+  dim3 grid(pnp_cdiv(Cout, 32), pnp_cdiv(CinP, 32), kh * kw);
+  split_weight_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(w, hi, lo, kh * kw, Cin, Cout, for_dgrad, CinP);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -863,11 +904,16 @@ extern "C" int pnp_conv2d_tc_dgrad(const uint16_t* dy_hi, const uint16_t* dy_lo,
 
 // dw[kh][kw][Cin][Cout] += x (*) dy on tcgen05 (x planes [B,H,W,Cin] -- the mirror-padded input for SYMMETRIC convs)
 extern "C" int pnp_conv2d_tc_wgrad(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dy_hi, const uint16_t* dy_lo,
-                                   float* dw, const pnp_conv_geom* g, int nterms, void* stream) {
+                                   float* dw, const pnp_conv_geom* g, int nterms, int x_channels, void* stream) {
   if (!g || !x_hi || !dy_hi || !dw) return PNP_ERR_BAD_ARG;
   if (nterms != 1 && nterms != 3) return PNP_ERR_BAD_ARG;
   if (nterms == 3 && (!x_lo || !dy_lo)) return PNP_ERR_BAD_ARG;
-  if (!tc_geom_ok(g)) return PNP_ERR_UNSUPPORTED;
+  const int xc = x_channels > 0 ? x_channels : g->Cin;     // channel count of the x planes (>= Cin, zero padded)
+  {
+    pnp_conv_geom t = *g;
+    t.Cin = xc;
+    if (xc < g->Cin || !tc_geom_ok(&t)) return PNP_ERR_UNSUPPORTED;
+  }
   WgArgs a;
   a.B = g->B; a.Cin = g->Cin; a.Cout = g->Cout; a.in_mul = g->stride; a.dw = dw;
   a.ntaps = g->kh * g->kw;
@@ -894,12 +940,12 @@ extern "C" int pnp_conv2d_tc_wgrad(const uint16_t* x_hi, const uint16_t* x_lo, c
   a.pb_per_split = pnp_cdiv(a.num_pb, splits);
   splits = pnp_cdiv(a.num_pb, a.pb_per_split);
   CUtensorMap mx_hi, mx_lo, md_hi, md_lo;
-  rc = make_act_map(&mx_hi, x_hi, g->B, g->H, g->W, g->Cin, a.tw, a.th, a.tn, g->stride);
+  rc = make_act_map(&mx_hi, x_hi, g->B, g->H, g->W, xc, a.tw, a.th, a.tn, g->stride);
   if (rc) return rc;
   rc = make_act_map(&md_hi, dy_hi, g->B, g->Ho, g->Wo, g->Cout, a.tw, a.th, a.tn, 1);
   if (rc) return rc;
   if (nterms == 3) {
-    rc = make_act_map(&mx_lo, x_lo, g->B, g->H, g->W, g->Cin, a.tw, a.th, a.tn, g->stride);
+    rc = make_act_map(&mx_lo, x_lo, g->B, g->H, g->W, xc, a.tw, a.th, a.tn, g->stride);
     if (rc) return rc;
     rc = make_act_map(&md_lo, dy_lo, g->B, g->Ho, g->Wo, g->Cout, a.tw, a.th, a.tn, 1);
     if (rc) return rc;

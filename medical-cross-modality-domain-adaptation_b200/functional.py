@@ -81,6 +81,7 @@ def _tc_mode():
 
 # tcgen05 wgrad can be switched off separately (PNP_TC_WGRAD=0) for A/B measurements
 TC_WGRAD = os.environ.get("PNP_TC_WGRAD", "1") != "0"
+TC_PAD32 = os.environ.get("PNP_TC_PAD32", "0") == "1"
 _tc_declined = set()     # (kind, geometry) the tcgen05 launchers returned PNP_ERR_UNSUPPORTED for -> general SIMT kernel
 
 
@@ -88,8 +89,21 @@ def _gkey(kind, g):
     return (kind, g.B, g.H, g.W, g.Cin, g.Ho, g.Wo, g.Cout, g.kh, g.kw, g.stride, g.dil, g.pad_t, g.pad_l)
 
 
+def _cin_pad(g):
+    """channel count of the (zero padded) operand planes: Cin = 32 layers (cls_1 res a) use the 64-channel K chunk"""
+    return g.Cin if g.Cin % 64 == 0 else ((g.Cin + 63) // 64) * 64
+
+
 def _tc_candidate(kind, g):
-    return g.Cin % 64 == 0 and g.Cout % 64 == 0 and g.kh * g.kw <= 25 and _gkey(kind, g) not in _tc_declined
+    if g.Cout % 64 != 0 or g.kh * g.kw > 25 or _gkey(kind, g) in _tc_declined:
+        return False
+    if g.Cin % 64 == 0:
+        # tiny strided data gradients (cls_5_3, m_cls_4) would be s*s latency-bound launches: general kernel instead
+        return not (kind == "dgrad" and g.stride > 1 and _conv_flops(g) < 4e9)
+    # padded-plane path (Cin = 32 -> 64 zero-padded K chunk), forward and wgrad only.  Measured on B200 (r1e): the 256x256
+    # cls_1 res-a layer is operand-bandwidth bound and runs 0.31 ms padded on tcgen05 vs 0.25 ms on the fp32 SIMT kernel,
+    # so it stays off by default (PNP_TC_PAD32=1 enables it).
+    return TC_PAD32 and kind in ("fwd", "wgrad") and g.Cin % 32 == 0 and g.Cin >= 32
 
 
 def _new_planes(shape, dev, nterms):
@@ -119,18 +133,26 @@ def split_bf16(x, nterms):
     return hi, lo
 
 
-def _weight_planes(W, for_dgrad, nterms):
+def _weight_planes(W, for_dgrad, nterms, cin_pad=0):
     ver = getattr(W, "pnp_version", None)
     cache = W.__dict__.setdefault("_pnp_planes", {})
-    key = (for_dgrad, nterms)
+    key = (for_dgrad, nterms, cin_pad)
     hit = cache.get(key)
     if hit is not None and ver is not None and hit[0] == ver:
         return hit[1], hit[2]
     kh, kw, cin, cout = W.shape
-    hi = torch.empty(kh * kw * cin * cout, dtype=torch.bfloat16, device=W.device)
+    hi = torch.empty(kh * kw * max(cin, cin_pad) * cout, dtype=torch.bfloat16, device=W.device)
     lo = torch.empty_like(hi) if nterms == 3 else None
-    call("pnp_split_weight_bf16", ptr(W), ptr(hi), ptr(lo), kh, kw, cin, cout, 1 if for_dgrad else 0, rt.stream())
+    call("pnp_split_weight_bf16", ptr(W), ptr(hi), ptr(lo), kh, kw, cin, cout, 1 if for_dgrad else 0, cin_pad, rt.stream())
     cache[key] = (ver, hi, lo)
+    return hi, lo
+
+
+def _padded_planes(x, nterms, cpad):
+    """[.., C] fp32 -> [.., cpad] bf16 planes (zero channels beyond C)"""
+    shape = tuple(x.shape[:-1]) + (cpad,)
+    hi, lo = _new_planes(shape, x.device, nterms)
+    call("pnp_split_bf16_pad", ptr(x), ptr(hi), ptr(lo), x.numel() // x.shape[-1], x.shape[-1], cpad, rt.stream())
     return hi, lo
 
 
@@ -156,12 +178,20 @@ def conv_fwd_raw(xp, W, geom, drop=None, stats=None, keep_planes=False):
     z = torch.empty(geom.B, geom.Ho, geom.Wo, geom.Cout, dtype=torch.float32, device=xp.device)
     nt = _tc_mode()
     if nt and _tc_candidate("fwd", geom):
-        planes = _planes_of(xp, nt)
-        whi, wlo = _weight_planes(W, False, nt)
+        cp = _cin_pad(geom)
+        if cp != geom.Cin:
+            planes = _padded_planes(xp, nt, cp)
+            whi, wlo = _weight_planes(W, False, nt, cp)
+            g_tc = ConvGeom(geom.B, geom.H, geom.W, cp, geom.Ho, geom.Wo, geom.Cout, geom.kh, geom.kw, geom.stride, geom.dil,
+                            geom.pad_t, geom.pad_l)
+        else:
+            planes = _planes_of(xp, nt)
+            whi, wlo = _weight_planes(W, False, nt)
+            g_tc = geom
         fuse = stats is not None and FUSE_BN_STATS
         try:
-            _tc_launch("fwd", _conv_flops(geom), "pnp_conv2d_tc_fwd", ptr(planes[0]), ptr(planes[1]), ptr(whi), ptr(wlo), ptr(z),
-                       ctypes.byref(geom), nt, _byref(drop), 0, ptr(stats[0]) if fuse else None, ptr(stats[1]) if fuse else None,
+            _tc_launch("fwd%dx%d.%d.%d" % (geom.Ho, geom.Cin, geom.Cout, geom.kh * geom.stride), _conv_flops(geom), "pnp_conv2d_tc_fwd", ptr(planes[0]), ptr(planes[1]), ptr(whi), ptr(wlo), ptr(z),
+                       ctypes.byref(g_tc), nt, _byref(drop), 0, ptr(stats[0]) if fuse else None, ptr(stats[1]) if fuse else None,
                        rt.stream())
             return z, fuse, (planes if keep_planes else None)
         except _C.Unsupported:
@@ -179,7 +209,7 @@ def conv_dgrad_raw(dz, W, geom, into=None, dz_planes=None):
         hi, lo = dz_planes if dz_planes is not None else split_bf16(dz, nt)
         whi, wlo = _weight_planes(W, True, nt)
         try:
-            _tc_launch("dgrad", _conv_flops(geom), "pnp_conv2d_tc_dgrad", ptr(hi), ptr(lo), ptr(whi), ptr(wlo), ptr(dx),
+            _tc_launch("dgr%dx%d.%d.%d" % (geom.Ho, geom.Cin, geom.Cout, geom.kh * geom.stride), _conv_flops(geom), "pnp_conv2d_tc_dgrad", ptr(hi), ptr(lo), ptr(whi), ptr(wlo), ptr(dx),
                        ctypes.byref(geom), nt, acc, rt.stream())
             return dx
         except _C.Unsupported:
@@ -194,11 +224,17 @@ def conv_wgrad_raw(xp, dz, W, geom, x_planes=None, dz_planes=None):
         call("pnp_fill", ptr(W.grad), 0.0, W.numel(), rt.stream())
     nt = _tc_mode()
     if nt and TC_WGRAD and _tc_candidate("wgrad", geom):
-        xh, xl = x_planes if x_planes is not None else split_bf16(xp, nt)
+        cp = _cin_pad(geom)
+        if x_planes is not None:
+            xh, xl = x_planes
+        elif cp != geom.Cin:
+            xh, xl = _padded_planes(xp, nt, cp)
+        else:
+            xh, xl = _planes_of(xp, nt)
         dh, dl = dz_planes if dz_planes is not None else split_bf16(dz, nt)
         try:
-            _tc_launch("wgrad", _conv_flops(geom), "pnp_conv2d_tc_wgrad", ptr(xh), ptr(xl), ptr(dh), ptr(dl), ptr(W.grad),
-                       ctypes.byref(geom), nt, rt.stream())
+            _tc_launch("wgr%dx%d.%d.%d" % (geom.Ho, geom.Cin, geom.Cout, geom.kh * geom.stride), _conv_flops(geom), "pnp_conv2d_tc_wgrad", ptr(xh), ptr(xl), ptr(dh), ptr(dl), ptr(W.grad),
+                       ctypes.byref(geom), nt, cp if cp != geom.Cin else 0, rt.stream())
             return
         except _C.Unsupported:
             _tc_declined.add(_gkey("wgrad", geom))

@@ -49,6 +49,8 @@ CONV_CASES = [
     (2, 16, 16, 5, 16, 3, 2, 1, "SAME"),       # mask_cls_1: Cin=5
     (3, 12, 20, 24, 40, 3, 1, 1, "SAME"),      # odd sizes / ragged tiles
     (1, 7, 9, 8, 12, 3, 2, 1, "SAME"),         # odd spatial, stride 2
+    (1, 70, 45, 40, 5, 5, 1, 1, "SAME"),       # few-output direct kernel: ragged 32x32 tiles, zero padding
+    (2, 40, 33, 8, 8, 3, 1, 1, "SAME"),        # few-output direct kernel, 8 outputs
 ]
 
 
@@ -89,6 +91,8 @@ TC_CASES = [
     (1, 256, 256, 64, 64, 3, 1, 1, "SAME"),     # cls_1 res b: two 128-wide tiles per row
     (5, 16, 16, 512, 512, 3, 1, 1, "SAME"),     # cls_5: 16x16 images, 8 rows per tile
     (9, 4, 4, 128, 64, 3, 1, 1, "SAME"),        # tiny images: 8 images per tile, ragged batch
+    (2, 64, 64, 32, 64, 3, 1, 1, "SAME"),       # Cin = 32 (cls_1 res a): zero-padded 64-channel planes, fwd + wgrad
+    (8, 32, 32, 256, 512, 3, 1, 1, "SAME"),     # enough tiles for the 128x256 accumulator variant (fwd); dgrad N = 256 too
     # strided layers: forward through TMA element strides, dgrad as s*s phase convolutions, wgrad with strided x boxes
     (2, 32, 32, 64, 64, 3, 2, 1, "SAME"),       # cls_x_3 style 3x3 s2, pad (0,1)
     (2, 32, 32, 128, 128, 5, 2, 1, "SAME"),     # cls_2_3: 5x5 s2, pad (1,2)
@@ -109,6 +113,7 @@ def test_conv_tensor_core(case, backend, tol):
         pytest.fail("tcgen05 path unavailable on this device -- it must be the one that runs on B200")
     rt.set_conv_backend(backend)
     B, H, W, Cin, Cout, k, s, d, pad = case
+    F.TC_PAD32 = True          # exercise the zero-padded 64-channel plane path for the Cin = 32 case
     x = randn((B, H, W, Cin), 11)
     w = randn((k, k, Cin, Cout), 12, 0.05)
     xo, wo = x.double().requires_grad_(True), w.double().requires_grad_(True)
@@ -121,6 +126,7 @@ def test_conv_tensor_core(case, backend, tol):
     y.backward(r.to(DEV))
     check("dx", xg.grad, xo.grad, tol)
     check("dw", wg.grad, wo.grad, tol)
+    F.TC_PAD32 = False
     assert not F._tc_declined, "these shapes must run on tcgen05: %s" % (F._tc_declined,)
     rt.set_conv_backend("auto")
 
