@@ -100,7 +100,15 @@ def build_adversarial(B, backend, seed=0):
     return net, trainer
 
 
+def _host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arms use the physical cores instead (logical/2)"""
+    n = max(1, (os.cpu_count() or 2) // 2)
+    torch.set_num_threads(n)
+    return n
+
+
 def run_ours(a):
+    os.environ["NCCL_DEBUG"] = os.environ.get("PNP_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
     from pnp_b200 import parallel, _C
     parallel.init_from_env()
     import torch.distributed as dist
@@ -175,9 +183,10 @@ def run_ours(a):
     roof = None
     if rank == 0:
         F.PROFILE = []
-        for i in range(min(a.steps, 3)):
-            step_resident(i)
-        torch.cuda.synchronize()
+    for i in range(min(a.steps, 3)):      # every rank steps (the steps contain the gradient all-reduce); rank 0 records events
+        step_resident(i)
+    torch.cuda.synchronize()
+    if rank == 0:
         recs = F.PROFILE
         F.PROFILE = None
         by = {}
@@ -232,8 +241,8 @@ def run_ours(a):
 def cpu_baseline_sample(B, reps):
     """the oracle's joint adversarial step (same math, torch-CPU/oneDNN) on the host cores -- bounded sample"""
     from oracle.pnp_graphs import OracleAdversarial, init_numpy_params, synthetic_images
-    # torch's default intra-op pool (= physical cores it detects); forcing os.cpu_count() logical threads
-    # oversubscribes oneDNN on the GPU host and is >10x slower
+    # physical cores: forcing os.cpu_count() logical threads oversubscribes oneDNN on the GPU host and is >10x slower
+    _host_threads()
     ws, bns = OracleAdversarial.layout()
     P = init_numpy_params(ws, bns, 0, 0.05)
     o = OracleAdversarial(P, B, lambda_mask_loss=0.3, dis_sub_iter=1, gen_sub_iter=1, critic_keep_prob=0.75)
@@ -256,6 +265,7 @@ def run_reference(a):
     if rank != 0:
         return
     from oracle.pnp_graphs import OracleAdversarial, init_numpy_params, synthetic_images
+    _host_threads()
     B = 1
     ws, bns = OracleAdversarial.layout()
     P = init_numpy_params(ws, bns, 0, 0.05)

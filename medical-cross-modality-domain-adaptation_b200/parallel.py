@@ -22,7 +22,9 @@ def init_from_env(backend=None):
     if torch.cuda.is_available():
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    dist.init_process_group(backend=backend)
+    import datetime
+    # a rank that stops participating must abort the job quickly instead of hanging the box
+    dist.init_process_group(backend=backend, timeout=datetime.timedelta(seconds=int(os.environ.get("PNP_DIST_TIMEOUT", "180"))))
 
 
 class DataParallel:
