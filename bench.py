@@ -215,6 +215,19 @@ def run_ours(a):
             roof = {"bound": "tensor", "achieved": 0.0, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": 0.0, "traffic": None,
                     "note": "no tcgen05 launches recorded (backend=%s)" % a.backend}
 
+    if a.profile and rank == 0 and world == 1:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(2):
+                step_resident(i)
+            torch.cuda.synchronize()
+        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:45]
+        tot = sum(e.device_time_total for e in prof.key_averages())
+        for e in rows:
+            print("[prof] %-64s x%4d %9.3f ms %5.1f%%" % (e.key[:64], e.count, e.device_time_total / 1e3 / 2, 100.0 * e.device_time_total / tot),
+                  file=sys.stderr)
+        print("[prof] total device time per step %.3f ms" % (tot / 1e3 / 2), file=sys.stderr)
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = cpu_baseline_sample(2, 1)
@@ -302,6 +315,7 @@ def main():
     ap.add_argument("--keep-prob", type=float, default=0.75)
     ap.add_argument("--backend", default="auto", choices=["auto", "simt", "tc3", "tc1"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="print a per-kernel device-time table (torch profiler) to stderr")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

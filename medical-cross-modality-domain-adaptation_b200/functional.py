@@ -98,8 +98,9 @@ def _tc_candidate(kind, g):
     if g.Cout % 64 != 0 or g.kh * g.kw > 25 or _gkey(kind, g) in _tc_declined:
         return False
     if g.Cin % 64 == 0:
-        # tiny strided data gradients (cls_5_3, m_cls_4) would be s*s latency-bound launches: general kernel instead
-        return not (kind == "dgrad" and g.stride > 1 and _conv_flops(g) < 4e9)
+        # (measured r1e: even the tiny stride-4 data gradients -- cls_5_3, m_cls_4, s*s latency-bound phase launches -- are
+        #  2.5x faster here than on the general kernel, whose transposed gather multiplies 15/16 zeros)
+        return True
     # padded-plane path (Cin = 32 -> 64 zero-padded K chunk), forward and wgrad only.  Measured on B200 (r1e): the 256x256
     # cls_1 res-a layer is operand-bandwidth bound and runs 0.31 ms padded on tcgen05 vs 0.25 ms on the fp32 SIMT kernel,
     # so it stays off by default (PNP_TC_PAD32=1 enables it).
