@@ -44,6 +44,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -177,26 +180,24 @@ __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                float* __restrict__ out, TcArgs a) {
+  // PERSISTENT: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the smem ring and its phases run
+  // across tile boundaries (the producer prefetches the next tile while the last MMAs of the current one retire) and the
+  // accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the main loop of tile i+1.
   using Cfg = TcCfg<BLOCK_N, NTERMS>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  // bars[0..STAGES) full, [STAGES..2*STAGES) empty, [2*STAGES] tmem_full ; then tmem base holder
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty ; then the TMEM base holder
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile coordinates
-  int mt = blockIdx.x;
-  const int txi = mt % a.tiles_x;
-  mt /= a.tiles_x;
-  const int tyi = mt % a.tiles_y;
-  const int tni = mt / a.tiles_y;
-  const int x0 = txi * a.tw, y0 = tyi * a.th, img0 = tni * a.tn;
-  const int n0 = blockIdx.y * BLOCK_N;
-
+  const int n_tiles = a.Cout / BLOCK_N;
+  const int m_tiles = a.tiles_x * a.tiles_y * a.tiles_n;
+  const int num_tiles = m_tiles * n_tiles;
   const int kchunks = a.Cin / BLOCK_K;
   const int num_kb = a.ntaps * kchunks;
 
@@ -208,10 +209,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       mbar_init(smem_u32(&bars[s]), 1);
       mbar_init(smem_u32(&bars[STAGES + s]), 1);
     }
-    mbar_init(smem_u32(&bars[2 * STAGES]), 1);
+    mbar_init(smem_u32(&tmem_full[0]), 1);
+    mbar_init(smem_u32(&tmem_full[1]), 1);
+    mbar_init(smem_u32(&tmem_empty[0]), 128);      // the 128 epilogue threads release an accumulator
+    mbar_init(smem_u32(&tmem_empty[1]), 128);
     fence_barrier_init();
   }
-  if (warp == 1) tcgen05_alloc(smem_u32(tmem_holder), Cfg::TMEM_COLS);
+  if (warp == 1) tcgen05_alloc(smem_u32(tmem_holder), 2 * Cfg::TMEM_COLS);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -224,23 +228,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const uint32_t tx_bytes = Cfg::NPLANES * (box_a_bytes + Cfg::B_TILE_BYTES);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int tap = kb / kchunks;
-        const int kc = kb - tap * kchunks;
-        mbar_wait(smem_u32(&bars[STAGES + stage]), phase ^ 1);
-        const uint32_t full = smem_u32(&bars[stage]);
-        mbar_expect_tx(full, tx_bytes);
-        uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
-        const int cx = x0 * a.in_mul + a.tap_ox[tap];
-        const int cy = y0 * a.in_mul + a.tap_oy[tap];
-        const int wrow = a.tap_wrow[tap] + n0;
-        tma_load_4d(smem_u32(st), &map_a_hi, full, kc * BLOCK_K, cx, cy, img0);
-        tma_load_2d(smem_u32(st + Cfg::NPLANES * A_TILE_BYTES), &map_b_hi, full, kc * BLOCK_K, wrow);
-        if (NTERMS > 1) {
-          tma_load_4d(smem_u32(st + A_TILE_BYTES), &map_a_lo, full, kc * BLOCK_K, cx, cy, img0);
-          tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES), &map_b_lo, full, kc * BLOCK_K, wrow);
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int mt = t / n_tiles;
+        const int n0 = (t - mt * n_tiles) * BLOCK_N;
+        const int txi = mt % a.tiles_x;
+        mt /= a.tiles_x;
+        const int tyi = mt % a.tiles_y;
+        const int tni = mt / a.tiles_y;
+        const int x0 = txi * a.tw, y0 = tyi * a.th, img0 = tni * a.tn;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / kchunks;
+          const int kc = kb - tap * kchunks;
+          mbar_wait(smem_u32(&bars[STAGES + stage]), phase ^ 1);
+          const uint32_t full = smem_u32(&bars[stage]);
+          mbar_expect_tx(full, tx_bytes);
+          uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+          const int cx = x0 * a.in_mul + a.tap_ox[tap];
+          const int cy = y0 * a.in_mul + a.tap_oy[tap];
+          const int wrow = a.tap_wrow[tap] + n0;
+          tma_load_4d(smem_u32(st), &map_a_hi, full, kc * BLOCK_K, cx, cy, img0);
+          tma_load_2d(smem_u32(st + Cfg::NPLANES * A_TILE_BYTES), &map_b_hi, full, kc * BLOCK_K, wrow);
+          if (NTERMS > 1) {
+            tma_load_4d(smem_u32(st + A_TILE_BYTES), &map_a_lo, full, kc * BLOCK_K, cx, cy, img0);
+            tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES), &map_b_lo, full, kc * BLOCK_K, wrow);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -249,33 +262,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(smem_u32(&bars[stage]), phase);
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);     // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t st = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t a_hi = st;
-        const uint32_t a_lo = st + A_TILE_BYTES;
-        const uint32_t b_hi = st + Cfg::NPLANES * A_TILE_BYTES;
-        const uint32_t b_lo = b_hi + Cfg::B_TILE_BYTES;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&bars[stage]), phase);
+          tcgen05_fence_after();
+          const uint32_t st = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t a_hi = st;
+          const uint32_t a_lo = st + A_TILE_BYTES;
+          const uint32_t b_hi = st + Cfg::NPLANES * A_TILE_BYTES;
+          const uint32_t b_lo = b_hi + Cfg::B_TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          const uint32_t koff = k * UMMA_K * 2;   // bytes inside the 128-byte swizzle row
-          const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff);
-          const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff);
-          if (NTERMS > 1) {
-            const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff);
-            const uint64_t db_lo = make_kmajor_sw128_desc(b_lo + koff);
-            // small cross terms first, then the dominant hi*hi term
-            tcgen05_mma_bf16(tmem_base, da_lo, db_hi, idesc, (kb | k) != 0);
-            tcgen05_mma_bf16(tmem_base, da_hi, db_lo, idesc, 1);
-            tcgen05_mma_bf16(tmem_base, da_hi, db_hi, idesc, 1);
-          } else {
-            tcgen05_mma_bf16(tmem_base, da_hi, db_hi, idesc, (kb | k) != 0);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * 2;   // bytes inside the 128-byte swizzle row
+            const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff);
+            const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff);
+            if (NTERMS > 1) {
+              const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff);
+              const uint64_t db_lo = make_kmajor_sw128_desc(b_lo + koff);
+              // small cross terms first, then the dominant hi*hi term
+              tcgen05_mma_bf16(tmem_d, da_lo, db_hi, idesc, (kb | k) != 0);
+              tcgen05_mma_bf16(tmem_d, da_hi, db_lo, idesc, 1);
+              tcgen05_mma_bf16(tmem_d, da_hi, db_hi, idesc, 1);
+            } else {
+              tcgen05_mma_bf16(tmem_d, da_hi, db_hi, idesc, (kb | k) != 0);
+            }
           }
+          tcgen05_commit(smem_u32(&bars[STAGES + stage]));   // frees the smem slot when these MMAs retire
+          if (kb == num_kb - 1) tcgen05_commit(smem_u32(&tmem_full[acc]));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(smem_u32(&bars[STAGES + stage]));   // frees the smem slot when these MMAs retire
-        if (kb == num_kb - 1) tcgen05_commit(smem_u32(&bars[2 * STAGES]));
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
@@ -287,79 +309,89 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int rem = m - ni * per_img;
     const int yy = rem / a.tw;
     const int xx = rem - yy * a.tw;
-    const int img = img0 + ni, u = y0 + yy, v_ = x0 + xx;
-    const bool valid = (ni < a.tn) && (img < a.B) && (u < a.U) && (v_ < a.V);
-    const int oy = u * a.out_mul + a.out_py, ox = v_ * a.out_mul + a.out_px;
-    const long long pix = ((long long)img * a.OH + oy) * a.OW + ox;
-    float* orow = out + pix * a.Cout + n0;
     const bool drop_on = a.drop.seed_ptr != nullptr;
     unsigned long long seed = 0ull;
     if (drop_on) seed = *a.drop.seed_ptr;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int mt = t / n_tiles;
+      const int n0 = (t - mt * n_tiles) * BLOCK_N;
+      const int txi = mt % a.tiles_x;
+      mt /= a.tiles_x;
+      const int tyi = mt % a.tiles_y;
+      const int tni = mt / a.tiles_y;
+      const int x0 = txi * a.tw, y0 = tyi * a.th, img0 = tni * a.tn;
+      const int img = img0 + ni, u = y0 + yy, v_ = x0 + xx;
+      const bool valid = (ni < a.tn) && (img < a.B) && (u < a.U) && (v_ < a.V);
+      const int oy = u * a.out_mul + a.out_py, ox = v_ * a.out_mul + a.out_px;
+      const long long pix = ((long long)img * a.OH + oy) * a.OW + ox;
+      float* orow = out + pix * a.Cout + n0;
 
-    mbar_wait(smem_u32(&bars[2 * STAGES]), 0);
-    tcgen05_fence_after();
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+      tcgen05_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t r[32];
-      tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      tcgen05_wait_ld();
-      float v[32];
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), r);
+        tcgen05_wait_ld();
+        float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-      if (drop_on && valid) {
-        const unsigned long long base4 = (unsigned long long)(pix * a.Cout + n0 + c0) >> 2;
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (drop_on && valid) {
+          const unsigned long long base4 = (unsigned long long)(pix * a.Cout + n0 + c0) >> 2;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 mu = pnp_dropout_mult4(a.drop, seed, base4 + i);
-          v[4 * i] *= mu.x; v[4 * i + 1] *= mu.y; v[4 * i + 2] *= mu.z; v[4 * i + 3] *= mu.w;
-        }
-      }
-      if (a.bn_sum != nullptr) {
-        // per-channel partial sums over this warp's 32 rows: butterfly transpose-reduce (31 shuffles / array)
-        float s[32], ss[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { float t = valid ? v[i] : 0.f; s[i] = t; ss[i] = t * t; }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-          const bool upper = (lane & off) != 0;
-#pragma unroll
-          for (int i = 0; i < off; ++i) {
-            // lanes with bit `off` clear keep element i, send element i+off ; the others the opposite
-            float send_s = upper ? s[i] : s[i + off];
-            float keep_s = upper ? s[i + off] : s[i];
-            float send_q = upper ? ss[i] : ss[i + off];
-            float keep_q = upper ? ss[i + off] : ss[i];
-            s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
-            ss[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+          for (int i = 0; i < 8; ++i) {
+            float4 mu = pnp_dropout_mult4(a.drop, seed, base4 + i);
+            v[4 * i] *= mu.x; v[4 * i + 1] *= mu.y; v[4 * i + 2] *= mu.z; v[4 * i + 3] *= mu.w;
           }
         }
-        // after the butterfly lane L holds the column whose index has bit b set iff lane bit b is set, b = 16..1
-        int col = 0;
+        if (a.bn_sum != nullptr) {
+          // per-channel partial sums over this warp's 32 rows: butterfly transpose-reduce (31 shuffles / array)
+          float s[32], ss[32];
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) col += (lane & off) ? off : 0;
-        atomicAdd(a.bn_sum + n0 + c0 + col, (double)s[0]);
-        atomicAdd(a.bn_sumsq + n0 + c0 + col, (double)ss[0]);
-      }
-      if (valid) {
-        float4* dst = reinterpret_cast<float4*>(orow + c0);
+          for (int i = 0; i < 32; ++i) { float tv = valid ? v[i] : 0.f; s[i] = tv; ss[i] = tv * tv; }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          if (a.accumulate) {
-            float4 p = dst[i];
-            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              float send_s = upper ? s[i] : s[i + off];
+              float keep_s = upper ? s[i + off] : s[i];
+              float send_q = upper ? ss[i] : ss[i + off];
+              float keep_q = upper ? ss[i + off] : ss[i];
+              s[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+              ss[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+            }
           }
-          dst[i] = o;
+          // after the butterfly lane L holds column L of this 32-column chunk
+          atomicAdd(a.bn_sum + n0 + c0 + lane, (double)s[0]);
+          atomicAdd(a.bn_sumsq + n0 + c0 + lane, (double)ss[0]);
+        }
+        if (valid) {
+          float4* dst = reinterpret_cast<float4*>(orow + c0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            if (a.accumulate) {
+              float4 p = dst[i];
+              o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+            }
+            dst[i] = o;
+          }
         }
       }
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(&tmem_empty[acc]));       // this thread is done reading accumulator `acc`
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
-    tcgen05_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tcgen05_fence_after();
-    tcgen05_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tcgen05_dealloc(tmem_base, 2 * Cfg::TMEM_COLS);
   }
 }
 
@@ -709,7 +741,14 @@ int launch_tc(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensor
     PNP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid(a.tiles_x * a.tiles_y * a.tiles_n, a.Cout / BLOCK_N);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    PNP_CUDA(cudaGetDevice(&dev));
+    PNP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n * (a.Cout / BLOCK_N);
+  dim3 grid((unsigned)(tiles < num_sms ? tiles : num_sms));     // persistent: one CTA per SM walks the tile list
   conv_tc_kernel<BLOCK_N, NTERMS><<<grid, 192, Cfg::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, y, a);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
