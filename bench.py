@@ -202,10 +202,19 @@ def run_ours(a):
         tc_fl = sum(fl for _, _, fl, _ in recs)
         pk = _peaks()
         nterms = 1 if a.backend == "tc1" else 3
+        traffic, traffic_note = None, "no ncu capture committed"
+        tj = os.path.join(ROOT, "profiles", "r1_conv_tc_ncu.json")
+        if os.path.exists(tj):
+            with open(tj) as f:
+                nj = json.load(f)
+            traffic = nj.get("mean_dram_bytes_per_launch")
+            traffic_note = ("dram__bytes_read+write per launch, mean over the %d conv_tc_kernel launches of the committed ncu --set full "
+                            "capture (profiles/r1_conv_tc_ncu.csv); operands 4 B/element (bf16 hi+lo), outputs stay in the 126 MB L2"
+                            % len(nj.get("launches", [])))
         if recs and tc_ms > 0:
             ach = tc_fl / (tc_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05.mma kind::f16 + TMA)", "achieved": ach, "peak": pk["bf16_tflops"],
-                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"],
+                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["source"],
                     "launches_per_step": len(recs) / min(a.steps, 3), "kernel_ms_per_step": tc_ms / min(a.steps, 3),
                     "share_of_step": (tc_ms / min(a.steps, 3)) / ms_step, "mma_terms": nterms,
                     "issued_frac": nterms * ach / pk["bf16_tflops"],
@@ -224,7 +233,7 @@ def run_ours(a):
         rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:45]
         tot = sum(e.device_time_total for e in prof.key_averages())
         for e in rows:
-            print("[prof] %-64s x%4d %9.3f ms %5.1f%%" % (e.key[:64], e.count, e.device_time_total / 1e3 / 2, 100.0 * e.device_time_total / tot),
+            print("[prof] %-110s x%4d %9.3f ms %5.1f%%" % (e.key.replace("(anonymous namespace)::", "")[:110], e.count, e.device_time_total / 1e3 / 2, 100.0 * e.device_time_total / tot),
                   file=sys.stderr)
         print("[prof] total device time per step %.3f ms" % (tot / 1e3 / 2), file=sys.stderr)
 

@@ -161,7 +161,42 @@ struct TcArgs {
   PnpDropout drop;
   double* bn_sum;
   double* bn_sumsq;
+  // phases: a strided data gradient is s*s independent stride-1 convolutions ("phases"), each over its own subset of the
+  // taps (every tap belongs to exactly one phase) and its own output sub-grid; all of them run in ONE persistent launch.
+  int total_tiles;            // all phases, all (m, n) tiles
+  int nphases;                // 0: single phase described by the fields above
+  struct Phase {
+    short tap_begin, tap_count, py, px;
+    int U, V, tiles_x, tiles_y, tile_base;    // tile_base: first global tile id of this phase
+  } ph[16];
 };
+
+struct TileCoord {
+  int x0, y0, img0, n0, tap_begin, tap_count, U, V, py, px;
+};
+
+template <int BLOCK_N>
+__device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int t, int n_tiles) {
+  TileCoord c;
+  int tiles_x = a.tiles_x, tiles_y = a.tiles_y;
+  c.tap_begin = 0; c.tap_count = a.ntaps; c.U = a.U; c.V = a.V; c.py = a.out_py; c.px = a.out_px;
+  if (a.nphases > 0) {
+    int p = 0;
+    while (p + 1 < a.nphases && t >= a.ph[p + 1].tile_base) ++p;
+    t -= a.ph[p].tile_base;
+    tiles_x = a.ph[p].tiles_x; tiles_y = a.ph[p].tiles_y;
+    c.tap_begin = a.ph[p].tap_begin; c.tap_count = a.ph[p].tap_count;
+    c.U = a.ph[p].U; c.V = a.ph[p].V; c.py = a.ph[p].py; c.px = a.ph[p].px;
+  }
+  int mt = t / n_tiles;
+  c.n0 = (t - mt * n_tiles) * BLOCK_N;
+  const int txi = mt % tiles_x;
+  mt /= tiles_x;
+  const int tyi = mt % tiles_y;
+  const int tni = mt / tiles_y;
+  c.x0 = txi * a.tw; c.y0 = tyi * a.th; c.img0 = tni * a.tn;
+  return c;
+}
 
 template <int BLOCK_N, int NTERMS>
 struct TcCfg {
@@ -196,10 +231,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = a.Cout / BLOCK_N;
-  const int m_tiles = a.tiles_x * a.tiles_y * a.tiles_n;
-  const int num_tiles = m_tiles * n_tiles;
+  const int num_tiles = a.total_tiles;
   const int kchunks = a.Cin / BLOCK_K;
-  const int num_kb = a.ntaps * kchunks;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a_hi);
@@ -229,16 +262,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int mt = t / n_tiles;
-        const int n0 = (t - mt * n_tiles) * BLOCK_N;
-        const int txi = mt % a.tiles_x;
-        mt /= a.tiles_x;
-        const int tyi = mt % a.tiles_y;
-        const int tni = mt / a.tiles_y;
-        const int x0 = txi * a.tw, y0 = tyi * a.th, img0 = tni * a.tn;
+        const TileCoord tc = decode_tile<BLOCK_N>(a, t, n_tiles);
+        const int x0 = tc.x0, y0 = tc.y0, img0 = tc.img0, n0 = tc.n0;
+        const int num_kb = tc.tap_count * kchunks;
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / kchunks;
-          const int kc = kb - tap * kchunks;
+          const int tl = kb / kchunks;
+          const int kc = kb - tl * kchunks;
+          const int tap = tc.tap_begin + tl;
           mbar_wait(smem_u32(&bars[STAGES + stage]), phase ^ 1);
           const uint32_t full = smem_u32(&bars[stage]);
           mbar_expect_tx(full, tx_bytes);
@@ -265,6 +295,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int num_kb = decode_tile<BLOCK_N>(a, t, n_tiles).tap_count * kchunks;
         mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);     // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -315,16 +346,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      int mt = t / n_tiles;
-      const int n0 = (t - mt * n_tiles) * BLOCK_N;
-      const int txi = mt % a.tiles_x;
-      mt /= a.tiles_x;
-      const int tyi = mt % a.tiles_y;
-      const int tni = mt / a.tiles_y;
-      const int x0 = txi * a.tw, y0 = tyi * a.th, img0 = tni * a.tn;
-      const int img = img0 + ni, u = y0 + yy, v_ = x0 + xx;
-      const bool valid = (ni < a.tn) && (img < a.B) && (u < a.U) && (v_ < a.V);
-      const int oy = u * a.out_mul + a.out_py, ox = v_ * a.out_mul + a.out_px;
+      const TileCoord tc = decode_tile<BLOCK_N>(a, t, n_tiles);
+      const int n0 = tc.n0;
+      const int img = tc.img0 + ni, u = tc.y0 + yy, v_ = tc.x0 + xx;
+      const bool valid = (ni < a.tn) && (img < a.B) && (u < tc.U) && (v_ < tc.V);
+      const int oy = u * a.out_mul + tc.py, ox = v_ * a.out_mul + tc.px;
       const long long pix = ((long long)img * a.OH + oy) * a.OW + ox;
       float* orow = out + pix * a.Cout + n0;
 
@@ -747,7 +773,7 @@ int launch_tc(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensor
     PNP_CUDA(cudaGetDevice(&dev));
     PNP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const long long tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n * (a.Cout / BLOCK_N);
+  const long long tiles = a.total_tiles;
   dim3 grid((unsigned)(tiles < num_sms ? tiles : num_sms));     // persistent: one CTA per SM walks the tile list
   conv_tc_kernel<BLOCK_N, NTERMS><<<grid, 192, Cfg::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, y, a);
   PNP_LAUNCH_CHECK();
@@ -781,10 +807,10 @@ PnpDropout make_drop(const pnp_dropout_cfg* d) {
 // one launch of the generalized tap-table convolution: A planes [B, AH, AW, Cin] -> out [B, OH, OW, Cout]
 int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_stride, const uint16_t* w_hi, const uint16_t* w_lo,
            long long w_rows, float* out, TcArgs& a, int nterms, cudaStream_t s) {
-  int rc = choose_tile(a.U, a.V, a.B, BLOCK_M, 0, &a.tw, &a.th, &a.tn);
+  int rc = choose_tile(a.U, a.V, a.B, BLOCK_M, 0, &a.tw, &a.th, &a.tn);     // (a.U, a.V): largest phase extent
   if (rc) return rc;
-  a.tiles_x = a.V / a.tw;
-  if (a.V % a.tw != 0) return PNP_ERR_UNSUPPORTED;
+  a.tiles_x = pnp_cdiv(a.V, a.tw);
+  if (a.nphases == 0 && a.V % a.tw != 0) return PNP_ERR_UNSUPPORTED;
   a.tiles_y = pnp_cdiv(a.U, a.th);
   a.tiles_n = pnp_cdiv(a.B, a.tn);
   // N = 256 tiles halve the shared-memory operand traffic per MMA (the 128x128 tile is shared-memory-bandwidth bound:
@@ -794,6 +820,21 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
   {
     const long long mtiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n;
     if (a.Cout % 256 == 0 && mtiles * (a.Cout / 256) >= 96) block_n = 256;
+  }
+  {
+    const int n_tiles = a.Cout / block_n;
+    if (a.nphases == 0) {
+      a.total_tiles = a.tiles_x * a.tiles_y * a.tiles_n * n_tiles;
+    } else {
+      int base = 0;
+      for (int p = 0; p < a.nphases; ++p) {
+        a.ph[p].tiles_x = pnp_cdiv(a.ph[p].V, a.tw);
+        a.ph[p].tiles_y = pnp_cdiv(a.ph[p].U, a.th);
+        a.ph[p].tile_base = base;
+        base += a.ph[p].tiles_x * a.ph[p].tiles_y * a.tiles_n * n_tiles;
+      }
+      a.total_tiles = base;
+    }
   }
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   rc = make_act_map(&ma_hi, a_hi, a.B, AH, AW, a.Cin, a.tw, a.th, a.tn, a_stride);
@@ -876,7 +917,7 @@ extern "C" int pnp_conv2d_tc_fwd(const uint16_t* x_hi, const uint16_t* x_lo, con
   if (!tc_geom_ok(g)) return PNP_ERR_UNSUPPORTED;
   TcArgs a;
   a.B = g->B; a.OH = g->Ho; a.OW = g->Wo; a.Cout = g->Cout; a.Cin = g->Cin;
-  a.U = g->Ho; a.V = g->Wo; a.out_mul = 1; a.out_py = 0; a.out_px = 0; a.in_mul = g->stride;
+  a.U = g->Ho; a.V = g->Wo; a.out_mul = 1; a.out_py = 0; a.out_px = 0; a.in_mul = g->stride; a.nphases = 0;
   a.ntaps = g->kh * g->kw;
   for (int ky = 0; ky < g->kh; ++ky)
     for (int kx = 0; kx < g->kw; ++kx) {
@@ -909,15 +950,20 @@ extern "C" int pnp_conv2d_tc_dgrad(const uint16_t* dy_hi, const uint16_t* dy_lo,
     for (int k = 0; k < g->kw; ++k) hx = hx || ((p + g->pad_l - k * g->dil) % s == 0);
     if (!hy || !hx) return PNP_ERR_UNSUPPORTED;
   }
+  TcArgs a;
+  a.B = g->B; a.OH = g->H; a.OW = g->W; a.Cout = g->Cin; a.Cin = g->Cout;
+  a.out_mul = s; a.out_py = 0; a.out_px = 0; a.in_mul = 1;
+  a.accumulate = accumulate;
+  a.drop = make_drop(nullptr);
+  a.bn_sum = nullptr;
+  a.bn_sumsq = nullptr;
+  a.U = 0; a.V = 0;
+  int np = 0, nt = 0;
   for (int py = 0; py < s; ++py)
     for (int px = 0; px < s; ++px) {
-      TcArgs a;
-      a.B = g->B; a.OH = g->H; a.OW = g->W; a.Cout = g->Cin; a.Cin = g->Cout;
-      a.U = (g->H - py + s - 1) / s;
-      a.V = (g->W - px + s - 1) / s;
-      if (a.U <= 0 || a.V <= 0) continue;
-      a.out_mul = s; a.out_py = py; a.out_px = px; a.in_mul = 1;
-      int nt = 0;
+      const int U = (g->H - py + s - 1) / s, V = (g->W - px + s - 1) / s;
+      if (U <= 0 || V <= 0) continue;
+      a.ph[np].tap_begin = (short)nt;
       for (int ky = 0; ky < g->kh; ++ky) {
         int ny = py + g->pad_t - ky * g->dil;
         if (ny % s != 0) continue;
@@ -930,14 +976,18 @@ extern "C" int pnp_conv2d_tc_dgrad(const uint16_t* dy_hi, const uint16_t* dy_lo,
           ++nt;
         }
       }
-      a.ntaps = nt;
-      a.accumulate = accumulate;
-      a.drop = make_drop(nullptr);
-      a.bn_sum = nullptr;
-      a.bn_sumsq = nullptr;
-      int rc = run_tc(dy_hi, dy_lo, g->Ho, g->Wo, 1, w_hi, w_lo, (long long)g->kh * g->kw * g->Cin, dx, a, nterms, (cudaStream_t)stream);
-      if (rc) return rc;
+      a.ph[np].tap_count = (short)(nt - a.ph[np].tap_begin);
+      a.ph[np].py = (short)py; a.ph[np].px = (short)px;
+      a.ph[np].U = U; a.ph[np].V = V;
+      if (U > a.U) a.U = U;
+      if (V > a.V) a.V = V;
+      ++np;
     }
+  a.ntaps = nt;
+  a.nphases = (s == 1) ? 0 : np;
+  if (s == 1) { a.out_py = 0; a.out_px = 0; }
+  int rc = run_tc(dy_hi, dy_lo, g->Ho, g->Wo, 1, w_hi, w_lo, (long long)g->kh * g->kw * g->Cin, dx, a, nterms, (cudaStream_t)stream);
+  if (rc) return rc;
   return PNP_OK;
 }
 

@@ -87,25 +87,41 @@ bn_reduce_kernel(const float* __restrict__ z, const float* __restrict__ dy, cons
     }
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
     int cnt = 0;
-    for (long long r = r0 + rlane; r < r1; r += rstep) {
-      long long off = r * C4 + q;
-      float4 zv = __ldg(reinterpret_cast<const float4*>(z) + off);
+    // two rows per iteration: all loads of both rows are issued before either is consumed (memory-level parallelism)
+    for (long long r = r0 + rlane; r < r1; r += 2 * rstep) {
+      const long long offA = r * C4 + q;
+      const bool hasB = (r + rstep) < r1;
+      const long long offB = hasB ? (r + rstep) * C4 + q : offA;
+      float4 zA = __ldg(reinterpret_cast<const float4*>(z) + offA);
+      float4 zB = __ldg(reinterpret_cast<const float4*>(z) + offB);
       if (WITH_G) {
-        float4 g = __ldg(reinterpret_cast<const float4*>(dy) + off);
+        float4 gA = __ldg(reinterpret_cast<const float4*>(dy) + offA);
+        float4 gB = __ldg(reinterpret_cast<const float4*>(dy) + offB);
         if (act != PNP_ACT_NONE) {
-          float4 yv = __ldg(reinterpret_cast<const float4*>(yact) + off);
-          g.x *= act_slope(yv.x, act); g.y *= act_slope(yv.y, act);
-          g.z *= act_slope(yv.z, act); g.w *= act_slope(yv.w, act);
+          float4 yA = __ldg(reinterpret_cast<const float4*>(yact) + offA);
+          float4 yB = __ldg(reinterpret_cast<const float4*>(yact) + offB);
+          gA.x *= act_slope(yA.x, act); gA.y *= act_slope(yA.y, act); gA.z *= act_slope(yA.z, act); gA.w *= act_slope(yA.w, act);
+          gB.x *= act_slope(yB.x, act); gB.y *= act_slope(yB.y, act); gB.z *= act_slope(yB.z, act); gB.w *= act_slope(yB.w, act);
         }
-        reinterpret_cast<float4*>(gout)[off] = g;
-        a0 += g.x; a1 += g.y; a2 += g.z; a3 += g.w;
-        b0 += g.x * (zv.x - mu.x) * is.x; b1 += g.y * (zv.y - mu.y) * is.y;
-        b2 += g.z * (zv.z - mu.z) * is.z; b3 += g.w * (zv.w - mu.w) * is.w;
+        reinterpret_cast<float4*>(gout)[offA] = gA;
+        a0 += gA.x; a1 += gA.y; a2 += gA.z; a3 += gA.w;
+        b0 += gA.x * (zA.x - mu.x) * is.x; b1 += gA.y * (zA.y - mu.y) * is.y;
+        b2 += gA.z * (zA.z - mu.z) * is.z; b3 += gA.w * (zA.w - mu.w) * is.w;
+        if (hasB) {
+          reinterpret_cast<float4*>(gout)[offB] = gB;
+          a0 += gB.x; a1 += gB.y; a2 += gB.z; a3 += gB.w;
+          b0 += gB.x * (zB.x - mu.x) * is.x; b1 += gB.y * (zB.y - mu.y) * is.y;
+          b2 += gB.z * (zB.z - mu.z) * is.z; b3 += gB.w * (zB.w - mu.w) * is.w;
+        }
       } else {
-        a0 += zv.x; a1 += zv.y; a2 += zv.z; a3 += zv.w;
-        b0 += zv.x * zv.x; b1 += zv.y * zv.y; b2 += zv.z * zv.z; b3 += zv.w * zv.w;
+        a0 += zA.x; a1 += zA.y; a2 += zA.z; a3 += zA.w;
+        b0 += zA.x * zA.x; b1 += zA.y * zA.y; b2 += zA.z * zA.z; b3 += zA.w * zA.w;
+        if (hasB) {
+          a0 += zB.x; a1 += zB.y; a2 += zB.z; a3 += zB.w;
+          b0 += zB.x * zB.x; b1 += zB.y * zB.y; b2 += zB.z * zB.z; b3 += zB.w * zB.w;
+        }
       }
-      if (++cnt == 64) {   // keep fp32 partial sums short, promote to fp64
+      if (++cnt == 32) {   // keep fp32 partial sums short (64 rows), promote to fp64
         da[0] += a0; da[1] += a1; da[2] += a2; da[3] += a3; da[4] += b0; da[5] += b1; da[6] += b2; da[7] += b3;
         a0 = a1 = a2 = a3 = b0 = b1 = b2 = b3 = 0.f;
         cnt = 0;

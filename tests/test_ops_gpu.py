@@ -238,7 +238,13 @@ def test_fused_bn_stats_match_separate_pass():
     L, ops, F, rt = _prod()
     rt.reset_default_graph()
     rt.set_conv_backend("tc3")
-    x, w = randn((3, 32, 32, 64), 41), randn((3, 3, 64, 128), 42, 0.1)
+    _fused_vs_separate(L, F, rt, randn((3, 32, 32, 64), 41), randn((3, 3, 64, 128), 42, 0.1))
+    # enough tiles for the 128x256 accumulator variant of the persistent kernel (two TMEM buffers of 256 columns)
+    _fused_vs_separate(L, F, rt, randn((8, 32, 32, 256), 43), randn((3, 3, 256, 512), 44, 0.05))
+    rt.set_conv_backend("auto")
+
+
+def _fused_vs_separate(L, F, rt, x, w):
     outs = []
     for fuse in (True, False):
         rt.reset_default_graph()
@@ -249,7 +255,6 @@ def test_fused_bn_stats_match_separate_pass():
     check("y", outs[0][0], outs[1][0], 1e-5)
     check("moving_mean", outs[0][1], outs[1][1], 1e-5)
     check("moving_var", outs[0][2], outs[1][2], 1e-5)
-    rt.set_conv_backend("auto")
 
 
 def test_maxpool():
