@@ -179,3 +179,46 @@ def test_data_parallel_gloo_world_size_2():
         assert world == 2 and rank == r and scale == 0.5
         assert gsum == 3.0 and gsum * scale == 1.5      # (1 + 2) / 2
         assert th == 0.0                                # rank 0's parameters everywhere
+
+
+def test_checkpoint_transplant_chain_baseline_to_gan(tmp_path):
+    """train_segmenter.py checkpoint -> `--phase pre-train` initialisation:
+    restore(no_gan=True) takes only group*/output* conv weights (adversarial.py:514-532), load_batch_norm_weights maps the
+    baseline's anonymous BatchNorm_k scopes onto group_g/pred_* in creation order (lists/old_bn_list -> lists/pred_bn_list,
+    adversarial.py:743-765), adapt_copy_weights clones the MR front into the CT DAM (lists/half_zip_*_vars, :706-741)."""
+    import pnp_b200
+    from pnp_b200 import runtime as rt, source_segmenter as seg, adversarial as adv
+    from pnp_b200.lib import _save
+    from pnp_b200.train_gan import configure
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_var_names.json")))
+    seg.Full_DRN(channels=3, n_class=5, batch_size=2, cost_kwargs={"cross_flag": True, "miu_cross": 1.0, "miu_dice": 1.0})
+    rng = np.random.RandomState(3)
+    base = {n: rng.randn(*v.shape).astype(np.float32) for n, v in rt.graph.vars.items()}
+    rt.load_state_dict(base)
+    ck = _save(rt.state_dict(), str(tmp_path / "model.cpkt"), global_step=7)
+    assert ck.endswith("model.cpkt-7.npz")
+    c, nc, tc = configure("pre-train")
+    net = adv.Full_DRN(channels=3, n_class=5, batch_size=2, cost_kwargs=c, network_config=nc)
+    before = {n: v.detach().clone() for n, v in rt.graph.vars.items()}
+    net.restore(ck, no_gan=True)
+    net.load_batch_norm_weights(ck)
+    net.adapt_copy_weights()
+    v = rt.graph.vars
+    # conv weights of the frozen segmenter come from the baseline, name for name
+    for n in base:
+        if "/Variable" in n:
+            assert np.array_equal(v[n].numpy(), base[n]), n
+    # BN: old_bn_list[i] -> pred_bn_list[i]  (the reference's two lists are index-aligned)
+    scope_of = {}
+    for n in v:
+        if "/pred_" in n:
+            scope_of[n.split("/", 1)[1]] = n
+    for old, new in zip(gold["old_bn_list"], gold["pred_bn_list"]):
+        assert np.array_equal(v[scope_of[new]].numpy(), base[old]), (old, new)
+    # DAM initialised from the MR front: half_zip_mri_vars[i] -> half_zip_ct_vars[i]
+    for m, c_ in zip(gold["half_zip_mri_vars"], gold["half_zip_ct_vars"]):
+        assert np.array_equal(v[c_].numpy(), v[m].numpy()), (m, c_)
+    # critics untouched
+    for n in v:
+        if "cls" in n:
+            assert torch.equal(v[n], before[n]), n
