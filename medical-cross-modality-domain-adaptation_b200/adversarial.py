@@ -363,7 +363,7 @@ class Trainer(object):
         self._mode = mode
 
     # ---- the two hot steps --------------------------------------------------------------------------------------------
-    def d_step(self, mr_batch, ct_batch, keep_prob=0.75):
+    def d_step(self, mr_batch, ct_batch, keep_prob=0.75, apply=True):
         """adversarial.py:840-862: feed mr+ct, all segmenter BN switches False, dropout on; dis_optimizer; clip."""
         net = self.net
         self._set_mode("D")
@@ -380,12 +380,17 @@ class Trainer(object):
             mr_m = net.create_mask_critic(fm["logits"])
         terms = net.dis_loss_terms(ct_cls, mr_cls, ct_m, mr_m)
         torch.autograd.backward([t for t, _ in terms], [self._one, self._lam][:len(terms)])
+        if apply:
+            self.d_apply()
+        return terms
+
+    def d_apply(self):
+        """the data-parallel exchange + update of a D step: ONE all-reduce over the gradient arena, then RMSProp + clip"""
         scale = self.dp.allreduce(self.d_arena.grad)
         self.dis_optimizer.step(grad_scale=scale)
         self.global_step += 1
-        return terms
 
-    def g_step(self, ct_batch, keep_prob=0.75):
+    def g_step(self, ct_batch, keep_prob=0.75, apply=True):
         """adversarial.py:869-882: feed ct only, ct_front_bn True (DAM BN trains), others False; gen_optimizer."""
         net = self.net
         self._set_mode("G")
@@ -396,10 +401,14 @@ class Trainer(object):
         ct_m = net.create_mask_critic(fc_["logits"]) if net.lambda_mask_loss != 0 else None
         terms = net.gen_loss_terms(ct_cls, ct_m)
         torch.autograd.backward([t for t, _ in terms], [self._one, self._lam][:len(terms)])
+        if apply:
+            self.g_apply()
+        return terms
+
+    def g_apply(self):
         scale = self.dp.allreduce(self.g_arena.grad)
         self.gen_optimizer.step(grad_scale=scale)
         self.global_step += 1
-        return terms
 
     @staticmethod
     def loss_value(terms):
