@@ -126,16 +126,27 @@ def run_ours(a):
     ct_src = SyntheticSource(B, seed=4321 + rank, shift=0.3, scale=0.8, pool=3)
     dev_pool = [(m[0].to(dev), c[0].to(dev)) for m, c in zip(mr_src.pool, ct_src.pool)]
 
+    graphed = False
+    if a.graph:
+        graphed = trainer.capture_joint_step(dev_pool[0][0], dev_pool[0][1], a.keep_prob)
+    launches_per_step = [None]
+
     def step_resident(i):
         mr, ct = dev_pool[i % len(dev_pool)]
-        trainer.d_step(mr, ct, a.keep_prob)
-        trainer.g_step(ct, a.keep_prob)
+        if graphed and F.PROFILE is None:
+            trainer.joint_step(mr, ct, a.keep_prob)
+        else:
+            trainer.d_step(mr, ct, a.keep_prob)
+            trainer.g_step(ct, a.keep_prob)
 
     def step_e2e(i):
         mr_h, ct_h = mr_src.pool[i % 3][0], ct_src.pool[i % 3][0]
-        mr, ct = mr_h.to(dev, non_blocking=True), ct_h.to(dev, non_blocking=True)
-        d = trainer.d_step(mr, ct, a.keep_prob)
-        g = trainer.g_step(ct, a.keep_prob)
+        if graphed:
+            d, g = trainer.joint_step(mr_h, ct_h, a.keep_prob)      # pinned host -> static device buffers -> graph replay
+        else:
+            mr, ct = mr_h.to(dev, non_blocking=True), ct_h.to(dev, non_blocking=True)
+            d = trainer.d_step(mr, ct, a.keep_prob)
+            g = trainer.g_step(ct, a.keep_prob)
         return trainer.loss_value(d), trainer.loss_value(g)     # .item() reads: device -> host every step
 
     def barrier():
@@ -159,14 +170,18 @@ def run_ours(a):
         barrier()
         return float(t.item())
 
+    # kernel launches of one step, counted on an eager step (a graph replay issues the same kernels without host calls)
+    l0 = _C.launch_count
+    trainer.d_step(dev_pool[0][0], dev_pool[0][1], a.keep_prob)
+    trainer.g_step(dev_pool[0][1], a.keep_prob)
+    launches_per_step[0] = _C.launch_count - l0
     for i in range(a.warmup):
         step_resident(i)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = _C.launch_count
     ms_total = timed(step_resident, a.steps)
-    launches = _C.launch_count - l0
+    launches = launches_per_step[0] * a.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / a.steps
     slices_per_step = 3 * B * world
@@ -249,7 +264,7 @@ def run_ours(a):
             "dtype": "f32 (tcgen05 bf16 hi/lo split x%d, fp32 accumulate)" % (1 if a.backend == "tc1" else 3), "data": "synthetic",
             "config": {"workload": "train_gan.py --phase train-gan joint step: 1 D update (B MR + B CT, +clip) + 1 G update (B CT); "
                                    "BASELINE configs[3] at N GPUs", "batch_per_gpu_per_domain": B, "slices_per_step": slices_per_step,
-                       "keep_prob": a.keep_prob, "conv_backend": a.backend, "parallelism": "dp%d" % world,
+                       "keep_prob": a.keep_prob, "conv_backend": a.backend, "parallelism": "dp%d" % world, "cuda_graph": bool(graphed),
                        "l2": "per-step working set (activations of %d slices, GBs) exceeds the 126 MB L2; no explicit flush" % (3 * B)},
             "conv_tflops_algorithmic": gf_step / ms_step / 1e3,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
@@ -324,6 +339,8 @@ def main():
     ap.add_argument("--keep-prob", type=float, default=0.75)
     ap.add_argument("--backend", default="auto", choices=["auto", "simt", "tc3", "tc1"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", dest="graph", action="store_true", default=True, help="replay the step as one CUDA graph (default)")
+    ap.add_argument("--no-graph", dest="graph", action="store_false")
     ap.add_argument("--profile", action="store_true", help="print a per-kernel device-time table (torch profiler) to stderr")
     a = ap.parse_args()
     if a.impl == "reference":

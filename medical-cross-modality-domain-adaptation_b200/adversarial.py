@@ -410,6 +410,46 @@ class Trainer(object):
         self.gen_optimizer.step(grad_scale=scale)
         self.global_step += 1
 
+    # ---- the joint adversarial step as ONE CUDA graph ---------------------------------------------------------------
+    def capture_joint_step(self, mr_example, ct_example, keep_prob=0.75, warmup=2):
+        """Capture `d_step(mr, ct)` + `g_step(ct)` (forward, backward, all-reduce, optimizer, clip: ~1.4 k kernel launches)
+        into one CUDA graph on static input buffers.  Dropout seeds, optimizer hyper-state and BN statistics live in device
+        memory, so every replay is a genuinely new training step.  Returns False (and stays eager) if capture fails."""
+        self._graph = None
+        try:
+            self._gx_mr = mr_example.clone()
+            self._gx_ct = ct_example.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self.d_step(self._gx_mr, self._gx_ct, keep_prob)
+                    self.g_step(self._gx_ct, keep_prob)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                d = self.d_step(self._gx_mr, self._gx_ct, keep_prob)
+                gg = self.g_step(self._gx_ct, keep_prob)
+            self._graph, self._graph_out, self._graph_kp = g, (d, gg), keep_prob
+            return True
+        except Exception as e:      # noqa: BLE001 -- any capture problem => eager path, loudly
+            import warnings
+            warnings.warn("CUDA-graph capture of the adversarial step failed (%s: %s); running eagerly" % (type(e).__name__, e))
+            self._graph = None
+            torch.cuda.synchronize()
+            return False
+
+    def joint_step(self, mr_batch, ct_batch, keep_prob=0.75):
+        """one full adversarial step (D update + clip, then G update); replays the captured graph when there is one"""
+        if getattr(self, "_graph", None) is not None and keep_prob == self._graph_kp:
+            self._gx_mr.copy_(mr_batch, non_blocking=True)
+            self._gx_ct.copy_(ct_batch, non_blocking=True)
+            self._graph.replay()
+            self.global_step += 2
+            return self._graph_out
+        return self.d_step(mr_batch, ct_batch, keep_prob), self.g_step(ct_batch, keep_prob)
+
     @staticmethod
     def loss_value(terms):
         return sum(float(t.detach()) * w for t, w in terms)

@@ -244,3 +244,28 @@ def test_config4_joint_adversarial_step(backend):
     assert abs(got - rg["gen_loss"]) <= 1e-3 * max(abs(rg["gen_loss"]), 2e-3 * float(rg["ct_cls"].abs().max()))
     _compare_state(rt, oracle, 1e-3)
     rt.set_conv_backend("auto")
+
+
+def test_cuda_graph_replay_equals_eager_steps():
+    """Trainer.capture_joint_step: replaying the captured D+G step k times == k eager joint steps (same data, dropout off):
+    the graph must carry every side effect of a step (BN moving statistics, RMSProp slots, clip, seeds) in device memory."""
+    from pnp_b200 import runtime as rt
+    from oracle.pnp_graphs import synthetic_images
+    mr, ct = synthetic_images(B, 1234).to(DEV), synthetic_images(B, 4321, 0.3, 0.8).to(DEV)
+    states = []
+    for use_graph in (False, True):
+        net, trainer, _ = _adv_pair("simt", 0.3, "train-gan")
+        if use_graph:
+            assert trainer.capture_joint_step(mr, ct, keep_prob=1.0, warmup=1), "CUDA-graph capture failed"
+            for _ in range(2):
+                d, g = trainer.joint_step(mr, ct, keep_prob=1.0)
+        else:
+            for _ in range(3):
+                d, g = trainer.joint_step(mr, ct, keep_prob=1.0)
+        torch.cuda.synchronize()
+        states.append((rt.state_dict(), trainer.loss_value(d), trainer.loss_value(g)))
+    (sa, da, ga), (sb, db, gb) = states
+    worst = max(rel_err(torch.tensor(sb[n]), torch.tensor(sa[n])) for n in sa)
+    print("  graph vs eager after 3 joint steps: worst variable rel err %.3e, dis_loss %.6e / %.6e" % (worst, da, db))
+    assert worst <= 1e-4 and abs(da - db) <= 1e-4 * max(abs(da), 1e-6) and abs(ga - gb) <= 1e-4 * max(abs(ga), 1e-6)
+    rt.set_conv_backend("auto")
