@@ -271,8 +271,21 @@ def run_ours(a):
         }
         print(json.dumps(out))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # teardown must never hang the launcher: drop the captured graph (it pins NCCL work) before the last barrier, and
+        # leave through a watchdog-protected hard exit
+        sys.stdout.flush()
+        sys.stderr.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        trainer._graph = None
+        trainer._graph_out = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+        os._exit(0)
 
 
 def cpu_baseline_sample(B, reps):
