@@ -310,6 +310,7 @@ class Trainer(object):
         self.train_config = dict(train_config)
         self.lr_update_flag = self.train_config.get("lr_update", False)
         self.mr_source, self.ct_source = mr_source, ct_source
+        self.mr_train_list, self.ct_train_list = mr_train_list, ct_train_list
         self.dp = parallel.DataParallel()
         self.global_step = 0
         self.dis_sub_iter = self.train_config.get("dis_sub_iter", 1)
@@ -410,6 +411,15 @@ class Trainer(object):
         self.gen_optimizer.step(grad_scale=scale)
         self.global_step += 1
 
+    def evaluate(self, ct_batch, ct_labels_onehot):
+        """adversarial.py:894-922 (CT validation statistics): inference-mode forward of the adapted segmenter (DAM + shared back
+        half, moving-statistics BN, keep_prob 1) -> hard Dice (background included) and the confusion matrix"""
+        with torch.no_grad():
+            out = self.net.segment(ct_batch, "ct", 1.0, front_bn=False, joint_bn=False)
+            dice, arr = self.net.dice_eval(out["logits"], ct_labels_onehot)
+            cm = F.confusion_counts(out["logits"], ct_labels_onehot)
+        return {"dice_eval": float(dice), "dice_arr": [float(a) for a in arr], "confusion_matrix": cm.cpu().numpy()}
+
     # ---- the joint adversarial step as ONE CUDA graph ---------------------------------------------------------------
     def capture_joint_step(self, mr_example, ct_example, keep_prob=0.75, warmup=2):
         """Capture `d_step(mr, ct)` + `g_step(ct)` (forward, backward, all-reduce, optimizer, clip: ~1.4 k kernel launches)
@@ -472,8 +482,15 @@ class Trainer(object):
             self.dis_optimizer.set_lr(self.LR_refresh)
             self.gen_optimizer.set_lr(self.LR_refresh)
         B = self.batch_size
-        mr_src = self.mr_source or SyntheticSource(B, seed=1234 + self.dp.rank, num_cls=self.num_cls or 5)
-        ct_src = self.ct_source or SyntheticSource(B, seed=4321 + self.dp.rank, shift=0.3, scale=0.8, num_cls=self.num_cls or 5)
+        def source(given, files, seed, **kw):
+            if given is not None:
+                return given
+            if files:                  # lists/{mr,ct}_train_list: single-example TFRecord files (README.md:49-64)
+                from .tfrecord import TFRecordSource
+                return TFRecordSource(files, B, seed=seed + self.dp.rank)
+            return SyntheticSource(B, seed=seed + self.dp.rank, num_cls=self.num_cls or 5, **kw)
+        mr_src = source(self.mr_source, self.mr_train_list, 1234)
+        ct_src = source(self.ct_source, self.ct_train_list, 4321, shift=0.3, scale=0.8)
         dev = rt.device()
         dis_interval, gen_interval = cfg.get("dis_interval", 1), cfg.get("gen_interval", 1)
         dis_inc, gen_inc = cfg.get("dis_sub_iter_inc", 0), cfg.get("gen_sub_iter_inc", 0)

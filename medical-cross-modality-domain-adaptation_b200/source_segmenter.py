@@ -196,7 +196,13 @@ class Trainer(object):
                 self.optimizer.set_lr(self._new_LR)
         elif restore:
             print("Unable to restore, start from beginning")
-        src = self.source or SyntheticSource(self.batch_size, seed=1234 + self.dp.rank, num_cls=self.num_cls)
+        if self.source is not None:
+            src = self.source
+        elif self.train_list:      # the reference's lists/*_train_list of single-example TFRecord files
+            from .tfrecord import TFRecordSource
+            src = TFRecordSource(self.train_list, self.batch_size, seed=1234 + self.dp.rank)
+        else:
+            src = SyntheticSource(self.batch_size, seed=1234 + self.dp.rank, num_cls=self.num_cls)
         for epoch in range(epochs):
             for step in range(epoch * training_iters, (epoch + 1) * training_iters):
                 start = time.time()

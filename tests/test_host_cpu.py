@@ -222,3 +222,34 @@ def test_checkpoint_transplant_chain_baseline_to_gan(tmp_path):
     for n in v:
         if "cls" in n:
             assert torch.equal(v[n], before[n]), n
+
+
+def test_tfrecord_reader_round_trip_and_reference_slicing(tmp_path):
+    """SURVEY 8f #2: the reference's TFRecord schema (README.md:49-64) decoded without TensorFlow; label = middle slice"""
+    from pnp_b200 import tfrecord as tfr
+    assert tfr.crc32c(b"123456789") == 0xE3069283                      # CRC-32C check value
+    rng = np.random.RandomState(0)
+    files = []
+    truth = []
+    for i in range(5):
+        img = rng.randn(256, 256, 3).astype(np.float32)
+        lab = rng.randint(0, 5, (256, 256, 3)).astype(np.float32)
+        p = str(tmp_path / ("s%d.tfrecords" % i))
+        tfr.write_record(p, [tfr.encode_example(img, lab)])
+        files.append(p)
+        truth.append((img, lab))
+    ex = tfr.parse_example(next(tfr.read_records(files[2])))
+    assert ex["dsize_dim0"] == [256] and ex["dsize_dim2"] == [3] and ex["lsize_dim1"] == [256] and len(ex["data_vol"]) == 256 * 256 * 3 * 4
+    x, y = tfr.decode_slice(next(tfr.read_records(files[2])))
+    assert np.array_equal(x, truth[2][0]) and np.array_equal(y, truth[2][1][:, :, 1].astype(np.int64))
+    src = tfr.TFRecordSource(files, batch_size=3, seed=1)
+    xb, yb = src.next()
+    assert tuple(xb.shape) == (3, 256, 256, 3) and xb.dtype == torch.float32 and tuple(yb.shape) == (3, 256, 256) and yb.dtype == torch.int64
+    xb2, _ = src.next()                                                    # wraps around the 5-file list
+    assert tuple(xb2.shape) == (3, 256, 256, 3)
+    # corruption is detected
+    raw = bytearray(open(files[0], "rb").read())
+    raw[100] ^= 0xFF
+    open(files[0], "wb").write(bytes(raw))
+    with pytest.raises(IOError):
+        list(tfr.read_records(files[0]))
