@@ -131,6 +131,8 @@ int pnp_seed_advance(unsigned long long* seed_ptr, void* stream);
 /* tf.nn.max_pool 2x2/2 (layers.py:102-103) */
 int pnp_maxpool2_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream);
 int pnp_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, void* stream);
+/* tf.nn.avg_pool 2x2/2 (layers.py:105-106); backward != 0: in = dy [B,H/2,W/2,C], out = dx [B,H,W,C] */
+int pnp_avgpool2(const float* in, float* out, int B, int H, int W, int C, int backward, void* stream);
 /* tf.pad(..., 'SYMMETRIC') by p on each spatial side (layers.py:19-23,68-72) */
 int pnp_mirror_pad_fwd(const float* x, float* y, int B, int H, int W, int C, int p, void* stream);
 int pnp_mirror_pad_bwd(const float* dy, float* dx, int B, int H, int W, int C, int p, void* stream);

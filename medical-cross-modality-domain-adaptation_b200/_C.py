@@ -59,6 +59,7 @@ SIGNATURES = {
     "pnp_seed_advance": [P, P],
     "pnp_maxpool2_fwd": [P, P, c_int, c_int, c_int, c_int, P],
     "pnp_maxpool2_bwd": [P, P, P, c_int, c_int, c_int, c_int, P],
+    "pnp_avgpool2": [P, P, c_int, c_int, c_int, c_int, c_int, P],
     "pnp_mirror_pad_fwd": [P, P, c_int, c_int, c_int, c_int, c_int, P],
     "pnp_mirror_pad_bwd": [P, P, c_int, c_int, c_int, c_int, c_int, P],
     "pnp_phase_shift_fwd": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],

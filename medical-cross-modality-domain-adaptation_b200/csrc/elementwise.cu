@@ -355,6 +355,28 @@ maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, f
   }
 }
 
+// tf.nn.avg_pool 2x2/2 (layers.py:105-106); with_grad: dx = dy/4 broadcast to the window
+__global__ void __launch_bounds__(256)
+avgpool2_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C, int backward) {
+  const int Ho = H / 2, Wo = W / 2;
+  long long total = (long long)B * Ho * Wo * C;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    int c = (int)(i % C);
+    long long p = i / C;
+    int ox = (int)(p % Wo);
+    long long t = p / Wo;
+    int oy = (int)(t % Ho);
+    int b = (int)(t / Ho);
+    long long base = (((long long)b * H + 2 * oy) * W + 2 * ox) * C + c;
+    if (backward) {
+      float g = 0.25f * in[i];
+      out[base] = g; out[base + C] = g; out[base + (long long)W * C] = g; out[base + (long long)W * C + C] = g;
+    } else {
+      out[i] = 0.25f * (in[base] + in[base + C] + in[base + (long long)W * C] + in[base + (long long)W * C + C]);
+    }
+  }
+}
+
 __device__ __forceinline__ int mirror_idx(int i, int n) { return i < 0 ? (-i - 1) : (i >= n ? 2 * n - 1 - i : i); }
 
 __global__ void __launch_bounds__(256)
@@ -853,6 +875,15 @@ extern "C" int pnp_maxpool2_bwd(const float* x, const float* dy, float* dx, int 
   long long total = (long long)B * (H / 2) * (W / 2) * C;
   if (C % 4 == 0) maxpool2_bwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S_>>>(x, dy, dx, B, H, W, C);
   else maxpool2_bwd_kernel<1><<<grid_for(total, 256 * 4), 256, 0, S_>>>(x, dy, dx, B, H, W, C);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_avgpool2(const float* in, float* out, int B, int H, int W, int C, int backward, void* stream) {
+  if (!in || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
+  if ((H | W) & 1) return PNP_ERR_UNSUPPORTED;
+  long long total = (long long)B * (H / 2) * (W / 2) * C;
+  avgpool2_kernel<<<grid_for(total, 256 * 4), 256, 0, S_>>>(in, out, B, H, W, C, backward);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }

@@ -516,6 +516,28 @@ def max_pool2(x):
     return _MaxPool2Fn.apply(x)
 
 
+class _AvgPool2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        B, H, W, C = x.shape
+        y = torch.empty(B, H // 2, W // 2, C, dtype=x.dtype, device=x.device)
+        call("pnp_avgpool2", ptr(x), ptr(y), B, H, W, C, 0, rt.stream())
+        ctx.shape = (B, H, W, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, H, W, C = ctx.shape
+        dx = torch.empty(ctx.shape, dtype=dy.dtype, device=dy.device)
+        call("pnp_avgpool2", ptr(dy.contiguous()), ptr(dx), B, H, W, C, 1, rt.stream())
+        return dx
+
+
+def avg_pool2(x):
+    return _AvgPool2Fn.apply(x)
+
+
 class _PhaseShiftFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, r, G, order_b1):

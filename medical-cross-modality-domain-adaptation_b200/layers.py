@@ -192,8 +192,10 @@ def max_pool2d(x, n):
 
 
 def avg_pool2d(x, n):
-    """layers.py:105-106 -- not on the hot path (never called by the reference graphs)"""
-    raise NotImplementedError("avg_pool2d is unused by the reference graphs and not part of the B200 hot path")
+    """layers.py:105-106 (n must be 2; never called by the reference graphs, kept for surface completeness)"""
+    if n != 2:
+        raise NotImplementedError("avg_pool2d: only 2x2/2 pooling is implemented")
+    return F.avg_pool2(x)
 
 
 def simple_concat2d(x1, x2):

@@ -273,6 +273,20 @@ def test_maxpool():
         check("dx", xg.grad, xo.grad, 1e-7)
 
 
+def test_avgpool():
+    L, ops, F, rt = _prod()
+    x = randn((2, 8, 12, 6), 53)
+    xo = x.double().requires_grad_(True)
+    yo = torch.nn.functional.avg_pool2d(xo.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    r = randn(tuple(yo.shape), 54)
+    (yo * r.double()).sum().backward()
+    xg = _var(x)
+    y = L.avg_pool2d(xg, 2)
+    check("y", y, yo, 1e-6)
+    y.backward(r.to(DEV))
+    check("dx", xg.grad, xo.grad, 1e-6)
+
+
 @pytest.mark.parametrize("B", [1, 2, 3])
 @pytest.mark.parametrize("G", [1, 5])
 def test_phase_shift(B, G):
