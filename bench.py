@@ -210,7 +210,7 @@ def run_ours(a):
             c_ = by.setdefault(k_, [0, 0.0])
             c_[0] += 1
             c_[1] += s_.elapsed_time(e_)
-        top = sorted(by.items(), key=lambda kv: -kv[1][1])[:14]
+        top = sorted(by.items(), key=lambda kv: -kv[1][1])[:48]
         for (tag_, gf_), (n_, ms_) in top:
             print("[tc] %-18s %9.3f GF x%3d  %8.3f ms  %7.1f TF/s" % (tag_, gf_, n_, ms_, gf_ * n_ / ms_), file=sys.stderr)
         tc_ms = sum(s.elapsed_time(e) for s, e, _, _ in recs)

@@ -22,6 +22,7 @@
 // warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "../../include/pnp_b200.h"
@@ -139,6 +140,20 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// K-major operand tile whose rows are BK bf16 wide: BK = 64 -> 128-byte rows, SWIZZLE_128B (layout type 2, 8-row group = 1024 B);
+// BK = 32 -> 64-byte rows, SWIZZLE_64B (layout type 4, 8-row group = 512 B).  The 32-wide tile serves the Cin = 32 layers
+// natively (no zero-padded K) and halves the stage size of the 128x256 configuration (4 pipeline stages instead of 2).
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+  if (BK == 64) return make_kmajor_sw128_desc(smem_addr);
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10,
 // a/b major K (0) @15/@16, N>>3 @17, M>>4 @24
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
@@ -152,6 +167,7 @@ struct TcArgs {
   int out_mul, out_py, out_px;
   int in_mul;                 // TMA coordinate of tile origin = origin * in_mul + tap offset (stride of a strided forward conv)
   int Cin;                    // GEMM K per tap
+  int kchunks;                // Cin / BK
   int ntaps;
   short tap_oy[MAX_TAPS], tap_ox[MAX_TAPS];
   int tap_wrow[MAX_TAPS];     // first row of the tap's [N][K] slab in the weight plane
@@ -163,7 +179,11 @@ struct TcArgs {
   double* bn_sumsq;
   // phases: a strided data gradient is s*s independent stride-1 convolutions ("phases"), each over its own subset of the
   // taps (every tap belongs to exactly one phase) and its own output sub-grid; all of them run in ONE persistent launch.
-  int total_tiles;            // all phases, all (m, n) tiles
+  int total_tiles;            // all phases, all (m, n) tiles, times ksplit
+  int rot_mul;                // k-loop rotation per m-tile (see the producer)
+  int taps_inner;             // k-block order: 1 = channel chunk outer / taps inner (the shifted windows of one chunk hit L2)
+  int ksplit;                 // > 1: each (m, n) tile's k-blocks are divided among ksplit CTAs that atomically add their partial
+                              // sums into a zeroed output (few-tile, deep-K layers: 4x4 / 16x16 maps with 512 channels)
   int nphases;                // 0: single phase described by the fields above
   struct Phase {
     short tap_begin, tap_count, py, px;
@@ -172,13 +192,15 @@ struct TcArgs {
 };
 
 struct TileCoord {
-  int x0, y0, img0, n0, tap_begin, tap_count, U, V, py, px;
+  int x0, y0, img0, n0, tap_begin, tap_count, U, V, py, px, kb_begin, kb_count, mt;
 };
 
 template <int BLOCK_N>
 __device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int t, int n_tiles) {
   TileCoord c;
   int tiles_x = a.tiles_x, tiles_y = a.tiles_y;
+  int ks = 0;
+  if (a.ksplit > 1) { ks = t % a.ksplit; t /= a.ksplit; }
   c.tap_begin = 0; c.tap_count = a.ntaps; c.U = a.U; c.V = a.V; c.py = a.out_py; c.px = a.out_px;
   if (a.nphases > 0) {
     int p = 0;
@@ -189,18 +211,27 @@ __device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int t, int n_t
     c.U = a.ph[p].U; c.V = a.ph[p].V; c.py = a.ph[p].py; c.px = a.ph[p].px;
   }
   int mt = t / n_tiles;
+  c.mt = mt;
   c.n0 = (t - mt * n_tiles) * BLOCK_N;
   const int txi = mt % tiles_x;
   mt /= tiles_x;
   const int tyi = mt % tiles_y;
   const int tni = mt / tiles_y;
   c.x0 = txi * a.tw; c.y0 = tyi * a.th; c.img0 = tni * a.tn;
+  const int nkb = c.tap_count * a.kchunks;
+  if (a.ksplit > 1) {
+    c.kb_begin = (int)((long long)nkb * ks / a.ksplit);
+    c.kb_count = (int)((long long)nkb * (ks + 1) / a.ksplit) - c.kb_begin;
+  } else {
+    c.kb_begin = 0; c.kb_count = nkb;
+  }
   return c;
 }
 
-template <int BLOCK_N, int NTERMS>
+template <int BLOCK_N, int NTERMS, int BK>
 struct TcCfg {
-  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int A_TILE_BYTES = BLOCK_M * BK * 2;
+  static constexpr int B_TILE_BYTES = BLOCK_N * BK * 2;
   static constexpr int NPLANES = (NTERMS == 1) ? 1 : 2;
   static constexpr int STAGE_BYTES = NPLANES * (A_TILE_BYTES + B_TILE_BYTES);
   static constexpr int SMEM_BUDGET = 200 * 1024;
@@ -210,7 +241,7 @@ struct TcCfg {
   static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
-template <int BLOCK_N, int NTERMS>
+template <int BLOCK_N, int NTERMS, int BK>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -218,7 +249,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   // PERSISTENT: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the smem ring and its phases run
   // across tile boundaries (the producer prefetches the next tile while the last MMAs of the current one retire) and the
   // accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the main loop of tile i+1.
-  using Cfg = TcCfg<BLOCK_N, NTERMS>;
+  using Cfg = TcCfg<BLOCK_N, NTERMS, BK>;
+  constexpr int A_TILE_BYTES = Cfg::A_TILE_BYTES;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -232,7 +264,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int n_tiles = a.Cout / BLOCK_N;
   const int num_tiles = a.total_tiles;
-  const int kchunks = a.Cin / BLOCK_K;
+  const int kchunks = a.kchunks;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a_hi);
@@ -257,17 +289,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      const uint32_t box_a_bytes = (uint32_t)(a.tw * a.th * a.tn) * BLOCK_K * 2;
+      const uint32_t box_a_bytes = (uint32_t)(a.tw * a.th * a.tn) * BK * 2;
       const uint32_t tx_bytes = Cfg::NPLANES * (box_a_bytes + Cfg::B_TILE_BYTES);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile<BLOCK_N>(a, t, n_tiles);
         const int x0 = tc.x0, y0 = tc.y0, img0 = tc.img0, n0 = tc.n0;
-        const int num_kb = tc.tap_count * kchunks;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tl = kb / kchunks;
-          const int kc = kb - tl * kchunks;
+        // CTAs that share a weight tile (same n0, different m-tile) would otherwise request the same L2 lines in lockstep;
+        // rotating each m-tile's starting k-block spreads those requests over the whole weight slab (sum order is free)
+        const int rot = (tc.kb_count >= 16) ? (int)(((long long)tc.mt * a.rot_mul) % tc.kb_count) : 0;
+        for (int i = 0; i < tc.kb_count; ++i) {
+          int kr = i + rot;
+          if (kr >= tc.kb_count) kr -= tc.kb_count;
+          const int kb = tc.kb_begin + kr;
+          int tl, kc;
+          if (a.taps_inner) { kc = kb / tc.tap_count; tl = kb - kc * tc.tap_count; }
+          else { tl = kb / kchunks; kc = kb - tl * kchunks; }
           const int tap = tc.tap_begin + tl;
           mbar_wait(smem_u32(&bars[STAGES + stage]), phase ^ 1);
           const uint32_t full = smem_u32(&bars[stage]);
@@ -276,11 +314,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const int cx = x0 * a.in_mul + a.tap_ox[tap];
           const int cy = y0 * a.in_mul + a.tap_oy[tap];
           const int wrow = a.tap_wrow[tap] + n0;
-          tma_load_4d(smem_u32(st), &map_a_hi, full, kc * BLOCK_K, cx, cy, img0);
-          tma_load_2d(smem_u32(st + Cfg::NPLANES * A_TILE_BYTES), &map_b_hi, full, kc * BLOCK_K, wrow);
+          tma_load_4d(smem_u32(st), &map_a_hi, full, kc * BK, cx, cy, img0);
+          tma_load_2d(smem_u32(st + Cfg::NPLANES * A_TILE_BYTES), &map_b_hi, full, kc * BK, wrow);
           if (NTERMS > 1) {
-            tma_load_4d(smem_u32(st + A_TILE_BYTES), &map_a_lo, full, kc * BLOCK_K, cx, cy, img0);
-            tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES), &map_b_lo, full, kc * BLOCK_K, wrow);
+            tma_load_4d(smem_u32(st + A_TILE_BYTES), &map_a_lo, full, kc * BK, cx, cy, img0);
+            tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES), &map_b_lo, full, kc * BK, wrow);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -295,7 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int num_kb = decode_tile<BLOCK_N>(a, t, n_tiles).tap_count * kchunks;
+        const int num_kb = decode_tile<BLOCK_N>(a, t, n_tiles).kb_count;
         mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);     // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -308,13 +346,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const uint32_t b_hi = st + Cfg::NPLANES * A_TILE_BYTES;
           const uint32_t b_lo = b_hi + Cfg::B_TILE_BYTES;
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint32_t koff = k * UMMA_K * 2;   // bytes inside the 128-byte swizzle row
-            const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff);
-            const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff);
+            const uint64_t da_hi = make_kmajor_desc<BK>(a_hi + koff);
+            const uint64_t db_hi = make_kmajor_desc<BK>(b_hi + koff);
             if (NTERMS > 1) {
-              const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff);
-              const uint64_t db_lo = make_kmajor_sw128_desc(b_lo + koff);
+              const uint64_t da_lo = make_kmajor_desc<BK>(a_lo + koff);
+              const uint64_t db_lo = make_kmajor_desc<BK>(b_lo + koff);
               // small cross terms first, then the dominant hi*hi term
               tcgen05_mma_bf16(tmem_d, da_lo, db_hi, idesc, (kb | k) != 0);
               tcgen05_mma_bf16(tmem_d, da_hi, db_lo, idesc, 1);
@@ -399,6 +437,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            if (a.ksplit > 1) {
+              atomicAdd(dst + i, o);
+              continue;
+            }
             if (a.accumulate) {
               float4 p = dst[i];
               o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
@@ -712,29 +754,29 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
 // ---------------------------------------------------------------------------------------------
 // host: tensor maps, tile selection, launches
 // ---------------------------------------------------------------------------------------------
-int make_act_map(CUtensorMap* m, const uint16_t* ptr, int B, int H, int W, int C, int tw, int th, int tn, int stride) {
+int make_act_map(CUtensorMap* m, const uint16_t* ptr, int B, int H, int W, int C, int tw, int th, int tn, int stride, int bk = BLOCK_K) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return PNP_ERR_DRIVER;
   if (tw * stride > 256 || th * stride > 256 || tn > 256) return PNP_ERR_UNSUPPORTED;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   // traversal stride: TMA loads ceil(box/stride) elements per dimension, i.e. every stride-th pixel (strided convolutions)
-  cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(tw * stride), (cuuint32_t)(th * stride), (cuuint32_t)tn};
+  cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(tw * stride), (cuuint32_t)(th * stride), (cuuint32_t)tn};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? PNP_OK : PNP_ERR_DRIVER;
 }
 
-int make_w_map(CUtensorMap* m, const uint16_t* ptr, long long rows, int K, int block_n) {
+int make_w_map(CUtensorMap* m, const uint16_t* ptr, long long rows, int K, int block_n, int bk = BLOCK_K) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return PNP_ERR_DRIVER;
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)block_n};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? PNP_OK : PNP_ERR_DRIVER;
 }
 
@@ -758,24 +800,29 @@ int choose_tile(int U, int V, int B, int rows, int exact, int* tw, int* th, int*
   return PNP_OK;
 }
 
-template <int BLOCK_N, int NTERMS>
-int launch_tc(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi, const CUtensorMap& mb_lo,
-              float* y, const TcArgs& a, cudaStream_t s) {
-  using Cfg = TcCfg<BLOCK_N, NTERMS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PNP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+int sm_count() {
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
-    PNP_CUDA(cudaGetDevice(&dev));
-    PNP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      num_sms = 148;
   }
+  return num_sms;
+}
+
+template <int BLOCK_N, int NTERMS, int BK>
+int launch_tc(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi, const CUtensorMap& mb_lo,
+              float* y, const TcArgs& a, cudaStream_t s) {
+  using Cfg = TcCfg<BLOCK_N, NTERMS, BK>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PNP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, NTERMS, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_sms = sm_count();
   const long long tiles = a.total_tiles;
   dim3 grid((unsigned)(tiles < num_sms ? tiles : num_sms));     // persistent: one CTA per SM walks the tile list
-  conv_tc_kernel<BLOCK_N, NTERMS><<<grid, 192, Cfg::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, y, a);
+  conv_tc_kernel<BLOCK_N, NTERMS, BK><<<grid, 192, Cfg::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, y, a);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -816,11 +863,21 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
   // N = 256 tiles halve the shared-memory operand traffic per MMA (the 128x128 tile is shared-memory-bandwidth bound:
   // 12 MMAs x 8 KB reads + 64 KB TMA fill per 768 tensor cycles) and take the 512-channel 32x32 layers from 1.73 waves
   // of 256 CTAs to one wave of 128; used whenever enough tiles remain to fill the machine
-  int block_n = (a.Cout % 128 == 0) ? 128 : 64;
+  int block_n = (a.Cout % 128 == 0) ? 128 : ((a.Cout % 64 == 0) ? 64 : 32);
   {
     const long long mtiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n;
     if (a.Cout % 256 == 0 && mtiles * (a.Cout / 256) >= 96) block_n = 256;
   }
+  // K-block width: 64 (SWIZZLE_128B) unless the reduction is 32 channels per tap; the 128x256 tile also prefers 32-wide blocks
+  // (96 KB stages leave room for only two of them, 48 KB stages for four)
+  int bk = (a.Cin % 64 == 0) ? 64 : 32;
+  {
+    static int bk256_env = -1;
+    if (bk256_env < 0) { const char* e = getenv("PNP_TC_BK256"); bk256_env = e ? atoi(e) : 32; }
+    if (block_n == 256 && bk256_env == 32) bk = 32;
+    if (block_n == 128 && bk == 32) block_n = 64;      // (no 128 x 32-wide instantiation)
+  }
+  a.kchunks = a.Cin / bk;
   {
     const int n_tiles = a.Cout / block_n;
     if (a.nphases == 0) {
@@ -836,35 +893,70 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
       a.total_tiles = base;
     }
   }
+  // split-K: a layer with far fewer tiles than SMs and a deep reduction (cls_5's 5x5 stride-4 conv: 4 tiles x 200 k-blocks)
+  // would otherwise run its whole K loop on a handful of SMs
+  {
+    static int rot_env = -1;
+    static int order_env = -1;
+    if (rot_env < 0) { const char* e = getenv("PNP_TC_ROT"); rot_env = e ? atoi(e) : 7; }
+    if (order_env < 0) { const char* e = getenv("PNP_TC_ORDER"); order_env = e ? atoi(e) : 0; }
+    a.rot_mul = rot_env;
+    a.taps_inner = order_env;
+  }
+  a.ksplit = 1;
+  double* bn_sum_after = nullptr;
+  double* bn_sumsq_after = nullptr;
+  {
+    int min_taps = a.ntaps;
+    for (int p = 0; p < a.nphases; ++p) min_taps = a.ph[p].tap_count < min_taps ? a.ph[p].tap_count : min_taps;
+    const int min_kb = min_taps * a.kchunks;
+    const int sms = sm_count();
+    if (a.total_tiles * 2 <= sms && min_kb >= 8) {
+      int ks = sms / a.total_tiles;
+      if (ks > min_kb / 4) ks = min_kb / 4;
+      if (ks > 32) ks = 32;
+      if (ks > 1) {
+        a.ksplit = ks;
+        a.total_tiles *= ks;
+        if (!a.accumulate) PNP_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)a.B * a.OH * a.OW * a.Cout, s));
+        bn_sum_after = a.bn_sum; bn_sumsq_after = a.bn_sumsq;      // statistics of partial sums are meaningless: separate pass
+        a.bn_sum = nullptr; a.bn_sumsq = nullptr;
+      }
+    }
+  }
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  rc = make_act_map(&ma_hi, a_hi, a.B, AH, AW, a.Cin, a.tw, a.th, a.tn, a_stride);
+  rc = make_act_map(&ma_hi, a_hi, a.B, AH, AW, a.Cin, a.tw, a.th, a.tn, a_stride, bk);
   if (rc) return rc;
-  rc = make_w_map(&mb_hi, w_hi, w_rows, a.Cin, block_n);
+  rc = make_w_map(&mb_hi, w_hi, w_rows, a.Cin, block_n, bk);
   if (rc) return rc;
   if (nterms == 3) {
-    rc = make_act_map(&ma_lo, a_lo, a.B, AH, AW, a.Cin, a.tw, a.th, a.tn, a_stride);
+    rc = make_act_map(&ma_lo, a_lo, a.B, AH, AW, a.Cin, a.tw, a.th, a.tn, a_stride, bk);
     if (rc) return rc;
-    rc = make_w_map(&mb_lo, w_lo, w_rows, a.Cin, block_n);
+    rc = make_w_map(&mb_lo, w_lo, w_rows, a.Cin, block_n, bk);
     if (rc) return rc;
   } else {
     ma_lo = ma_hi;
     mb_lo = mb_hi;
   }
-  if (block_n == 256) {
-    if (nterms == 3) return launch_tc<256, 3>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
-    return launch_tc<256, 1>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
-  }
-  if (block_n == 128) {
-    if (nterms == 3) return launch_tc<128, 3>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
-    return launch_tc<128, 1>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
-  }
-  if (nterms == 3) return launch_tc<64, 3>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
-  return launch_tc<64, 1>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
+#define PNP_TC_GO(N_, K_)                                                                                  \
+  rc = (nterms == 3) ? launch_tc<N_, 3, K_>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s)                         \
+                     : launch_tc<N_, 1, K_>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s)
+  if (block_n == 256 && bk == 64) { PNP_TC_GO(256, 64); }
+  else if (block_n == 256) { PNP_TC_GO(256, 32); }
+  else if (block_n == 128) { PNP_TC_GO(128, 64); }
+  else if (block_n == 64 && bk == 64) { PNP_TC_GO(64, 64); }
+  else if (block_n == 64) { PNP_TC_GO(64, 32); }
+  else if (bk == 64) { PNP_TC_GO(32, 64); }
+  else { PNP_TC_GO(32, 32); }
+#undef PNP_TC_GO
+  if (rc) return rc;
+  if (bn_sum_after) return pnp_bn_stats(out, (long long)a.B * a.OH * a.OW, a.Cout, bn_sum_after, bn_sumsq_after, (void*)s);
+  return PNP_OK;
 }
 
 bool tc_geom_ok(const pnp_conv_geom* g) {
   return g && g->B > 0 && g->H > 0 && g->W > 0 && g->Ho > 0 && g->Wo > 0 && g->kh > 0 && g->kw > 0 && g->dil > 0 && g->stride > 0 &&
-         g->kh * g->kw <= MAX_TAPS && g->Cin % 64 == 0 && g->Cout % 64 == 0;
+         g->kh * g->kw <= MAX_TAPS && (g->Cin % 64 == 0 || g->Cin == 32) && (g->Cout % 64 == 0 || g->Cout == 32);
 }
 
 }  // namespace
@@ -1001,7 +1093,7 @@ extern "C" int pnp_conv2d_tc_wgrad(const uint16_t* x_hi, const uint16_t* x_lo, c
   {
     pnp_conv_geom t = *g;
     t.Cin = xc;
-    if (xc < g->Cin || !tc_geom_ok(&t)) return PNP_ERR_UNSUPPORTED;
+    if (xc < g->Cin || !tc_geom_ok(&t) || xc % 64 != 0 || g->Cout % 64 != 0) return PNP_ERR_UNSUPPORTED;
   }
   WgArgs a;
   a.B = g->B; a.Cin = g->Cin; a.Cout = g->Cout; a.in_mul = g->stride; a.dw = dw;

@@ -150,7 +150,7 @@ int reduce_launch_cfg(long long M, int C, int* tpr, long long* rpb, int* grid) {
   if (t > 256) return PNP_ERR_UNSUPPORTED;
   *tpr = t;
   int rstep = 256 / t;
-  long long rows = (long long)rstep * 32;
+  long long rows = (long long)rstep * 8;      // 8 rows per thread = 4 dependent DRAM round trips (was 32: ~17 us latency floor per launch)
   long long g = (M + rows - 1) / rows;
   long long cap = (long long)kSMs * 8;     // 8 resident CTAs of 256 threads per SM, one wave
   if (g > cap) { g = cap; rows = (M + g - 1) / g; }
@@ -787,7 +787,7 @@ extern "C" int pnp_bn_act_apply(const float* z, const float* scale, const float*
   if (skip && (Cs % 4 != 0 || skip_off % 4 != 0 || skip_off < 0 || skip_off + Cs > C)) return PNP_ERR_UNSUPPORTED;
   if ((scale == nullptr) != (shift == nullptr)) return PNP_ERR_BAD_ARG;
   long long n4 = M * (C / 4);
-  bn_act_apply_kernel<<<grid_for(n4, 256 * 4), 256, 0, S_>>>(z, scale, shift, skip, Cs, skip_off, act, y, y_hi, y_lo, n4, C / 4);
+  bn_act_apply_kernel<<<grid_for(n4, 256), 256, 0, S_>>>(z, scale, shift, skip, Cs, skip_off, act, y, y_hi, y_lo, n4, C / 4);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -819,7 +819,7 @@ extern "C" int pnp_bn_bwd_apply(const float* g, const float* z, const float* mea
   if (training && (!z || !mean || !coef)) return PNP_ERR_BAD_ARG;
   if (C % 4 != 0) return PNP_ERR_UNSUPPORTED;
   long long n4 = M * (C / 4);
-  bn_bwd_apply_kernel<<<grid_for(n4, 256 * 4), 256, 0, S_>>>(g, z, mean, invstd, gamma, coef, training, make_drop(drop), dz, dz_hi, dz_lo,
+  bn_bwd_apply_kernel<<<grid_for(n4, 256), 256, 0, S_>>>(g, z, mean, invstd, gamma, coef, training, make_drop(drop), dz, dz_hi, dz_lo,
                                                             n4, C / 4);
   PNP_LAUNCH_CHECK();
   return PNP_OK;

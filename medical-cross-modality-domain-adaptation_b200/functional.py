@@ -94,17 +94,27 @@ def _cin_pad(g):
     return g.Cin if g.Cin % 64 == 0 else ((g.Cin + 63) // 64) * 64
 
 
+def _tc_ch(c):
+    """channel counts the tcgen05 kernels tile natively: multiples of 64 (128-byte swizzle rows) or exactly 32 (64-byte rows)"""
+    return c % 64 == 0 or c == 32
+
+
+# the native 32-channel tcgen05 tiles (K block of 32 / N tile of 32); PNP_TC_K32=0 sends those layers back to the SIMT kernel
+TC_K32 = os.environ.get("PNP_TC_K32", "1") != "0"
+
+
 def _tc_candidate(kind, g):
-    if g.Cout % 64 != 0 or g.kh * g.kw > 25 or _gkey(kind, g) in _tc_declined:
+    if g.kh * g.kw > 25 or _gkey(kind, g) in _tc_declined:
         return False
-    if g.Cin % 64 == 0:
+    if g.Cin % 64 == 0 and g.Cout % 64 == 0:
         # (measured r1e: even the tiny stride-4 data gradients -- cls_5_3, m_cls_4, s*s latency-bound phase launches -- are
         #  2.5x faster here than on the general kernel, whose transposed gather multiplies 15/16 zeros)
         return True
-    # padded-plane path (Cin = 32 -> 64 zero-padded K chunk), forward and wgrad only.  Measured on B200 (r1e): the 256x256
-    # cls_1 res-a layer is operand-bandwidth bound and runs 0.31 ms padded on tcgen05 vs 0.25 ms on the fp32 SIMT kernel,
-    # so it stays off by default (PNP_TC_PAD32=1 enables it).
-    return TC_PAD32 and kind in ("fwd", "wgrad") and g.Cin % 32 == 0 and g.Cin >= 32
+    if kind == "wgrad":
+        # the weight-gradient GEMM has M = Cin: 32 channels would fill a quarter of the 128-row MMA; zero-padded planes
+        # measured slower than the fp32 SIMT kernel (r1e), so they stay opt-in (PNP_TC_PAD32=1)
+        return TC_PAD32 and g.Cout % 64 == 0 and g.Cin % 32 == 0 and g.Cin >= 32
+    return TC_K32 and _tc_ch(g.Cin) and _tc_ch(g.Cout)
 
 
 def _new_planes(shape, dev, nterms):
@@ -124,7 +134,7 @@ def _planes_of(x, nterms):
 def _want_planes(C):
     """producers emit planes for tensors a tcgen05 convolution is likely to consume (64-multiple channel counts)"""
     nt = _tc_mode()
-    return nt if (nt and FUSE_SPLIT and C % 64 == 0) else 0
+    return nt if (nt and FUSE_SPLIT and (C % 64 == 0 or (C == 32 and TC_K32))) else 0
 
 
 def split_bf16(x, nterms):
@@ -179,16 +189,9 @@ def conv_fwd_raw(xp, W, geom, drop=None, stats=None, keep_planes=False):
     z = torch.empty(geom.B, geom.Ho, geom.Wo, geom.Cout, dtype=torch.float32, device=xp.device)
     nt = _tc_mode()
     if nt and _tc_candidate("fwd", geom):
-        cp = _cin_pad(geom)
-        if cp != geom.Cin:
-            planes = _padded_planes(xp, nt, cp)
-            whi, wlo = _weight_planes(W, False, nt, cp)
-            g_tc = ConvGeom(geom.B, geom.H, geom.W, cp, geom.Ho, geom.Wo, geom.Cout, geom.kh, geom.kw, geom.stride, geom.dil,
-                            geom.pad_t, geom.pad_l)
-        else:
-            planes = _planes_of(xp, nt)
-            whi, wlo = _weight_planes(W, False, nt)
-            g_tc = geom
+        planes = _planes_of(xp, nt)
+        whi, wlo = _weight_planes(W, False, nt)
+        g_tc = geom
         fuse = stats is not None and FUSE_BN_STATS
         try:
             _tc_launch("fwd%dx%d.%d.%d" % (geom.Ho, geom.Cin, geom.Cout, geom.kh * geom.stride), _conv_flops(geom), "pnp_conv2d_tc_fwd", ptr(planes[0]), ptr(planes[1]), ptr(whi), ptr(wlo), ptr(z),
@@ -226,10 +229,10 @@ def conv_wgrad_raw(xp, dz, W, geom, x_planes=None, dz_planes=None):
     nt = _tc_mode()
     if nt and TC_WGRAD and _tc_candidate("wgrad", geom):
         cp = _cin_pad(geom)
-        if x_planes is not None:
+        if cp != geom.Cin:
+            xh, xl = _padded_planes(xp, nt, cp)      # (the planes kept by the forward pass are the unpadded 32-channel ones)
+        elif x_planes is not None:
             xh, xl = x_planes
-        elif cp != geom.Cin:
-            xh, xl = _padded_planes(xp, nt, cp)
         else:
             xh, xl = _planes_of(xp, nt)
         dh, dl = dz_planes if dz_planes is not None else split_bf16(dz, nt)

@@ -100,6 +100,12 @@ TC_CASES = [
     (2, 4, 4, 64, 64, 3, 2, 1, "SYMMETRIC"),    # cls_6: mirror pad + s2 -> 2x2
     (1, 256, 256, 64, 64, 3, 2, 1, "SAME"),     # cls_1_3 at full size: 256-wide strided TMA box
     (2, 8, 8, 128, 256, 5, 4, 1, "SYMMETRIC"),  # m_cls_4
+    # 32-channel layers: native 32-wide K blocks (SWIZZLE_64B operand tiles) and 32-wide N tiles
+    (2, 32, 32, 32, 32, 3, 1, 1, "SAME"),       # g2 / m_cls_3 style: K block 32, N tile 32
+    (1, 128, 128, 64, 32, 3, 1, 1, "SAME"),     # N tile 32 with 64-wide K; its dgrad reduces over 32 channels into 64
+    (2, 32, 32, 32, 64, 3, 2, 1, "SAME"),       # strided, Cin = 32: phase dgrad with N = 32
+    (1, 256, 256, 32, 64, 3, 1, 1, "SAME"),     # cls_1 res a at full width
+    (3, 16, 16, 32, 128, 3, 1, 2, "SAME"),      # dilated, Cout = 128 from 32 channels
 ]
 
 
