@@ -202,8 +202,17 @@ def run_ours(a):
         step_resident(i)
     torch.cuda.synchronize()
     if rank == 0:
-        recs = F.PROFILE
+        recs_all = F.PROFILE
         F.PROFILE = None
+        recs = [r_ for r_ in recs_all if not r_[3].startswith("simt:")]      # the roofline is the tcgen05 kernel's
+        by_s = {}
+        for s_, e_, fl_, tag_ in recs_all:
+            if tag_.startswith("simt:"):
+                c_ = by_s.setdefault((tag_, round(fl_ / 1e9, 3)), [0, 0.0])
+                c_[0] += 1
+                c_[1] += s_.elapsed_time(e_)
+        for (tag_, gf_), (n_, ms_) in sorted(by_s.items(), key=lambda kv: -kv[1][1])[:40]:
+            print("[simt] %-24s %9.3f GF x%3d  %8.3f ms  %7.1f TF/s" % (tag_, gf_, n_, ms_, gf_ * n_ / ms_), file=sys.stderr)
         by = {}
         for s_, e_, fl_, tag_ in recs:
             k_ = (tag_, round(fl_ / 1e9, 3))

@@ -22,6 +22,8 @@ struct GatherArgs {
   int M;               // B*OH*OW
   int K;               // kh*kw*IC
   int accumulate;
+  int phase_rows;      // TRANSPOSED, stride s > 1: rows are ordered phase-major ((oy % s, ox % s) outermost, phase_rows rows each,
+                       // a multiple of BM) so that every CTA owns ONE phase and skips the k-blocks of taps that cannot reach it
   PnpDropout drop;
 };
 
@@ -66,10 +68,21 @@ conv_gather_kernel(const float* __restrict__ in, const float* __restrict__ wmat,
     int m = m0 + row;
     r_ok[j] = m < a.M;
     int mm = r_ok[j] ? m : 0;
-    int b = mm / (a.OH * a.OW);
-    int rem = mm - b * (a.OH * a.OW);
-    int oy = rem / a.OW;
-    int ox = rem - oy * a.OW;
+    int b, oy, ox;
+    if (TRANSPOSED && a.phase_rows > 0) {
+      const int p = mm / a.phase_rows, r = mm - p * a.phase_rows;
+      const int PH = a.OH / a.stride, PW = a.OW / a.stride;
+      b = r / (PH * PW);
+      const int rem = r - b * (PH * PW);
+      const int yy = rem / PW;
+      oy = yy * a.stride + p / a.stride;
+      ox = (rem - yy * PW) * a.stride + p % a.stride;
+    } else {
+      b = mm / (a.OH * a.OW);
+      const int rem = mm - b * (a.OH * a.OW);
+      oy = rem / a.OW;
+      ox = rem - oy * a.OW;
+    }
     if (TRANSPOSED) {
       r_y[j] = oy + a.pad_t;
       r_x[j] = ox + a.pad_l;
@@ -174,11 +187,31 @@ conv_gather_kernel(const float* __restrict__ in, const float* __restrict__ wmat,
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   const int nkb = (a.K + BK - 1) / BK;
-  load_tiles(0);
-  store_tiles();
+  // phase-major strided data gradient: a k-block (BK channels of one tap, IC % BK == 0) contributes to this CTA's phase only
+  // if the tap offset is congruent to the phase modulo the stride -- 1 block in s*s for a dense tap grid
+  const bool phased = TRANSPOSED && a.phase_rows > 0;
+  const int cta_p = phased ? (m0 / a.phase_rows) : 0;
+  const int cta_py = phased ? cta_p / a.stride : 0, cta_px = phased ? cta_p % a.stride : 0;
+  auto next_kb = [&](int kb) {
+    if (!phased) return kb;
+    for (; kb < nkb; ++kb) {
+      const int tap = (kb * BK) / a.IC;
+      const int ky = tap / a.kw, kx = tap - ky * a.kw;
+      if ((cta_py + a.pad_t - ky * a.dil) % a.stride == 0 && (cta_px + a.pad_l - kx * a.dil) % a.stride == 0) break;
+    }
+    return kb;
+  };
+  int kb_cur = next_kb(0);
+  if (kb_cur < nkb) {
+    load_tiles(kb_cur * BK);
+    store_tiles();
+  }
   __syncthreads();
-  for (int kb = 0; kb < nkb; ++kb) {
-    if (kb + 1 < nkb) load_tiles((kb + 1) * BK);
+  while (kb_cur < nkb) {
+    const int kb_nxt = next_kb(kb_cur + 1);
+    const bool more = kb_nxt < nkb;
+    kb_cur = kb_nxt;
+    if (more) load_tiles(kb_nxt * BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float av[TM], bv[TN];
@@ -198,7 +231,7 @@ conv_gather_kernel(const float* __restrict__ in, const float* __restrict__ wmat,
         for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
-    if (kb + 1 < nkb) {
+    if (more) {
       store_tiles();
       __syncthreads();
     }
@@ -213,11 +246,20 @@ conv_gather_kernel(const float* __restrict__ in, const float* __restrict__ wmat,
   for (int i = 0; i < TM; ++i) {
     int m = m0 + row_index(i, ty, TM, BM);
     if (m >= a.M) continue;
+    long long mlin = m;
+    if (TRANSPOSED && a.phase_rows > 0) {
+      const int p = m / a.phase_rows, r = m - p * a.phase_rows;
+      const int PH = a.OH / a.stride, PW = a.OW / a.stride;
+      const int b = r / (PH * PW);
+      const int rem = r - b * (PH * PW);
+      const int yy = rem / PW;
+      mlin = ((long long)b * a.OH + yy * a.stride + p / a.stride) * a.OW + (rem - yy * PW) * a.stride + p % a.stride;
+    }
 #pragma unroll
     for (int j = 0; j < TN; j += 4) {
       int n = n0 + row_index(j, tx, TN, BN);
       if (n >= a.OC) continue;
-      long long idx = (long long)m * a.OC + n;
+      long long idx = mlin * a.OC + n;
       float4 v = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
       if (vec_store && n + 3 < a.OC) {
         if (drop_on) {
@@ -247,7 +289,13 @@ conv_gather_kernel(const float* __restrict__ in, const float* __restrict__ wmat,
 }
 
 template <int BM, int BN, int BK, int TM, int TN, int VEC, bool TR>
-int launch_gather(const float* in, const float* wmat, float* out, const GatherArgs& a, cudaStream_t s) {
+int launch_gather(const float* in, const float* wmat, float* out, const GatherArgs& a0, cudaStream_t s) {
+  GatherArgs a = a0;
+  a.phase_rows = 0;
+  if (TR && a.stride > 1 && a.OH % a.stride == 0 && a.OW % a.stride == 0 && a.IC % BK == 0) {
+    const long long pr = (long long)(a.M / (a.OH * a.OW)) * (a.OH / a.stride) * (a.OW / a.stride);
+    if (pr % BM == 0 && pr <= 0x7fffffffLL) a.phase_rows = (int)pr;
+  }
   dim3 grid(pnp_cdiv(a.M, BM), pnp_cdiv(a.OC, BN));
   dim3 block((BM / TM) * (BN / TN));
   conv_gather_kernel<BM, BN, BK, TM, TN, VEC, TR><<<grid, block, 0, s>>>(in, wmat, out, a);

@@ -200,7 +200,7 @@ def conv_fwd_raw(xp, W, geom, drop=None, stats=None, keep_planes=False):
             return z, fuse, (planes if keep_planes else None)
         except _C.Unsupported:
             _tc_declined.add(_gkey("fwd", geom))
-    call("pnp_conv2d_fwd", ptr(xp), ptr(W), ptr(z), ctypes.byref(geom), _byref(drop), 0, rt.stream())
+    _tc_launch("simt:fwd%dx%d.%d.%d" % (geom.Ho, geom.Cin, geom.Cout, geom.kh * geom.stride), _conv_flops(geom), "pnp_conv2d_fwd", ptr(xp), ptr(W), ptr(z), ctypes.byref(geom), _byref(drop), 0, rt.stream())
     return z, False, None
 
 
@@ -218,7 +218,7 @@ def conv_dgrad_raw(dz, W, geom, into=None, dz_planes=None):
             return dx
         except _C.Unsupported:
             _tc_declined.add(_gkey("dgrad", geom))
-    call("pnp_conv2d_dgrad", ptr(dz), ptr(_weight_T(W)), ptr(dx), ctypes.byref(geom), acc, rt.stream())
+    _tc_launch("simt:dgr%dx%d.%d.%d" % (geom.Ho, geom.Cin, geom.Cout, geom.kh * geom.stride), _conv_flops(geom), "pnp_conv2d_dgrad", ptr(dz), ptr(_weight_T(W)), ptr(dx), ctypes.byref(geom), acc, rt.stream())
     return dx
 
 
@@ -242,7 +242,7 @@ def conv_wgrad_raw(xp, dz, W, geom, x_planes=None, dz_planes=None):
             return
         except _C.Unsupported:
             _tc_declined.add(_gkey("wgrad", geom))
-    call("pnp_conv2d_wgrad", ptr(xp), ptr(dz), ptr(W.grad), ctypes.byref(geom), rt.stream())
+    _tc_launch("simt:wgr%dx%d.%d.%d" % (geom.Ho, geom.Cin, geom.Cout, geom.kh * geom.stride), _conv_flops(geom), "pnp_conv2d_wgrad", ptr(xp), ptr(dz), ptr(W.grad), ctypes.byref(geom), rt.stream())
 
 
 def _tc_will_run(kind, geom):

@@ -51,6 +51,10 @@ CONV_CASES = [
     (1, 7, 9, 8, 12, 3, 2, 1, "SAME"),         # odd spatial, stride 2
     (1, 70, 45, 40, 5, 5, 1, 1, "SAME"),       # few-output direct kernel: ragged 32x32 tiles, zero padding
     (2, 40, 33, 8, 8, 3, 1, 1, "SAME"),        # few-output direct kernel, 8 outputs
+    # strided data gradients large enough for the phase-major row order of the SIMT gather (one phase per CTA)
+    (8, 32, 32, 16, 32, 5, 4, 1, "SAME"),      # m_cls_2_3 at batch 8: 16 phases x 512 rows
+    (4, 32, 32, 16, 32, 3, 2, 1, "SAME"),      # stride 2, pad (0,1): 4 phases x 1024 rows
+    (4, 32, 32, 64, 64, 3, 2, 1, "SAME"),      # 64-channel output tile (BM = 128)
 ]
 
 
