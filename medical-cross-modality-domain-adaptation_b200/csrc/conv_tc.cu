@@ -126,6 +126,15 @@ __device__ __forceinline__ void tcgen05_ld_32x32b_x32(uint32_t taddr, uint32_t (
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tcgen05_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -149,9 +158,9 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)((BK == 32 ? 512 : 256) >> 4) << 32;      // 8 rows of 64 B / of 32 B
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;
+  d |= (uint64_t)(BK == 32 ? 4 : 6) << 61;                 // SWIZZLE_64B / SWIZZLE_32B (BK = 16: the 16-channel layers)
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10,
@@ -394,29 +403,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
       mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
       tcgen05_fence_after();
+      constexpr int EW = BLOCK_N < 32 ? 16 : 32;      // accumulator columns handled per pass
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = 0; c0 < BLOCK_N; c0 += EW) {
         uint32_t r[32];
-        tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), r);
+        if (EW == 32) tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), r);
+        else tcgen05_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), r);
         tcgen05_wait_ld();
-        float v[32];
+        float v[EW];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        for (int i = 0; i < EW; ++i) v[i] = __uint_as_float(r[i]);
         if (drop_on && valid) {
           const unsigned long long base4 = (unsigned long long)(pix * a.Cout + n0 + c0) >> 2;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < EW / 4; ++i) {
             float4 mu = pnp_dropout_mult4(a.drop, seed, base4 + i);
             v[4 * i] *= mu.x; v[4 * i + 1] *= mu.y; v[4 * i + 2] *= mu.z; v[4 * i + 3] *= mu.w;
           }
         }
         if (a.bn_sum != nullptr) {
-          // per-channel partial sums over this warp's 32 rows: butterfly transpose-reduce (31 shuffles / array)
-          float s[32], ss[32];
+          // per-channel partial sums over this warp's 32 rows: butterfly transpose-reduce
+          float s[EW], ss[EW];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { float tv = valid ? v[i] : 0.f; s[i] = tv; ss[i] = tv * tv; }
+          for (int i = 0; i < EW; ++i) { float tv = valid ? v[i] : 0.f; s[i] = tv; ss[i] = tv * tv; }
+          if (EW == 16) {   // 16 columns: fold the two half-warps first, then transpose-reduce inside each half
 #pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
+            for (int i = 0; i < EW; ++i) {
+              s[i] += __shfl_xor_sync(0xffffffffu, s[i], 16);
+              ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 16);
+            }
+          }
+#pragma unroll
+          for (int off = EW / 2; off >= 1; off >>= 1) {
             const bool upper = (lane & off) != 0;
 #pragma unroll
             for (int i = 0; i < off; ++i) {
@@ -428,14 +446,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               ss[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
             }
           }
-          // after the butterfly lane L holds column L of this 32-column chunk
-          atomicAdd(a.bn_sum + n0 + c0 + lane, (double)s[0]);
-          atomicAdd(a.bn_sumsq + n0 + c0 + lane, (double)ss[0]);
+          // after the butterfly lane L holds column L (mod EW) of this chunk
+          if (lane < EW) {
+            atomicAdd(a.bn_sum + n0 + c0 + lane, (double)s[0]);
+            atomicAdd(a.bn_sumsq + n0 + c0 + lane, (double)ss[0]);
+          }
         }
         if (valid) {
           float4* dst = reinterpret_cast<float4*>(orow + c0);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < EW / 4; ++i) {
             float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             if (a.ksplit > 1) {
               atomicAdd(dst + i, o);
@@ -592,9 +612,22 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, 
   return d;
 }
 
+__device__ __forceinline__ uint64_t make_mnmajor_sw64_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;       // distance between 32-element groups along M
+  d |= (uint64_t)(512 >> 4) << 32;                         // 8 pixels x 64 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                                  // SWIZZLE_64B
+  return d;
+}
+
 struct WgArgs {
   int B, Cin, Cout;
   int ntaps;
+  // taps packed along the 128-row M tile: 1 = 128 consecutive channels of one tap (two 64-channel boxes); 2 = Cin 64: two taps;
+  // 4 = Cin 32: four taps of 32-channel (64-byte, SWIZZLE_64B) boxes -- a narrow layer still fills the whole MMA
+  int pack, ngroups;
   short tap_oy[MAX_TAPS], tap_ox[MAX_TAPS];
   int in_mul;
   int tw, th, tn, tiles_x, tiles_y, tiles_n;
@@ -679,8 +712,18 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
             const CUtensorMap* md = p ? &map_dy_lo : &map_dy_hi;
             uint8_t* sa = st + p * Cfg::A_BYTES;
             uint8_t* sb = st + Cfg::NPLANES * Cfg::A_BYTES + p * Cfg::B_BYTES;
-            tma_load_4d(smem_u32(sa), mx, full, ci0, cx, cy, img0);
-            tma_load_4d(smem_u32(sa + WG_BOX_BYTES), mx, full, ci0 + 64, cx, cy, img0);   // beyond Cin: zero filled
+            if (a.pack == 1) {
+              tma_load_4d(smem_u32(sa), mx, full, ci0, cx, cy, img0);
+              tma_load_4d(smem_u32(sa + WG_BOX_BYTES), mx, full, ci0 + 64, cx, cy, img0);   // beyond Cin: zero filled
+            } else {
+              const int nb = a.pack;                       // 2 boxes of 8 KB or 4 boxes of 4 KB
+              const int bbytes = 2 * WG_BOX_BYTES / nb;
+              for (int j = 0; j < nb; ++j) {
+                int tp = tap * nb + j;
+                if (tp >= a.ntaps) tp = a.ntaps - 1;       // dummy rows of the last group (never written back)
+                tma_load_4d(smem_u32(sa + j * bbytes), mx, full, 0, x0 * a.in_mul + a.tap_ox[tp], y0 * a.in_mul + a.tap_oy[tp], img0);
+              }
+            }
 #pragma unroll
             for (int g = 0; g < BLOCK_N / 64; ++g) tma_load_4d(smem_u32(sb + g * WG_BOX_BYTES), md, full, co0 + g * 64, x0, y0, img0);
           }
@@ -701,10 +744,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
 #pragma unroll
           for (int k = 0; k < WG_PB / UMMA_K; ++k) {
             const uint32_t koff = k * (UMMA_K / 8) * 1024;       // 16 pixels = two 8-row swizzle atoms
-            const uint64_t da_hi = make_mnmajor_sw128_desc(a_hi + koff, WG_BOX_BYTES);
+            const uint32_t koff_a = (a.pack == 4) ? koff / 2 : koff;
+            const uint64_t da_hi = (a.pack == 4) ? make_mnmajor_sw64_desc(a_hi + koff_a, WG_BOX_BYTES / 2)
+                                                 : make_mnmajor_sw128_desc(a_hi + koff_a, WG_BOX_BYTES);
             const uint64_t db_hi = make_mnmajor_sw128_desc(b_hi + koff, WG_BOX_BYTES);
             if (NTERMS > 1) {
-              const uint64_t da_lo = make_mnmajor_sw128_desc(a_lo + koff, WG_BOX_BYTES);
+              const uint64_t da_lo = (a.pack == 4) ? make_mnmajor_sw64_desc(a_lo + koff_a, WG_BOX_BYTES / 2)
+                                                   : make_mnmajor_sw128_desc(a_lo + koff_a, WG_BOX_BYTES);
               const uint64_t db_lo = make_mnmajor_sw128_desc(b_lo + koff, WG_BOX_BYTES);
               tcgen05_mma_bf16(tmem_base, da_lo, db_hi, idesc, (kb | k) != 0);
               tcgen05_mma_bf16(tmem_base, da_hi, db_lo, idesc, 1);
@@ -721,9 +767,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
     } else {
       const int q = warp & 3;
       const int m = q * 32 + lane;
-      const int ci = ci0 + m;
-      const bool valid = ci < a.Cin;
-      float* orow = a.dw + ((long long)tap * a.Cin + ci) * a.Cout + co0;
+      int ci = ci0 + m, tap_w = tap;
+      if (a.pack == 2) { tap_w = tap * 2 + (m >> 6); ci = m & 63; }
+      else if (a.pack == 4) { tap_w = tap * 4 + (m >> 5); ci = m & 31; }
+      const bool valid = ci < a.Cin && tap_w < a.ntaps;
+      float* orow = a.dw + ((long long)tap_w * a.Cin + ci) * a.Cout + co0;
       mbar_wait(smem_u32(&bars[2 * STAGES]), 0);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -764,7 +812,7 @@ int make_act_map(CUtensorMap* m, const uint16_t* ptr, int B, int H, int W, int C
   cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(tw * stride), (cuuint32_t)(th * stride), (cuuint32_t)tn};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? PNP_OK : PNP_ERR_DRIVER;
 }
 
@@ -776,7 +824,7 @@ int make_w_map(CUtensorMap* m, const uint16_t* ptr, long long rows, int K, int b
   cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)block_n};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? PNP_OK : PNP_ERR_DRIVER;
 }
 
@@ -836,7 +884,7 @@ int launch_wg(const CUtensorMap& mx_hi, const CUtensorMap& mx_lo, const CUtensor
     PNP_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BLOCK_N, NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid(a.ntaps * a.mt * a.nt, splits);
+  dim3 grid(a.ngroups * a.mt * a.nt, splits);
   conv_wgrad_tc_kernel<BLOCK_N, NTERMS><<<grid, 192, Cfg::SMEM_BYTES, s>>>(mx_hi, mx_lo, md_hi, md_lo, a);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
@@ -863,14 +911,14 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
   // N = 256 tiles halve the shared-memory operand traffic per MMA (the 128x128 tile is shared-memory-bandwidth bound:
   // 12 MMAs x 8 KB reads + 64 KB TMA fill per 768 tensor cycles) and take the 512-channel 32x32 layers from 1.73 waves
   // of 256 CTAs to one wave of 128; used whenever enough tiles remain to fill the machine
-  int block_n = (a.Cout % 128 == 0) ? 128 : ((a.Cout % 64 == 0) ? 64 : 32);
+  int block_n = (a.Cout % 128 == 0) ? 128 : ((a.Cout % 64 == 0) ? 64 : ((a.Cout % 32 == 0) ? 32 : 16));
   {
     const long long mtiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n;
     if (a.Cout % 256 == 0 && mtiles * (a.Cout / 256) >= 96) block_n = 256;
   }
   // K-block width: 64 (SWIZZLE_128B) unless the reduction is 32 channels per tap; the 128x256 tile also prefers 32-wide blocks
   // (96 KB stages leave room for only two of them, 48 KB stages for four)
-  int bk = (a.Cin % 64 == 0) ? 64 : 32;
+  int bk = (a.Cin % 64 == 0) ? 64 : ((a.Cin % 32 == 0) ? 32 : 16);
   {
     static int bk256_env = -1;
     if (bk256_env < 0) { const char* e = getenv("PNP_TC_BK256"); bk256_env = e ? atoi(e) : 32; }
@@ -942,12 +990,16 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
   rc = (nterms == 3) ? launch_tc<N_, 3, K_>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s)                         \
                      : launch_tc<N_, 1, K_>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s)
   if (block_n == 256 && bk == 64) { PNP_TC_GO(256, 64); }
-  else if (block_n == 256) { PNP_TC_GO(256, 32); }
-  else if (block_n == 128) { PNP_TC_GO(128, 64); }
+  else if (block_n == 256 && bk == 32) { PNP_TC_GO(256, 32); }
+  else if (block_n == 128 && bk == 64) { PNP_TC_GO(128, 64); }
   else if (block_n == 64 && bk == 64) { PNP_TC_GO(64, 64); }
-  else if (block_n == 64) { PNP_TC_GO(64, 32); }
-  else if (bk == 64) { PNP_TC_GO(32, 64); }
-  else { PNP_TC_GO(32, 32); }
+  else if (block_n == 64 && bk == 32) { PNP_TC_GO(64, 32); }
+  else if (block_n == 32 && bk == 64) { PNP_TC_GO(32, 64); }
+  else if (block_n == 32 && bk == 32) { PNP_TC_GO(32, 32); }
+  else if (block_n == 32 && bk == 16) { PNP_TC_GO(32, 16); }
+  else if (block_n == 16 && bk == 16) { PNP_TC_GO(16, 16); }
+  else if (block_n == 16 && bk == 32) { PNP_TC_GO(16, 32); }
+  else return PNP_ERR_UNSUPPORTED;      // (no layer of the graphs needs the remaining tile shapes)
 #undef PNP_TC_GO
   if (rc) return rc;
   if (bn_sum_after) return pnp_bn_stats(out, (long long)a.B * a.OH * a.OW, a.Cout, bn_sum_after, bn_sumsq_after, (void*)s);
@@ -956,7 +1008,8 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
 
 bool tc_geom_ok(const pnp_conv_geom* g) {
   return g && g->B > 0 && g->H > 0 && g->W > 0 && g->Ho > 0 && g->Wo > 0 && g->kh > 0 && g->kw > 0 && g->dil > 0 && g->stride > 0 &&
-         g->kh * g->kw <= MAX_TAPS && (g->Cin % 64 == 0 || g->Cin == 32) && (g->Cout % 64 == 0 || g->Cout == 32);
+         g->kh * g->kw <= MAX_TAPS && (g->Cin % 64 == 0 || g->Cin == 32 || g->Cin == 16) &&
+         (g->Cout % 64 == 0 || g->Cout == 32 || g->Cout == 16);
 }
 
 }  // namespace
@@ -1093,7 +1146,7 @@ extern "C" int pnp_conv2d_tc_wgrad(const uint16_t* x_hi, const uint16_t* x_lo, c
   {
     pnp_conv_geom t = *g;
     t.Cin = xc;
-    if (xc < g->Cin || !tc_geom_ok(&t) || xc % 64 != 0 || g->Cout % 64 != 0) return PNP_ERR_UNSUPPORTED;
+    if (xc < g->Cin || !tc_geom_ok(&t) || (xc % 64 != 0 && !(xc == 32 && g->Cin == 32)) || g->Cout % 64 != 0) return PNP_ERR_UNSUPPORTED;
   }
   WgArgs a;
   a.B = g->B; a.Cin = g->Cin; a.Cout = g->Cout; a.in_mul = g->stride; a.dw = dw;
@@ -1112,8 +1165,13 @@ extern "C" int pnp_conv2d_tc_wgrad(const uint16_t* x_hi, const uint16_t* x_lo, c
   const int block_n = (g->Cout % 128 == 0) ? 128 : 64;
   a.mt = pnp_cdiv(g->Cin, 128);
   a.nt = g->Cout / block_n;
-  const int tiles = a.ntaps * a.mt * a.nt;
-  int splits = (2 * 148 + tiles - 1) / tiles;
+  a.pack = 1;
+  if (g->Cin == 64 && xc == 64) a.pack = 2;
+  else if (g->Cin == 32 && xc == 32) a.pack = 4;
+  a.ngroups = pnp_cdiv(a.ntaps, a.pack);
+  const int x_bk = (a.pack == 4) ? 32 : 64;
+  const int tiles = a.ngroups * a.mt * a.nt;
+  int splits = (2 * sm_count()) / tiles;       // floor: tiles * splits CTAs must fit two full waves (one CTA per SM), never spill into a third
   int max_splits = a.num_pb / 4;
   if (max_splits < 1) max_splits = 1;
   if (splits > max_splits) splits = max_splits;
@@ -1121,12 +1179,12 @@ extern "C" int pnp_conv2d_tc_wgrad(const uint16_t* x_hi, const uint16_t* x_lo, c
   a.pb_per_split = pnp_cdiv(a.num_pb, splits);
   splits = pnp_cdiv(a.num_pb, a.pb_per_split);
   CUtensorMap mx_hi, mx_lo, md_hi, md_lo;
-  rc = make_act_map(&mx_hi, x_hi, g->B, g->H, g->W, xc, a.tw, a.th, a.tn, g->stride);
+  rc = make_act_map(&mx_hi, x_hi, g->B, g->H, g->W, xc, a.tw, a.th, a.tn, g->stride, x_bk);
   if (rc) return rc;
   rc = make_act_map(&md_hi, dy_hi, g->B, g->Ho, g->Wo, g->Cout, a.tw, a.th, a.tn, 1);
   if (rc) return rc;
   if (nterms == 3) {
-    rc = make_act_map(&mx_lo, x_lo, g->B, g->H, g->W, xc, a.tw, a.th, a.tn, g->stride);
+    rc = make_act_map(&mx_lo, x_lo, g->B, g->H, g->W, xc, a.tw, a.th, a.tn, g->stride, x_bk);
     if (rc) return rc;
     rc = make_act_map(&md_lo, dy_lo, g->B, g->Ho, g->Wo, g->Cout, a.tw, a.th, a.tn, 1);
     if (rc) return rc;

@@ -91,16 +91,21 @@ def _gkey(kind, g):
 
 def _cin_pad(g):
     """channel count of the (zero padded) operand planes: Cin = 32 layers (cls_1 res a) use the 64-channel K chunk"""
-    return g.Cin if g.Cin % 64 == 0 else ((g.Cin + 63) // 64) * 64
+    if g.Cin % 64 == 0 or (g.Cin == 32 and TC_K32):
+        return g.Cin
+    return ((g.Cin + 63) // 64) * 64
 
 
 def _tc_ch(c):
-    """channel counts the tcgen05 kernels tile natively: multiples of 64 (128-byte swizzle rows) or exactly 32 (64-byte rows)"""
-    return c % 64 == 0 or c == 32
+    """channel counts the tcgen05 kernels tile natively: multiples of 64 (128-byte swizzle rows), 32 (64-byte) or 16 (32-byte)"""
+    return c % 64 == 0 or c == 32 or (c == 16 and TC_K16)
 
 
 # the native 32-channel tcgen05 tiles (K block of 32 / N tile of 32); PNP_TC_K32=0 sends those layers back to the SIMT kernel
 TC_K32 = os.environ.get("PNP_TC_K32", "1") != "0"
+# 16-channel layers (g1/g2, mask critic): 16-wide K blocks (SWIZZLE_32B).  One TMA instruction moves only 4 KB there, so the
+# kernel is TMA-issue bound and roughly at par with the SIMT kernel (r1p: fwd 256x256 16->16 144 us vs 131 us, dgrad 121 vs 141)
+TC_K16 = os.environ.get("PNP_TC_K16", "1") != "0"
 
 
 def _tc_candidate(kind, g):
@@ -111,9 +116,11 @@ def _tc_candidate(kind, g):
         #  2.5x faster here than on the general kernel, whose transposed gather multiplies 15/16 zeros)
         return True
     if kind == "wgrad":
-        # the weight-gradient GEMM has M = Cin: 32 channels would fill a quarter of the 128-row MMA; zero-padded planes
-        # measured slower than the fp32 SIMT kernel (r1e), so they stay opt-in (PNP_TC_PAD32=1)
-        return TC_PAD32 and g.Cout % 64 == 0 and g.Cin % 32 == 0 and g.Cin >= 32
+        # the weight-gradient GEMM has M = Cin: a 32-channel layer packs four taps into the 128-row MMA tile (native 32-channel
+        # planes); the older zero-padded-plane variant measured slower than the SIMT kernel (r1e) and stays opt-in
+        if g.Cout % 64 != 0:
+            return False
+        return (TC_K32 and g.Cin == 32) or (TC_PAD32 and g.Cin % 32 == 0 and g.Cin >= 32)
     return TC_K32 and _tc_ch(g.Cin) and _tc_ch(g.Cout)
 
 
@@ -134,7 +141,7 @@ def _planes_of(x, nterms):
 def _want_planes(C):
     """producers emit planes for tensors a tcgen05 convolution is likely to consume (64-multiple channel counts)"""
     nt = _tc_mode()
-    return nt if (nt and FUSE_SPLIT and (C % 64 == 0 or (C == 32 and TC_K32))) else 0
+    return nt if (nt and FUSE_SPLIT and (C % 64 == 0 or (C == 32 and TC_K32) or (C == 16 and TC_K32 and TC_K16))) else 0
 
 
 def split_bf16(x, nterms):

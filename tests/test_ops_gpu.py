@@ -110,6 +110,11 @@ TC_CASES = [
     (2, 32, 32, 32, 64, 3, 2, 1, "SAME"),       # strided, Cin = 32: phase dgrad with N = 32
     (1, 256, 256, 32, 64, 3, 1, 1, "SAME"),     # cls_1 res a at full width
     (3, 16, 16, 32, 128, 3, 1, 2, "SAME"),      # dilated, Cout = 128 from 32 channels
+    # 16-channel layers: 16-wide K blocks (SWIZZLE_32B operand tiles), 16-wide N tiles
+    (2, 32, 32, 16, 16, 3, 1, 1, "SAME"),       # g1 res
+    (2, 32, 32, 16, 32, 3, 1, 1, "SAME"),       # g2 inc: forward N 32 / K 16, dgrad N 16 / K 32
+    (1, 256, 256, 16, 16, 3, 1, 1, "SAME"),     # g1 at full width
+    (8, 32, 32, 16, 32, 5, 4, 1, "SAME"),       # m_cls_2_3: 5x5 stride 4, phase dgrad with N = 16
 ]
 
 
