@@ -108,15 +108,32 @@ def _host_threads():
 
 
 def run_ours(a):
-    os.environ["NCCL_DEBUG"] = os.environ.get("PNP_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
+    # stdout must carry exactly one JSON line: NCCL prints its version banner to stdout when NCCL_DEBUG >= VERSION, so the variable
+    # is cleared (PNP_NCCL_DEBUG re-enables it) and fd 1 points at stderr while the communicator is created (first collective)
+    if "PNP_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["PNP_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
     from pnp_b200 import parallel, _C
-    parallel.init_from_env()
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        parallel.init_from_env()
+        if world > 1:
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     B = a.batch
     net, trainer = build_adversarial(B, a.backend)
     from pnp_b200 import functional as F, runtime as rt
@@ -206,7 +223,7 @@ def run_ours(a):
         F.PROFILE = None
         recs = [r_ for r_ in recs_all if not r_[3].startswith("simt:")]      # the roofline is the tcgen05 kernel's
         by_s = {}
-        for s_, e_, fl_, tag_ in recs_all:
+        for s_, e_, fl_, tag_, _k in recs_all:
             if tag_.startswith("simt:"):
                 c_ = by_s.setdefault((tag_, round(fl_ / 1e9, 3)), [0, 0.0])
                 c_[0] += 1
@@ -214,7 +231,7 @@ def run_ours(a):
         for (tag_, gf_), (n_, ms_) in sorted(by_s.items(), key=lambda kv: -kv[1][1])[:40]:
             print("[simt] %-24s %9.3f GF x%3d  %8.3f ms  %7.1f TF/s" % (tag_, gf_, n_, ms_, gf_ * n_ / ms_), file=sys.stderr)
         by = {}
-        for s_, e_, fl_, tag_ in recs:
+        for s_, e_, fl_, tag_, _k in recs:
             k_ = (tag_, round(fl_ / 1e9, 3))
             c_ = by.setdefault(k_, [0, 0.0])
             c_[0] += 1
@@ -222,8 +239,21 @@ def run_ours(a):
         top = sorted(by.items(), key=lambda kv: -kv[1][1])[:48]
         for (tag_, gf_), (n_, ms_) in top:
             print("[tc] %-18s %9.3f GF x%3d  %8.3f ms  %7.1f TF/s" % (tag_, gf_, n_, ms_, gf_ * n_ / ms_), file=sys.stderr)
-        tc_ms = sum(s.elapsed_time(e) for s, e, _, _ in recs)
-        tc_fl = sum(fl for _, _, fl, _ in recs)
+        all_ms = sum(r_[0].elapsed_time(r_[1]) for r_ in recs)
+        all_fl = sum(r_[2] for r_ in recs)
+        # the dominant kernel = the instantiation with the largest share of the step (agrees with profiles/r1_launches_summary.md)
+        per_k = {}
+        for s_, e_, fl_, tag_, k_ in recs:
+            c_ = per_k.setdefault(k_, [0, 0.0, 0.0])
+            c_[0] += 1
+            c_[1] += s_.elapsed_time(e_)
+            c_[2] += fl_
+        for k_, (n_, ms_, fl_) in sorted(per_k.items(), key=lambda kv: -kv[1][1]):
+            print("[kern] %-34s x%4d %9.3f ms  %7.1f TF/s" % (k_, n_, ms_, fl_ / ms_ / 1e9), file=sys.stderr)
+        dom = max(per_k.items(), key=lambda kv: kv[1][1])[0] if per_k else None
+        dom_recs = [r_ for r_ in recs if r_[4] == dom]
+        tc_ms = sum(r_[0].elapsed_time(r_[1]) for r_ in dom_recs)
+        tc_fl = sum(r_[2] for r_ in dom_recs)
         pk = _peaks()
         nterms = 1 if a.backend == "tc1" else 3
         traffic, traffic_note = None, "no ncu capture committed"
@@ -231,17 +261,23 @@ def run_ours(a):
         if os.path.exists(tj):
             with open(tj) as f:
                 nj = json.load(f)
-            traffic = nj.get("mean_dram_bytes_per_launch")
-            traffic_note = ("dram__bytes_read+write per launch, mean over the %d conv_tc_kernel launches of the committed ncu --set full "
-                            "capture (profiles/r1_conv_tc_ncu.csv); operands 4 B/element (bf16 hi+lo), outputs stay in the 126 MB L2"
-                            % len(nj.get("launches", [])))
+            mine = [l_ for l_ in nj.get("launches", []) if dom and l_["kernel"].endswith(dom)]
+            if mine:
+                traffic = sum(l_["dram_bytes"] for l_ in mine) / len(mine)
+                traffic_note = ("dram__bytes_read+write per launch, mean over the %d %s launches of the committed ncu --set full capture "
+                                "(profiles/r1_conv_tc_ncu.csv; different layers than the event-timed mean, same kernel); operands are "
+                                "4 B/element (bf16 hi+lo), outputs mostly stay in the 126 MB L2" % (len(mine), dom))
         if recs and tc_ms > 0:
             ach = tc_fl / (tc_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05.mma kind::f16 + TMA)", "achieved": ach, "peak": pk["bf16_tflops"],
+            ach_all = all_fl / (all_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "%s (tcgen05.mma kind::f16 + TMA, persistent)" % dom, "achieved": ach, "peak": pk["bf16_tflops"],
                     "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["source"],
-                    "launches_per_step": len(recs) / min(a.steps, 3), "kernel_ms_per_step": tc_ms / min(a.steps, 3),
+                    "launches_per_step": len(dom_recs) / min(a.steps, 3), "kernel_ms_per_step": tc_ms / min(a.steps, 3),
                     "share_of_step": (tc_ms / min(a.steps, 3)) / ms_step, "mma_terms": nterms,
                     "issued_frac": nterms * ach / pk["bf16_tflops"],
+                    "all_tcgen05_convs": {"achieved": ach_all, "frac": ach_all / pk["bf16_tflops"], "issued_frac": nterms * ach_all / pk["bf16_tflops"],
+                                          "launches_per_step": len(recs) / min(a.steps, 3), "kernel_ms_per_step": all_ms / min(a.steps, 3),
+                                          "share_of_step": (all_ms / min(a.steps, 3)) / ms_step},
                     "note": "achieved = algorithmic 2*M*N*K per launch / event time; the fp32-grade path issues mma_terms bf16 MMAs per "
                             "algorithmic MAC, so tensor-pipe occupancy ~ issued_frac"}
         else:

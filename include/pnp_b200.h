@@ -56,6 +56,9 @@ const char* pnp_error_string(int code);
 int pnp_version(void);
 /* 1 if the loaded library carries the tcgen05/TMA convolution path and the device is sm_100 */
 int pnp_tc_available(void);
+/* tile configuration chosen by the most recent pnp_conv2d_tc_fwd / _dgrad call (N tile, K block, split-K factor); lets the
+   benchmark attribute each timed launch to a kernel instantiation.  Host-side bookkeeping only. */
+int pnp_tc_last_config(int* block_n, int* block_k, int* ksplit);
 
 /* ---- convolution, general SIMT fp32 path (conv_simt.cu) --------------------------------------
  * replaces tf.nn.conv2d (layers.py:18,24,67,73) and tf.nn.atrous_conv2d (layers.py:86,92) plus
@@ -71,9 +74,12 @@ int pnp_conv2d_wgrad(const float* x, const float* dy, float* dw, const pnp_conv_
 int pnp_weight_transpose(const float* w, float* wT, int taps, int Cin, int Cout, void* stream);
 
 /* ---- convolution, tcgen05 + TMA tensor-core path (conv_tc.cu) ----------------------------------
- * Same math as pnp_conv2d_fwd for convolutions with Cin % 64 == 0 and Cout % 64 == 0 (any stride / dilation / kernel <= 5x5),
- * operands pre-split into bf16 planes (pnp_split_bf16); nterms = 3 gives fp32-grade results
- * (hi*hi + hi*lo + lo*hi), nterms = 1 is the plain bf16 path of BASELINE config 5. */
+ * Same math as pnp_conv2d_fwd for convolutions whose Cin and Cout are each a multiple of 64, or exactly 32 or 16 (any stride /
+ * dilation / kernel <= 5x5; K blocks of 64 / 32 / 16 channels = SWIZZLE_128B / 64B / 32B operand tiles), operands pre-split into
+ * bf16 planes (pnp_split_bf16); nterms = 3 gives fp32-grade results (hi*hi + hi*lo + lo*hi), nterms = 1 is the plain bf16 path
+ * of BASELINE config 5.  Unsupported shapes return PNP_ERR_UNSUPPORTED (the caller then uses pnp_conv2d_*).  Layers with very
+ * few tiles and a deep reduction are split along K inside the call (atomic accumulation into a zeroed y; bn_sum/bn_sumsq are then
+ * produced by an internal pnp_bn_stats pass).  The weight gradient takes Cin in {32, 64k} and Cout = 64k. */
 int pnp_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long long n, void* stream);
 /* w HWIO fp32 -> bf16 planes: for_dgrad == 0: [tap][Cout][Cin] (K-major B operand of the forward conv);
  * for_dgrad != 0: [tap][Cin][Cout] (K-major B operand of the data gradient) */

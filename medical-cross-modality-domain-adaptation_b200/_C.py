@@ -89,6 +89,8 @@ lib.pnp_error_string.argtypes = [c_int]
 lib.pnp_error_string.restype = ctypes.c_char_p
 lib.pnp_version.restype = c_int
 lib.pnp_tc_available.restype = c_int
+lib.pnp_tc_last_config.argtypes = [P, P, P]
+lib.pnp_tc_last_config.restype = c_int
 
 # launch counter: bench.py reports how many of OUR kernels ran inside the timed region
 launch_count = 0

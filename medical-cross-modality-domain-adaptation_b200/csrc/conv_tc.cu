@@ -848,6 +848,8 @@ int choose_tile(int U, int V, int B, int rows, int exact, int* tw, int* th, int*
   return PNP_OK;
 }
 
+int g_last_cfg[3] = {0, 0, 0};      // {N tile, K block, split-K factor} of the most recent conv launch (profiling aid)
+
 int sm_count() {
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -926,6 +928,7 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
     if (block_n == 128 && bk == 32) block_n = 64;      // (no 128 x 32-wide instantiation)
   }
   a.kchunks = a.Cin / bk;
+  g_last_cfg[0] = block_n; g_last_cfg[1] = bk; g_last_cfg[2] = 1;
   {
     const int n_tiles = a.Cout / block_n;
     if (a.nphases == 0) {
@@ -965,6 +968,7 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
       if (ks > 32) ks = 32;
       if (ks > 1) {
         a.ksplit = ks;
+        g_last_cfg[2] = ks;
         a.total_tiles *= ks;
         if (!a.accumulate) PNP_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)a.B * a.OH * a.OW * a.Cout, s));
         bn_sum_after = a.bn_sum; bn_sumsq_after = a.bn_sumsq;      // statistics of partial sums are meaningless: separate pass
@@ -1013,6 +1017,13 @@ bool tc_geom_ok(const pnp_conv_geom* g) {
 }
 
 }  // namespace
+
+extern "C" int pnp_tc_last_config(int* block_n, int* block_k, int* ksplit) {
+  if (block_n) *block_n = g_last_cfg[0];
+  if (block_k) *block_k = g_last_cfg[1];
+  if (ksplit) *ksplit = g_last_cfg[2];
+  return PNP_OK;
+}
 
 extern "C" int pnp_tc_available(void) {
   int dev = 0;

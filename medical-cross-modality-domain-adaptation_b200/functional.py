@@ -35,7 +35,14 @@ def _tc_launch(tag, flops, name, *args):
     e0.record()
     call(name, *args)
     e1.record()
-    PROFILE.append((e0, e1, flops, tag))
+    kern = "simt"
+    if name in ("pnp_conv2d_tc_fwd", "pnp_conv2d_tc_dgrad"):
+        n_, k_, s_ = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        _C.lib.pnp_tc_last_config(ctypes.byref(n_), ctypes.byref(k_), ctypes.byref(s_))
+        kern = "conv_tc_kernel<%d, %d, %d>" % (n_.value, 1 if _tc_mode() == 1 else 3, k_.value)
+    elif name == "pnp_conv2d_tc_wgrad":
+        kern = "conv_wgrad_tc_kernel"
+    PROFILE.append((e0, e1, flops, tag, kern))
 
 
 def same_pad(n, k, s, d=1):
