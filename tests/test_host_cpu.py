@@ -253,3 +253,33 @@ def test_tfrecord_reader_round_trip_and_reference_slicing(tmp_path):
     open(files[0], "wb").write(bytes(raw))
     with pytest.raises(IOError):
         list(tfr.read_records(files[0]))
+
+
+def test_conv_routing_table_matches_the_kernel_contract():
+    """host-side routing (functional._tc_candidate) against the channel contract documented in include/pnp_b200.h:
+    forward / data gradient on tcgen05 when Cin and Cout are each 64k, 32 or 16; weight gradient when Cin in {32, 64k}
+    and Cout = 64k; everything else (3/5/40-channel ends) on the general fp32 kernels."""
+    from pnp_b200 import functional as F
+    from pnp_b200._C import ConvGeom
+
+    def g(cin, cout, k=3, s=1):
+        return ConvGeom(8, 64, 64, cin, 64 // s, 64 // s, cout, k, k, s, 1, 1, 1)
+
+    assert F.TC_K32 and F.TC_K16
+    F._tc_declined.clear()
+    yes = [("fwd", 512, 512), ("dgrad", 512, 2560), ("wgrad", 64, 64), ("fwd", 32, 64), ("dgrad", 32, 64), ("wgrad", 32, 64),
+           ("fwd", 16, 16), ("dgrad", 16, 32), ("fwd", 16, 32), ("fwd", 64, 320), ("wgrad", 128, 256)]
+    no = [("fwd", 3, 16), ("fwd", 40, 5), ("dgrad", 40, 5), ("fwd", 5, 16), ("wgrad", 16, 16), ("wgrad", 16, 32), ("wgrad", 32, 32),
+          ("fwd", 48, 64), ("fwd", 64, 24)]
+    for kind, ci, co in yes:
+        assert F._tc_candidate(kind, g(ci, co)), (kind, ci, co)
+    for kind, ci, co in no:
+        assert not F._tc_candidate(kind, g(ci, co)), (kind, ci, co)
+    assert not F._tc_candidate("fwd", g(64, 64, k=7))            # more than 25 taps
+    # a shape the library declined once is not offered again
+    F._tc_declined.add(F._gkey("fwd", g(16, 64)))
+    assert not F._tc_candidate("fwd", g(16, 64))
+    F._tc_declined.clear()
+    # producers emit operand planes exactly for the tensors a tcgen05 convolution can consume
+    assert [bool(F._want_planes(c)) for c in (16, 32, 64, 320, 5, 40, 48)] == ([True, True, True, True, False, False, False]
+                                                                                if F._tc_mode() else [False] * 7)
