@@ -15,7 +15,7 @@ output_path = "./tmp_exps/mr_baseline"
 restore = True  # the reference restores even on a first run and falls through to "start from beginning" (:28,73)
 num_cls = 5
 batch_size = 10
-training_iters = 100
+training_iters = 10            # train_segmenter.py:33
 epochs = 5000
 checkpoint_space = 1500
 optimizer = 'adam'

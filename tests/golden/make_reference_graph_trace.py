@@ -1,0 +1,676 @@
+"""Trace the REFERENCE'S OWN graph-construction code (adversarial.py:44-443 + layers.py + ops.py, imported unmodified from
+/root/reference) under a recording shim of `tensorflow`, and commit the canonical layer list as
+tests/golden/reference_graph_trace.json.
+
+Nothing numerical runs: the shim's tensors carry only a static shape, a provenance tag and the variable they came from.  What
+the trace pins is the ARCHITECTURE the reference builds -- for every convolution its filter variable (name and shape), stride,
+dilation, padding rule, where dropout sits and which keep_prob feeds it, the batch-norm scope / training switch / trainable flag,
+the skip connection (identity or zero channel pad), the activation; the pooling positions; every PS call; the channel layout of
+the discriminator input; the final matmuls -- in execution order, for the zip network (MR path + CT "DAM" path), both calls of
+create_second_half, both calls of create_classifier and both calls of create_mask_critic.
+
+`Full_DRN.__init__` of the reference raises AttributeError at adversarial.py:102 (`self.predicter`) after the segmenter halves
+and the feature discriminator have been built; the mask critic is then traced by calling `create_mask_critic` exactly as
+adversarial.py:116-118 would.  tests/test_reference_graph_trace.py replays the PRODUCT's graph code on CPU with recording stand-ins
+for its kernels and compares the two lists.
+
+    python tests/golden/make_reference_graph_trace.py          # needs /root/reference; the tests only read the .json
+"""
+import contextlib
+import importlib.util
+import json
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+REF = os.environ.get("PNP_REFERENCE_ROOT", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_graph_trace.json")
+BATCH = 2          # any B >= 2 (the B == 1 branch of ops.py is a different permutation, not a different architecture)
+
+
+# ------------------------------------------------------------------------------------------------
+# symbolic tensors
+# ------------------------------------------------------------------------------------------------
+class _Shape(object):
+    def __init__(self, s):
+        self._s = list(s)
+
+    def as_list(self):
+        return list(self._s)
+
+
+class Sym(object):
+    """static shape + provenance.  `src` names what produced it (used to label the discriminator input channels)."""
+    _n = 0
+
+    def __init__(self, shape, src, var=None):
+        self.shape = [int(v) for v in shape]
+        self.src = src
+        self.var = var              # Variable record if this tensor IS a variable
+        Sym._n += 1
+        self.id = Sym._n
+
+    def get_shape(self):
+        return _Shape(self.shape)
+
+    def _bin(self, other, op):
+        o = other.src if isinstance(other, Sym) else repr(other)
+        out = Sym(self.shape, "%s(%s,%s)" % (op, self.src, o))
+        REC.raw(op, a=self, b=other, out=out)
+        return out
+
+    def __add__(self, o):
+        return self._bin(o, "add")
+
+    __radd__ = __add__
+
+    def __mul__(self, o):
+        return self._bin(o, "mul")
+
+    __rmul__ = __mul__
+
+    def __sub__(self, o):
+        return self._bin(o, "sub")
+
+    def __truediv__(self, o):
+        return self._bin(o, "div")
+
+    __div__ = __truediv__
+
+    def __neg__(self):
+        return self._bin(-1.0, "mul")
+
+    def __rsub__(self, o):
+        return self._bin(o, "sub")
+
+    def __rtruediv__(self, o):
+        return self._bin(o, "div")
+
+    __rdiv__ = __rtruediv__
+
+    def __getitem__(self, idx):
+        idx = idx if isinstance(idx, tuple) else (idx,)
+        shape = []
+        for n, i in zip(self.shape, idx):
+            if isinstance(i, slice):
+                shape.append(len(range(*i.indices(n))))
+        shape += self.shape[len(idx):]
+        return Sym(shape, self.src)
+
+
+class Flag(object):
+    """a scalar placeholder (BN training switch, keep_prob)"""
+
+    def __init__(self, name, default=None):
+        self.name, self.default = name, default
+
+    def tag(self):
+        return "ph:" + self.name
+
+
+def _short(src):
+    """compact provenance: the variable of the last convolution that produced the tensor"""
+    if src.startswith("PS("):
+        return "PS(%s)" % _short(src[3:-1])
+    if src.startswith("argmax("):
+        return "argmax(%s)" % _short(src[7:-1])
+    i = max(src.rfind("conv("), src.rfind("aconv("))
+    if i < 0:
+        return src
+    j = src.index("(", i)
+    return "out_of:" + src[j + 1:src.index(")", j)]
+
+
+def _tag(v):
+    if isinstance(v, Flag):
+        return v.tag()
+    if isinstance(v, bool):
+        return v
+    if isinstance(v, (int, float)):
+        return float(v)
+    return repr(v)
+
+
+# ------------------------------------------------------------------------------------------------
+# recorder: raw op stream -> canonical layer events
+# ------------------------------------------------------------------------------------------------
+class Recorder(object):
+    def __init__(self):
+        self.events = []          # canonical
+        self.section = None
+        self.depth_ps = 0
+        self.open = None          # conv event still collecting dropout / bn / skip / act
+        self.pending_pad = None   # SYMMETRIC tf.pad feeding the next conv
+        self.pending_skip = {}    # Sym id of a zero-channel-padded skip -> pad amount
+
+    def set_section(self, name):
+        self._close()
+        self.section = name
+
+    def emit(self, ev):
+        self._close()
+        ev["section"] = self.section
+        self.events.append(ev)
+
+    def _close(self):
+        if self.open is not None:
+            ev, self.open = self.open, None
+            ev.pop("_cur", None)
+            ev["section"] = self.section
+            self.events.append(ev)
+
+    def raw(self, op, **kw):
+        if self.depth_ps:
+            return
+        if op == "pad":
+            x, paddings, mode, out = kw["x"], kw["paddings"], kw["mode"], kw["out"]
+            if mode == "SYMMETRIC":
+                self.pending_pad = (out.id, paddings)
+            else:
+                assert paddings[0] == [0, 0] and paddings[1] == [0, 0] and paddings[2] == [0, 0], paddings
+                assert paddings[3][0] == paddings[3][1]
+                self.pending_skip[out.id] = (x.id, paddings[3][0])
+            return
+        if op in ("conv2d", "atrous_conv2d"):
+            self._close()
+            x, W = kw["x"], kw["W"]
+            padding = kw["padding"]
+            in_shape = x.shape
+            if self.pending_pad is not None and self.pending_pad[0] == x.id:
+                assert padding == "VALID"
+                p = self.pending_pad[1]
+                assert p[1][0] == p[1][1] == W.shape[0] // 2 and p[2][0] == p[2][1] == W.shape[1] // 2, (p, W.shape)
+                padding = "SYMMETRIC"
+                in_shape = [x.shape[0], x.shape[1] - 2 * p[1][0], x.shape[2] - 2 * p[2][0], x.shape[3]]
+            self.pending_pad = None
+            self.open = {"op": "conv", "w": W.var["name"], "wshape": list(W.shape), "w_trainable": W.var["trainable"],
+                         "w_kind": W.var["kind"], "w_stddev": W.var["stddev"],
+                         "stride": kw["stride"], "dil": kw["rate"], "padding": padding, "in": in_shape[1:], "out": kw["out"].shape[1:],
+                         "input_src": x.src if x.src.startswith("ph:") else None,
+                         "input_layout": ([[_short(s_), int(c_)] for s_, c_ in x.parts] if len(getattr(x, "parts", [])) > 1 else None),
+                         "keep": None, "bn": None, "bn_train": None, "bn_trainable": None, "bn_decay": None, "skip": "none", "act": "none",
+                         "_cur": kw["out"].id, "_x": x.id}
+            return
+        ev = self.open
+        if op == "dropout":
+            assert ev is not None and kw["x"].id == ev["_cur"], "dropout not directly after a convolution"
+            assert ev["bn"] is None and ev["keep"] is None
+            ev["keep"] = _tag(kw["keep_prob"])
+            ev["_cur"] = kw["out"].id
+            return
+        if op == "batch_norm":
+            assert ev is not None and kw["x"].id == ev["_cur"], "batch_norm not on the conv/dropout output"
+            ev["bn"], ev["bn_train"], ev["bn_trainable"], ev["bn_decay"] = kw["scope"], _tag(kw["is_training"]), kw["trainable"], kw["decay"]
+            ev["_cur"] = kw["out"].id
+            return
+        if op == "add":
+            a, b = kw["a"], kw["b"]
+            if not (ev is not None and isinstance(b, Sym) and b.id == ev["_cur"] and isinstance(a, Sym) and a.shape == b.shape
+                    and ev["bn"] is not None):
+                return            # loss arithmetic, not the `x_s + _inner_conv` of layers.py:164-166 / 186-189
+            if a.id in self.pending_skip:
+                ev["skip"] = "pad%d" % self.pending_skip[a.id][1]
+            else:
+                ev["skip"] = "identity"
+            ev["skip_from_conv_input_of"] = None
+            ev["_cur"] = kw["out"].id
+            return
+        if op in ("relu", "leaky_relu"):
+            assert ev is not None and kw["x"].id == ev["_cur"], "activation not on the layer output"
+            ev["act"] = "relu" if op == "relu" else "lrelu%g" % kw["alpha"]
+            ev["_cur"] = kw["out"].id
+            self._close()
+            return
+        if op == "max_pool":
+            self.emit({"op": "maxpool", "k": kw["k"], "stride": kw["stride"], "padding": kw["padding"], "in": kw["x"].shape[1:],
+                       "out": kw["out"].shape[1:]})
+            return
+        if op == "matmul":
+            self.emit({"op": "fc", "w": kw["W"].var["name"], "wshape": list(kw["W"].shape), "w_trainable": kw["W"].var["trainable"],
+                       "in": kw["x"].shape[1:]})
+            return
+        if op in ("tile", "concat", "argmax", "expand_dims", "cast", "reshape", "exp", "reduce_sum", "div", "clip", "stack", "mul", "sub", "add"):
+            return            # bookkeeping handled through Sym.src (discriminator input layout) or irrelevant here
+        raise RuntimeError("unhandled raw op %s" % op)
+
+
+REC = Recorder()
+
+
+# ------------------------------------------------------------------------------------------------
+# the tensorflow shim
+# ------------------------------------------------------------------------------------------------
+class Graph(object):
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.vars = {}                # full name -> record
+        self.order = []
+        self.scope = []               # variable-scope stack: names of tf.get_variable / batch_norm variables
+        self.nscope = []              # name-scope stack (variable scopes open one too): names of tf.Variable ops
+        self.used = {}                # ("v"|"n", scope path) -> {base name: count}   (TF's unique-name rule)
+
+    def path(self, kind="v"):
+        return "/".join(s for s in (self.scope if kind == "v" else self.nscope) if s)
+
+    def unique(self, base, kind="v"):
+        d = self.used.setdefault((kind, self.path(kind)), {})
+        n = d.get(base, 0)
+        d[base] = n + 1
+        return base if n == 0 else "%s_%d" % (base, n)
+
+    def full(self, name, kind="v"):
+        p = self.path(kind)
+        return (p + "/" + name) if p else name
+
+    def new_var(self, full, shape, trainable, kind, stddev=None):
+        rec = {"name": full, "shape": [int(v) for v in shape], "trainable": bool(trainable), "kind": kind, "stddev": stddev}
+        assert full not in self.vars, full
+        self.vars[full] = rec
+        self.order.append(full)
+        return rec
+
+
+G = Graph()
+
+
+class _Init(object):
+    def __init__(self, shape, stddev):
+        self.shape, self.stddev = shape, stddev
+
+
+def _conv_out(n, k, s, d, padding):
+    if padding == "SAME":
+        return -(-n // s)
+    return (n - ((k - 1) * d + 1)) // s + 1
+
+
+def _make_tf():
+    tf = types.ModuleType("tensorflow")
+    tf.float32, tf.int32, tf.int64, tf.string, tf.AUTO_REUSE = "float32", "int32", "int64", "string", "AUTO_REUSE"
+    tf.FixedLenFeature = lambda shape, dtype: ("FixedLenFeature", shape, dtype)
+    tf.reset_default_graph = G.reset
+
+    def placeholder(dtype, shape=None, name=None):
+        if shape is None:
+            ph = Flag(name or "keep_prob")
+            return ph
+        placeholder.count += 1
+        nm = name or "Placeholder_%d" % placeholder.count
+        return Sym([BATCH if v is None else v for v in shape], "ph:" + nm)
+    placeholder.count = 0
+    tf.placeholder = placeholder
+    tf.placeholder_with_default = lambda default, shape=None, name=None: Flag(name, default)
+
+    @contextlib.contextmanager
+    def variable_scope(name, reuse=None):
+        G.scope.append(name)
+        G.nscope.append(name)
+        try:
+            yield name
+        finally:
+            G.scope.pop()
+            G.nscope.pop()
+    tf.variable_scope = variable_scope
+
+    @contextlib.contextmanager
+    def name_scope(name):
+        G.nscope.append(name)          # affects tf.Variable names only; tf.get_variable (batch_norm) ignores it
+        try:
+            yield name
+        finally:
+            G.nscope.pop()
+    tf.name_scope = name_scope
+
+    tf.truncated_normal = lambda shape, stddev=1.0: _Init(shape, stddev)
+    tf.truncated_normal_initializer = lambda stddev=1.0: _Init(None, stddev)
+
+    def Variable(initial, trainable=True, name=None):
+        assert isinstance(initial, _Init)
+        full = G.full(G.unique(name or "Variable", "n"), "n")
+        rec = G.new_var(full, initial.shape, trainable, "tf.Variable", initial.stddev)
+        return Sym(initial.shape, "var:" + full, var=rec)
+    tf.Variable = Variable
+
+    def get_variable(name, shape=None, initializer=None, trainable=True):
+        full = G.full(name)
+        if full in G.vars:                   # AUTO_REUSE
+            rec = G.vars[full]
+            assert rec["shape"] == [int(v) for v in shape], (full, rec["shape"], shape)
+        else:
+            rec = G.new_var(full, shape, trainable, "tf.get_variable", initializer.stddev if initializer else None)
+        return Sym(shape, "var:" + full, var=rec)
+    tf.get_variable = get_variable
+
+    tf.constant = lambda value, shape=None: value
+    tf.cast = lambda x, dtype: (REC.raw("cast", x=x) or x) if isinstance(x, Sym) else x
+
+    def pad(x, paddings, mode="CONSTANT"):
+        p = [[int(a), int(b)] for a, b in paddings]
+        out = Sym([n + a + b for n, (a, b) in zip(x.shape, p)], x.src if mode != "SYMMETRIC" else "mirror(%s)" % x.src)
+        REC.raw("pad", x=x, paddings=p, mode=mode, out=out)
+        return out
+    tf.pad = pad
+
+    nn = types.ModuleType("tensorflow.nn")
+
+    def conv2d(x, W, strides, padding):
+        assert strides[0] == strides[3] == 1 and strides[1] == strides[2]
+        s = int(strides[1])
+        kh, kw, ci, co = W.shape
+        assert ci == x.shape[3], (W.var["name"], x.shape, W.shape)
+        out = Sym([x.shape[0], _conv_out(x.shape[1], kh, s, 1, padding), _conv_out(x.shape[2], kw, s, 1, padding), co], "conv(%s)" % W.var["name"])
+        REC.raw("conv2d", x=x, W=W, stride=s, rate=1, padding=padding, out=out)
+        return out
+    nn.conv2d = conv2d
+
+    def atrous_conv2d(x, W, rate, padding):
+        kh, kw, ci, co = W.shape
+        assert ci == x.shape[3]
+        out = Sym([x.shape[0], _conv_out(x.shape[1], kh, 1, rate, padding), _conv_out(x.shape[2], kw, 1, rate, padding), co], "aconv(%s)" % W.var["name"])
+        REC.raw("atrous_conv2d", x=x, W=W, stride=1, rate=int(rate), padding=padding, out=out)
+        return out
+    nn.atrous_conv2d = atrous_conv2d
+
+    def dropout(x, keep_prob):
+        out = Sym(x.shape, x.src)
+        REC.raw("dropout", x=x, keep_prob=keep_prob, out=out)
+        return out
+    nn.dropout = dropout
+
+    def relu(x):
+        out = Sym(x.shape, x.src)
+        REC.raw("relu", x=x, out=out)
+        return out
+    nn.relu = relu
+
+    def leaky_relu(x, alpha=0.2):
+        out = Sym(x.shape, x.src)
+        REC.raw("leaky_relu", x=x, alpha=alpha, out=out)
+        return out
+    nn.leaky_relu = leaky_relu
+
+    def max_pool(x, ksize, strides, padding):
+        k, s = int(ksize[1]), int(strides[1])
+        out = Sym([x.shape[0], -(-x.shape[1] // s), -(-x.shape[2] // s), x.shape[3]], "pool(%s)" % x.src)
+        REC.raw("max_pool", x=x, k=k, stride=s, padding=padding, out=out)
+        return out
+    nn.max_pool = max_pool
+    nn.l2_loss = lambda w: Sym([], "l2")
+    nn.softmax = lambda x: Sym(x.shape, x.src)
+    tf.nn = nn
+
+    contrib = types.ModuleType("tensorflow.contrib")
+    layers = types.ModuleType("tensorflow.contrib.layers")
+
+    def batch_norm(x, is_training=True, decay=0.999, scale=False, center=True, scope=None, variables_collections=None,
+                   updates_collections="UPDATE_OPS", trainable=True):
+        assert scale and center and updates_collections is None
+        sc = scope if scope is not None else G.unique("BatchNorm")
+        G.scope.append(sc)
+        try:
+            C = x.shape[-1]
+            for nm, tr in (("beta", trainable), ("gamma", trainable), ("moving_mean", False), ("moving_variance", False)):
+                full = G.full(nm)
+                if full not in G.vars:
+                    G.new_var(full, [C], tr, "batch_norm")
+                else:
+                    assert G.vars[full]["shape"] == [C]
+            full_scope = G.path()
+        finally:
+            G.scope.pop()
+        out = Sym(x.shape, x.src)
+        REC.raw("batch_norm", x=x, scope=full_scope, is_training=is_training, trainable=bool(trainable), decay=decay, out=out)
+        return out
+    layers.batch_norm = batch_norm
+    contrib.layers = layers
+    framework = types.ModuleType("tensorflow.contrib.framework")
+    contrib.framework = framework
+    tf.contrib = contrib
+
+    # ---- shape ops (PS, discriminator input assembly, softmax bookkeeping) ----
+    def reshape(x, shape):
+        shape = list(shape)
+        n = int(np.prod(x.shape))
+        if -1 in shape:
+            known = int(np.prod([v for v in shape if v != -1]))
+            shape[shape.index(-1)] = n // known
+        assert int(np.prod(shape)) == n, (x.shape, shape)
+        out = Sym(shape, x.src)
+        REC.raw("reshape", x=x, out=out)
+        return out
+    tf.reshape = reshape
+    tf.transpose = lambda x, perm: Sym([x.shape[p] for p in perm], x.src)
+
+    def split(value, num, axis):
+        axis = axis % len(value.shape)
+        assert value.shape[axis] % num == 0
+        s = list(value.shape)
+        s[axis] //= num
+        return [Sym(s, value.src) for _ in range(num)]
+    tf.split = split
+
+    def concat(values, axis, name=None):
+        axis = axis % len(values[0].shape)
+        s = list(values[0].shape)
+        s[axis] = sum(v.shape[axis] for v in values)
+        srcs = []
+        for v in values:
+            srcs += getattr(v, "parts", [(v.src, v.shape[axis])])
+        out = Sym(s, "concat")
+        out.parts = srcs if axis == len(s) - 1 else [(values[0].src, s[-1])]
+        if axis != len(s) - 1:
+            out.src = values[0].src
+        REC.raw("concat", out=out)
+        return out
+    tf.concat = concat
+    tf.squeeze = lambda x: Sym([v for v in x.shape if v != 1], x.src)
+
+    def expand_dims(x, axis):
+        s = list(x.shape)
+        s.insert(axis if axis >= 0 else len(s) + 1 + axis, 1)
+        out = Sym(s, x.src)
+        return out
+    tf.expand_dims = expand_dims
+
+    def tile(x, multiples):
+        if isinstance(multiples, Sym):
+            return Sym(x.shape[:3] + [x.shape[3] * 0 + 1 * x.shape[3]], x.src)       # pixel_wise_softmax_2 bookkeeping only
+        out = Sym([n * int(m) for n, m in zip(x.shape, multiples)], x.src)
+        out.parts = [(x.src, x.shape[-1])] * int(multiples[-1])
+        return out
+    tf.tile = tile
+
+    def argmax(x, axis):
+        s = list(x.shape)
+        s.pop(axis)
+        return Sym(s, "argmax(%s)" % x.src)
+    tf.argmax = argmax
+    tf.shape = lambda x: list(x.shape)
+    tf.equal = lambda a, b: True
+    tf.stack = lambda vals: Sym([len(vals)], "stack")
+    tf.exp = lambda x: Sym(x.shape, x.src)
+    tf.log = lambda x: Sym(x.shape, x.src)
+
+    def reduce_sum(x, axis=None, keep_dims=False):
+        if axis is None:
+            return Sym([], "sum")
+        s = list(x.shape)
+        if keep_dims:
+            s[axis] = 1
+        else:
+            s.pop(axis)
+        return Sym(s, x.src)
+    tf.reduce_sum = reduce_sum
+    tf.reduce_mean = lambda x, axis=None, name=None: Sym([], "mean")
+    tf.div = lambda a, b, name=None: Sym(a.shape, a.src)
+    tf.add = lambda a, b: Sym(a.shape, a.src)
+    tf.clip_by_value = lambda x, lo, hi, name=None: Sym(x.shape, x.src)
+    tf.reverse = lambda x, dims: Sym(x.shape, x.src)
+    tf.slice = lambda x, begin, size: x
+
+    def matmul(x, W):
+        assert x.shape[-1] == W.shape[0]
+        out = Sym([x.shape[0], W.shape[1]], "fc(%s)" % W.var["name"])
+        REC.raw("matmul", x=x, W=W, out=out)
+        return out
+    tf.matmul = matmul
+    tf.one_hot = lambda x, depth, axis=-1: Sym(list(x.shape) + [depth], x.src)
+    tf.confusion_matrix = lambda a, b, num_classes: Sym([num_classes, num_classes], "cm")
+
+    python = types.ModuleType("tensorflow.python")
+    python.debug = types.ModuleType("tensorflow.python.debug")
+    tf.python = python
+    return tf, {"tensorflow": tf, "tensorflow.nn": nn, "tensorflow.contrib": contrib, "tensorflow.contrib.layers": layers,
+                "tensorflow.python": python, "tensorflow.python.debug": python.debug}
+
+
+def _load(name, alias=None):
+    spec = importlib.util.spec_from_file_location(alias or name, os.path.join(REF, name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[alias or name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _layout(sym):
+    """channel layout of the discriminator input: [(source tag, channels), ...] with consecutive equal sources merged"""
+    out = []
+    for src, c in getattr(sym, "parts", [(sym.src, sym.shape[-1])]):
+        out.append([src, c])
+    return out
+
+
+def main():
+    tf, mods = _make_tf()
+    sys.modules.update(mods)
+    for name in ("nibabel", "matplotlib"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="pnp_trace_")
+    os.chdir(tmp)                     # adversarial.py opens a log file in the cwd at import time
+    try:
+        layers = _load("layers")
+        ops = _load("ops")
+
+        real_ps = ops.PS
+
+        def PS(X, r, n_channel=8, batch_size=10):
+            REC._close()
+            REC.depth_ps += 1
+            try:
+                out = real_ps(X, r, n_channel=n_channel, batch_size=batch_size)
+            finally:
+                REC.depth_ps -= 1
+            assert out.shape == [X.shape[0], X.shape[1] * r, X.shape[2] * r, n_channel], (X.shape, out.shape)
+            out.src = "PS(%s)" % X.src
+            out.parts = [(out.src, n_channel)]
+            REC.emit({"op": "PS", "r": int(r), "n_channel": int(n_channel), "batch_size_arg": "self.batch_size" if batch_size == BATCH else int(batch_size),
+                      "in": X.shape[1:], "out": out.shape[1:], "of": _short(X.src)})
+            return out
+        ops.PS = PS
+        _load("lib")
+        adv = _load("adversarial")
+
+        cfg = {"mr_front_trainable": False, "ct_front_trainable": True, "joint_trainable": False, "cls_trainable": True, "m_cls_trainable": True}
+        cost_kwargs = {"regularizer": 1e-4, "gan_regularizer": 1e-4, "miu_dis": 1e-3, "miu_gen": 2e-3, "lambda_mask_loss": 0.1}
+
+        # mark sections by wrapping the four graph-construction methods
+        calls = {}
+
+        def sectioned(fn, label):
+            def wrapper(self, *a, **k):
+                calls[label] = calls.get(label, 0) + 1
+                REC.set_section("%s#%d" % (label, calls[label]))
+                out = fn(self, *a, **k)
+                REC._close()
+                if label == "create_classifier":
+                    pass
+                return out
+            return wrapper
+        for label in ("create_zip_network", "create_second_half", "create_classifier", "create_mask_critic"):
+            setattr(adv.Full_DRN, label, sectioned(getattr(adv.Full_DRN, label), label))
+
+        # the discriminator input: capture the tensor entering cls_1 (first conv of each create_classifier call)
+        net = adv.Full_DRN.__new__(adv.Full_DRN)
+        err = None
+        try:
+            adv.Full_DRN.__init__(net, channels=3, n_class=5, batch_size=BATCH, cost_kwargs=cost_kwargs, network_config=cfg)
+        except AttributeError as e:           # adversarial.py:102  self.predicter
+            err = str(e)
+        assert err is not None and "predicter" in err, err
+        REC._close()
+        # adversarial.py:116-118, executed the way __init__ would have
+        with tf.variable_scope("mask_cls_scope", reuse=tf.AUTO_REUSE):
+            net.create_mask_critic(Sym([BATCH, 256, 256, 5], "ct_logits"), num_cls=5)
+            net.create_mask_critic(Sym([BATCH, 256, 256, 5], "mr_logits"), num_cls=5)
+        REC._close()
+    finally:
+        os.chdir(cwd)
+
+    for ev in REC.events:
+        ev.pop("_x", None)
+        ev.pop("skip_from_conv_input_of", None)
+    trace = {"batch": BATCH,
+             "init_error_after_classifier": err,
+             "events": REC.events,
+             "variables": [G.vars[n] for n in G.order],
+             "weight_lists": {k: [s.var["name"] for s in getattr(net, k)] for k in
+                              ("mr_front_weights", "ct_front_weights", "cls_weights", "m_cls_weights", "joint_weights")}}
+    trace["source_segmenter"] = trace_source_segmenter(tf)
+    with open(OUT, "w") as f:
+        json.dump(trace, f, indent=0, sort_keys=True)
+    print("wrote %s: %d + %d events, %d + %d variables" % (OUT, len(trace["events"]), len(trace["source_segmenter"]["events"]),
+                                                           len(trace["variables"]), len(trace["source_segmenter"]["variables"])))
+
+
+def trace_source_segmenter(tf):
+    """source_segmenter.py does not parse (SyntaxError at :611, inside Trainer.test_eval).  Everything before `class Trainer`
+    (line 303) -- the module preamble and class Full_DRN in full -- is compiled and executed verbatim."""
+    global REC
+    path = os.path.join(REF, "source_segmenter.py")
+    with open(path) as f:
+        src = f.read()
+    try:
+        compile(src, path, "exec")
+        syntax_error = None
+    except SyntaxError as e:
+        syntax_error = {"line": e.lineno, "msg": e.msg}
+    lines = src.split("\n")
+    cut = next(i for i, ln in enumerate(lines) if ln.startswith("class Trainer"))
+    head = "\n".join(lines[:cut]) + "\n"
+    REC = Recorder()
+    Sym._n = 0
+    G.reset()
+    mod = types.ModuleType("pnp_reference_source_segmenter")
+    mod.__file__ = path
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="pnp_trace_")
+    os.chdir(tmp)
+    try:
+        exec(compile(head, path, "exec"), mod.__dict__)
+        REC.set_section("create_network")
+        cost_kwargs = {"cross_flag": True, "miu_cross": 1.0, "dice_flag": True, "miu_dice": 1.0, "regularizer": 1e-4}
+        # distinct trainable flags show which groups each flag governs (source_segmenter.py:91-209)
+        net = mod.Full_DRN(channels=3, n_class=5, batch_size=BATCH, main_trainable=False, adapt_trainable=True, cost_kwargs=cost_kwargs)
+        REC._close()
+    finally:
+        os.chdir(cwd)
+    for ev in REC.events:
+        ev.pop("_x", None)
+        ev.pop("skip_from_conv_input_of", None)
+    return {"syntax_error": syntax_error, "executed_lines": cut, "events": REC.events, "variables": [G.vars[n] for n in G.order],
+            "conv_weights": [s.var["name"] for s in net.conv_weights],
+            "ctor_args": {"main_trainable": False, "adapt_trainable": True}}
+
+
+if __name__ == "__main__":
+    main()
