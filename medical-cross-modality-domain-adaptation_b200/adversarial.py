@@ -315,6 +315,9 @@ class Trainer(object):
         self.global_step = 0
         self.dis_sub_iter = self.train_config.get("dis_sub_iter", 1)
         self.gen_sub_iter = self.train_config.get("gen_sub_iter", 1)
+        # the objectives `dis_loss + dis_reg / dis_sub_iter` are built once from train_config (adversarial.py:644,650); the
+        # schedule's later `dis_sub_iter += dis_sub_iter_inc` (a local of train(), :829/:886) never reaches them
+        self._obj_dis_sub_iter, self._obj_gen_sub_iter = self.dis_sub_iter, self.gen_sub_iter
         self._build_optimizers()
 
     def _build_optimizers(self):
@@ -343,11 +346,11 @@ class Trainer(object):
         net = self.net
         d_ids = {id(w) for w in net.cls_weights_unique}
         m_ids = {id(w) for w in net.m_cls_weights_unique}
-        base = net.gan_reg_coeff * net.miu_dis * 2.0 / float(self.dis_sub_iter)
+        base = net.gan_reg_coeff * net.miu_dis * 2.0 / float(self._obj_dis_sub_iter)
         wd = [base if id(v) in d_ids else (base * net.lambda_mask_loss if id(v) in m_ids else 0.0) for v in self.d_vars]
         self.dis_optimizer.set_weight_decay(wd)
         g_ids = {id(w) for w in net.ct_front_weights}
-        gb = net.gan_reg_coeff * net.miu_gen / float(self.gen_sub_iter)
+        gb = net.gan_reg_coeff * net.miu_gen / float(self._obj_gen_sub_iter)
         self.gen_optimizer.set_weight_decay([gb if id(v) in g_ids else 0.0 for v in self.g_vars])
 
     def _set_mode(self, mode):
@@ -512,7 +515,6 @@ class Trainer(object):
                 if step % upd_interval == 0 and step != 0:
                     self.dis_sub_iter += dis_inc
                     self.gen_sub_iter += gen_inc
-                    self._refresh_weight_decay()
                 if step % display_step == 0:
                     logging.info("Training step %s epoch %s finished, %.3f s" % (step, epoch, time.time() - start))
                 if step % ckpt_space == 0 and step != 0:

@@ -625,11 +625,240 @@ def main():
              "variables": [G.vars[n] for n in G.order],
              "weight_lists": {k: [s.var["name"] for s in getattr(net, k)] for k in
                               ("mr_front_weights", "ct_front_weights", "cls_weights", "m_cls_weights", "joint_weights")}}
+    trace["var_groups"], trace["optimizer"], trace["cost_numeric"] = trace_training_wiring(tf, adv, net, trace["weight_lists"])
+    trace["schedule"] = trace_training_schedule(tf, adv, net)
     trace["source_segmenter"] = trace_source_segmenter(tf)
     with open(OUT, "w") as f:
         json.dump(trace, f, indent=0, sort_keys=True)
     print("wrote %s: %d + %d events, %d + %d variables" % (OUT, len(trace["events"]), len(trace["source_segmenter"]["events"]),
                                                            len(trace["variables"]), len(trace["source_segmenter"]["variables"])))
+
+
+class _Num(object):
+    """temporarily turn the shim numeric: the reference's loss code is plain arithmetic over a handful of reductions"""
+
+    def __init__(self, tf):
+        self.tf = tf
+        self.saved = {}
+
+    def __enter__(self):
+        tf = self.tf
+        num = {"reduce_mean": lambda x, axis=None, name=None: np.mean(x), "reduce_sum": lambda x, axis=None, keep_dims=False: np.sum(x),
+               "log": np.log, "clip_by_value": lambda x, lo, hi, name=None: np.clip(x, lo, hi),
+               "Variable": lambda initial, trainable=True, name=None: float(initial)}
+        for k, v in num.items():
+            self.saved[k] = getattr(tf, k)
+            setattr(tf, k, v)
+        self.saved_nn = (tf.nn.l2_loss, tf.nn.softmax)
+        tf.nn.l2_loss = lambda w: float(w.l2) if hasattr(w, "l2") else float(np.sum(np.asarray(w, np.float64) ** 2) / 2)
+
+        def softmax(x):
+            e = np.exp(x - x.max(axis=-1, keepdims=True))
+            return e / e.sum(axis=-1, keepdims=True)
+        tf.nn.softmax = softmax
+        return self
+
+    def __exit__(self, *a):
+        for k, v in self.saved.items():
+            setattr(self.tf, k, v)
+        self.tf.nn.l2_loss, self.tf.nn.softmax = self.saved_nn
+
+
+class _VarObj(object):
+    def __init__(self, rec, l2=None):
+        self.name = rec["name"] + ":0"
+        self.rec = rec
+        self.l2 = l2
+
+
+def trace_training_wiring(tf, adv, net, weight_lists):
+    """adversarial.py:445-501 (cost, variable groups) and :633-656 (optimizers, clip) executed on the traced graph"""
+    # ---- _get_variables_by_scope: membership by substring, in tf.global_variables() order
+    tf.contrib.framework.get_variables = lambda: [_VarObj(G.vars[n]) for n in G.order]
+    adv.Full_DRN._get_variables_by_scope(net)
+    groups = {k: [v.rec["name"] for v in getattr(net, k)] for k in ("adapt_vars", "cls_vars", "seg_vars", "mri_seg_vars")}
+
+    # ---- _get_optimizer with recording optimizers
+    opt_log = {"optimizers": [], "clip": []}
+
+    class _Loss(object):
+        """linear combination of named scalars"""
+
+        def __init__(self, terms):
+            self.terms = dict(terms)
+
+        def __add__(self, o):
+            t = dict(self.terms)
+            for k, v in (o.terms if isinstance(o, _Loss) else {"const": o}).items():
+                t[k] = t.get(k, 0.0) + v
+            return _Loss(t)
+
+        __radd__ = __add__
+
+        def __mul__(self, c):
+            return _Loss({k: v * float(c) for k, v in self.terms.items()})
+
+        __rmul__ = __mul__
+
+    class RMSPropOptimizer(object):
+        def __init__(self, learning_rate=None, **kw):
+            self.cfg = {"kind": "RMSPropOptimizer", "learning_rate": learning_rate, "kwargs": dict(kw)}
+
+        def minimize(self, loss, global_step=None, var_list=None):
+            rec = dict(self.cfg)
+            rec["objective"] = loss.terms
+            rec["var_list"] = [v.rec["name"] for v in var_list]
+            opt_log["optimizers"].append(rec)
+            return "train_op_%d" % len(opt_log["optimizers"])
+    train = types.ModuleType("tensorflow.train")
+    train.RMSPropOptimizer = RMSPropOptimizer
+    tf.train = train
+    saved_var, saved_assign, saved_clip = tf.Variable, getattr(tf, "assign", None), tf.clip_by_value
+    tf.Variable = lambda initial, trainable=True, name=None: float(initial)
+    tf.clip_by_value = lambda v, lo, hi, name=None: ("clip", v, float(lo), float(hi))
+    tf.assign = lambda var, val: opt_log["clip"].append({"var": var.rec["name"], "lo": val[2], "hi": val[3], "of_same_var": val[1] is var})
+    net.dis_loss, net.dis_reg = _Loss({"dis_loss": 1.0}), _Loss({"dis_reg": 1.0})
+    net.ct_gen_loss, net.gen_reg = _Loss({"ct_gen_loss": 1.0}), _Loss({"gen_reg": 1.0})
+    me = types.SimpleNamespace(opt_kwargs={"learning_rate": 3e-4}, net=net, train_config={"dis_sub_iter": 20, "gen_sub_iter": 1})
+    adv.Trainer._get_optimizer(me, 200, "global_step")
+    opt_log["learning_rate_node"] = me.learning_rate_node
+    opt_log["train_config_used"] = {"dis_sub_iter": 20, "gen_sub_iter": 1}
+    tf.Variable, tf.clip_by_value = saved_var, saved_clip
+    if saved_assign is not None:
+        tf.assign = saved_assign
+
+    # ---- _get_cost evaluated numerically: critic outputs and per-variable l2 values are the inputs
+    rng = np.random.RandomState(7)
+    uniq = sorted({n for lst in weight_lists.values() for n in lst})
+    l2 = {n: float(rng.uniform(0.5, 20.0)) for n in uniq}
+    for key, lst in weight_lists.items():
+        setattr(net, key, [_VarObj({"name": n}, l2[n]) for n in lst])          # same multiplicities the graph code produced
+    cls = {k: rng.standard_normal((BATCH, 1)) for k in ("ct_cls", "mr_cls", "ct_mask", "mr_mask")}
+    cases = []
+    for lam in (0.3, 0.0, None):
+        ck = {"regularizer": 1e-4, "gan_regularizer": 1e-4, "miu_dis": 0.002, "miu_gen": 0.002}
+        if lam is not None:
+            ck["lambda_mask_loss"] = lam
+        with _Num(tf):
+            out = adv.Full_DRN._get_cost(net, None, None, cls["ct_cls"], cls["mr_cls"], cls["ct_mask"], cls["mr_mask"], dict(ck))
+        cases.append({"cost_kwargs": ck, "dis_loss": float(out[0]), "gen_loss": float(out[1]), "fixed_coeff_reg": float(out[2]),
+                      "dis_reg": float(out[3]), "gen_reg": float(out[4])})
+    cost = {"l2": l2, "critic_outputs": {k: v.reshape(-1).tolist() for k, v in cls.items()}, "cases": cases}
+    return groups, opt_log, cost
+
+
+def trace_training_schedule(tf, adv, net):
+    """Trainer.train (adversarial.py:767-946) inherited VERBATIM by a subclass that only replaces the data / monitoring
+    helpers (next_batch, output_minibatch_stats, _initialize's summaries) and runs against a recording Session: what comes out
+    is the order of optimizer / clip runs and the feed_dict of each (which BN switches and keep_prob every step kind uses)."""
+    log = []
+    names = {id(net.mr): "mr", id(net.ct): "ct", id(net.mr_front_bn): "mr_front_bn", id(net.joint_bn): "joint_bn",
+             id(net.ct_front_bn): "ct_front_bn", id(net.cls_bn): "cls_bn", id(net.m_cls_bn): "m_cls_bn", id(net.keep_prob): "keep_prob"}
+
+    class _Feed(object):
+        def __init__(self, q):
+            self.q = q
+
+    class Session(object):
+        def __init__(self, config=None):
+            self.graph = "graph"
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def _one(self, f):
+            if isinstance(f, _Feed):
+                return np.zeros((BATCH, 256, 256, 4), np.float32) if f.q.endswith("data") else "fid"
+            return f
+
+        def run(self, fetches, feed_dict=None):
+            feeds = {}
+            for k, v in (feed_dict or {}).items():
+                feeds[names[id(k)]] = "batch" if isinstance(v, np.ndarray) else v
+            if isinstance(fetches, tuple) and len(fetches) == 2 and fetches[0] == "assign_lr":
+                log.append({"op": "assign_lr", "value": fetches[1]})
+                return None
+            first = fetches[0] if isinstance(fetches, (list, tuple)) and fetches else fetches
+            if first == "dis_optimizer" or first == "gen_optimizer":
+                log.append({"op": first, "feeds": feeds})
+                return None, me.learning_rate_node
+            if isinstance(first, tuple) and first and first[0] == "clip_assign":
+                log.append({"op": "clip_op", "n": len(fetches)})
+                return [None] * len(fetches)
+            if isinstance(first, tuple) and first and first[0] == "assign_lr":
+                log.append({"op": "assign_lr", "value": first[1]})
+                return None
+            if isinstance(fetches, (list, tuple)):
+                return [self._one(f) for f in fetches]
+            return self._one(fetches)
+    tf.Session = Session
+    tf.ConfigProto = lambda: types.SimpleNamespace(gpu_options=types.SimpleNamespace(allow_growth=False))
+    tf.summary = types.SimpleNamespace(FileWriter=lambda *a, **k: None)
+    tf.train.Coordinator = lambda: types.SimpleNamespace(request_stop=lambda: None, join=lambda threads: None)
+    tf.train.get_checkpoint_state = lambda path: None
+    tf.train.start_queue_runners = lambda sess=None, coord=None, start=True: []
+
+    class RMSPropOptimizer(object):
+        n = 0
+
+        def __init__(self, learning_rate=None, **kw):
+            pass
+
+        def minimize(self, loss, global_step=None, var_list=None):
+            RMSPropOptimizer.n += 1
+            return "dis_optimizer" if RMSPropOptimizer.n == 1 else "gen_optimizer"      # order of adversarial.py:643-651
+    tf.train.RMSPropOptimizer = RMSPropOptimizer
+    saved = (tf.Variable, tf.clip_by_value, getattr(tf, "assign", None))
+    tf.Variable = lambda initial, trainable=True, name=None: float(initial) if not isinstance(initial, _Init) else saved[0](initial, trainable, name)
+    tf.clip_by_value = lambda v, lo, hi, name=None: ("clip", v, float(lo), float(hi))
+    tf.assign = lambda var, val: ("clip_assign", var) if hasattr(var, "rec") else ("assign_lr", float(val))
+
+    class _Loss(object):
+        def __add__(self, o):
+            return self
+        __radd__ = __add__
+        __mul__ = __rmul__ = __add__
+    net.dis_loss = net.dis_reg = net.ct_gen_loss = net.gen_reg = _Loss()
+
+    class Me(adv.Trainer):
+        def __init__(self):                                   # (the real one only stores arguments and opens the input queues)
+            self.net = net
+            self.num_cls = 5
+            self.batch_size = BATCH
+            self.opt_kwargs = {"learning_rate": 3e-4}
+            self.train_config = {"restore_from_baseline": False, "copy_main": False, "clear_rms": False, "lr_update": True,
+                                 "dis_interval": 1, "gen_interval": 1, "dis_sub_iter": 2, "gen_sub_iter": 1, "tag": "t",
+                                 "iter_upd_interval": 2, "dis_sub_iter_inc": 1, "gen_sub_iter_inc": 0, "lr_decay_factor": 0.98,
+                                 "checkpoint_space": 100, "training_iters": 5, "epochs": 1}
+            self.lr_update_flag = self.train_config["lr_update"]
+            self.ct_train_queue, self.ct_val_queue, self.mr_train_queue, self.mr_val_queue = "ct_train", "ct_val", "mr_train", "mr_val"
+
+        def _initialize(self, training_iters, output_path):    # adversarial.py:658-705 minus the tensorboard summaries
+            self.global_step = types.SimpleNamespace(eval=lambda: 0)
+            self.dis_optimizer, self.gen_optimizer = adv.Trainer._get_optimizer(self, training_iters, self.global_step)
+            return "init_glb", "init_loc"
+
+        def next_batch(self, input_queue, **k):
+            return _Feed(input_queue + ":data"), _Feed(input_queue + ":fid")
+
+        def output_minibatch_stats(self, sess, writer, step, *a, **k):
+            log.append({"op": "stats", "step": step, "detail": bool(k.get("detail", False))})
+    me = Me()
+    cfg_in = dict(me.train_config)
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="pnp_sched_")
+    os.chdir(tmp)
+    try:
+        me.train(output_path="./out", restore=True, restored_path="./out", training_iters=5, epochs=1, dropout=0.75, display_step=10 ** 6)
+    finally:
+        os.chdir(cwd)
+        tf.Variable, tf.clip_by_value = saved[0], saved[1]
+        if saved[2] is not None:
+            tf.assign = saved[2]
+    return {"train_config": cfg_in, "train_args": {"training_iters": 5, "epochs": 1, "dropout": 0.75}, "events": log}
 
 
 def trace_source_segmenter(tf):
@@ -667,7 +896,19 @@ def trace_source_segmenter(tf):
     for ev in REC.events:
         ev.pop("_x", None)
         ev.pop("skip_from_conv_input_of", None)
+    # source_segmenter.py:241-273 evaluated numerically on a small map (logits scaled so the 0.005 clip is active)
+    rng = np.random.RandomState(11)
+    logits = 4.0 * rng.standard_normal((2, 6, 5, 5))
+    lab = rng.randint(0, 5, size=(2, 6, 5))
+    lab[0, :3] = 0
+    y = np.eye(5)[lab]
+    me = types.SimpleNamespace(y=y, n_class=5)
+    with _Num(tf):
+        wce = float(mod.Full_DRN._softmax_weighted_loss(me, logits))
+        dice = float(mod.Full_DRN._dice_loss_fun(me, logits))
+    losses = {"logits": logits.tolist(), "labels": lab.tolist(), "weighted_loss": wce, "dice_loss": dice}
     return {"syntax_error": syntax_error, "executed_lines": cut, "events": REC.events, "variables": [G.vars[n] for n in G.order],
+            "losses_numeric": losses,
             "conv_weights": [s.var["name"] for s in net.conv_weights],
             "ctor_args": {"main_trainable": False, "adapt_trainable": True}}
 

@@ -98,6 +98,18 @@ class _Tracer(object):
         return torch.empty(x.shape[0], w.shape[1], device="meta")
 
 
+class _Graph(object):
+    """the variable registry as it was when the fixture built its network (a later Full_DRN resets the global one)"""
+
+    def __init__(self, vars_, order):
+        self.vars, self.order = vars_, order
+        self.graph = self
+
+
+def _snapshot(rt):
+    return _Graph(dict(rt.graph.vars), list(rt.graph.order))
+
+
 @pytest.fixture(scope="module")
 def product():
     from pnp_b200 import adversarial as A, functional as F, runtime as rt
@@ -123,7 +135,7 @@ def product():
     finally:
         for k, v in saved.items():
             setattr(F, k, v)
-    return net, rt, out
+    return net, _snapshot(rt), out
 
 
 def _ref_events(section):
@@ -247,7 +259,7 @@ def product_segmenter():
     finally:
         for k, v in saved.items():
             setattr(F, k, v)
-    return net, rt, tr.events
+    return net, _snapshot(rt), tr.events
 
 
 def test_source_segmenter_file_state_is_what_the_survey_says():
@@ -286,3 +298,161 @@ def test_source_segmenter_variables_and_l2_list_match_the_reference(product_segm
     ids = {id(v): k for k, v in rt.graph.vars.items()}
     assert [ids[id(w)] for w in net.conv_weights] == ref["conv_weights"]
     assert ref["conv_weights"].count("group_4/Variable_3") == 2 and "group_4/Variable_2" not in ref["conv_weights"]
+
+
+# ------------------------------------------------------------------------------------------------
+# training wiring: variable groups, optimizers, clip, cost arithmetic (adversarial.py:445-501, 633-656)
+# ------------------------------------------------------------------------------------------------
+def test_variable_groups_match_the_reference(product):
+    net, rt, _ = product
+    names = {id(v): k for k, v in rt.graph.vars.items()}
+    for key in ("adapt_vars", "cls_vars", "seg_vars", "mri_seg_vars"):
+        assert sorted(names[id(v)] for v in getattr(net, key)) == sorted(REF["var_groups"][key]), key
+    assert len(REF["var_groups"]["cls_vars"]) == 122 and len(REF["var_groups"]["adapt_vars"]) == 101
+
+
+def test_optimizer_wiring_matches_the_reference():
+    from pnp_b200 import adversarial as A, runtime as rt
+    net = A.Full_DRN(3, 5, B, cost_kwargs=dict(COST), network_config=dict(CFG))          # (makes its graph the current one)
+    opt = REF["optimizer"]
+    d_ref, g_ref = opt["optimizers"]
+    sub = opt["train_config_used"]
+    tr = A.Trainer(net, batch_size=B, opt_kwargs={"learning_rate": opt["learning_rate_node"]}, train_config=dict(sub, lr_update=False))
+    names = {id(v): k for k, v in rt.graph.vars.items()}
+    trainable = {v["name"] for v in REF["variables"] if v["trainable"]}
+    # minimize(var_list=cls_vars / adapt_vars): the variables that can receive a gradient
+    assert d_ref["kind"] == g_ref["kind"] == "RMSPropOptimizer" and d_ref["kwargs"] == g_ref["kwargs"] == {}
+    assert sorted(names[id(v)] for v in tr.d_vars) == sorted(n for n in d_ref["var_list"] if n in trainable)
+    assert sorted(names[id(v)] for v in tr.g_vars) == sorted(n for n in g_ref["var_list"] if n in trainable)
+    assert tr.dis_optimizer.get_lr() == pytest.approx(d_ref["learning_rate"]) and tr.gen_optimizer.get_lr() == pytest.approx(g_ref["learning_rate"])
+    assert (tr.dis_optimizer.decay, tr.dis_optimizer.momentum, tr.dis_optimizer.eps) == (0.9, 0.0, 1e-10)      # TF-1.4 defaults
+    # objectives: dis_loss + dis_reg / dis_sub_iter   and   ct_gen_loss + gen_reg / gen_sub_iter
+    assert d_ref["objective"] == {"dis_loss": 1.0, "dis_reg": pytest.approx(1.0 / sub["dis_sub_iter"])}
+    assert g_ref["objective"] == {"ct_gen_loss": 1.0, "gen_reg": pytest.approx(1.0 / sub["gen_sub_iter"])}
+    # ... which the product folds into per-variable weight decay: d(objective)/dw = coefficient * multiplicity * w
+    mult = lambda key, n: REF["weight_lists"][key].count(n)
+    wd_d = dict(zip((names[id(v)] for v in tr.d_vars), tr.dis_optimizer.seg_wd.tolist()))
+    for n, got in wd_d.items():
+        lam = net.lambda_mask_loss if n.startswith("mask_cls_scope") else 1.0
+        m = mult("cls_weights", n) + mult("m_cls_weights", n)
+        want = net.gan_reg_coeff * net.miu_dis * m * lam / sub["dis_sub_iter"]
+        assert got == pytest.approx(want, rel=1e-6, abs=1e-12), n
+    wd_g = dict(zip((names[id(v)] for v in tr.g_vars), tr.gen_optimizer.seg_wd.tolist()))
+    for n, got in wd_g.items():
+        want = net.gan_reg_coeff * net.miu_gen * mult("ct_front_weights", n) / sub["gen_sub_iter"]
+        assert got == pytest.approx(want, rel=1e-6, abs=1e-12), n
+    # clip_op: +-0.03 on every cls variable whose name contains "Variable" (26 filters / FC matrices, no batch-norm parameter)
+    clip_ref = {c["var"]: (c["lo"], c["hi"]) for c in opt["clip"]}
+    assert len(clip_ref) == 26 and set(clip_ref.values()) == {(-0.03, 0.03)} and all(c["of_same_var"] for c in opt["clip"])
+    clip_got = dict(zip((names[id(v)] for v in tr.d_vars), tr.dis_optimizer.seg_clip.tolist()))
+    assert {n for n, c in clip_got.items() if c > 0} == set(clip_ref) and all(c == pytest.approx(0.03) for c in clip_got.values() if c > 0)
+    assert all(c == 0 for c in tr.gen_optimizer.seg_clip.tolist())
+
+
+def test_oracle_cost_arithmetic_equals_the_reference_code():
+    """adversarial.py:445-476 executed numerically by the reference vs OracleAdversarial.dis_losses / gen_losses"""
+    import numpy as np
+    from oracle import pnp_graphs as PG
+    c = REF["cost_numeric"]
+    for case in c["cases"]:
+        ck = case["cost_kwargs"]
+        lam = ck.get("lambda_mask_loss", 1.0)
+        adv = PG.OracleAdversarial({}, B, dtype=torch.float64, miu_dis=ck["miu_dis"], miu_gen=ck["miu_gen"], lambda_mask_loss=lam,
+                                   gan_regularizer=ck["gan_regularizer"], regularizer=ck["regularizer"])
+        for n, v in c["l2"].items():
+            if n in adv.ps.w:
+                adv.ps.w[n] = torch.tensor([np.sqrt(2.0 * v)], dtype=torch.float64)        # l2_loss(w) == v
+        co = {k: torch.tensor(v, dtype=torch.float64).reshape(-1, 1) for k, v in c["critic_outputs"].items()}
+        dis_loss, dis_reg = adv.dis_losses(co["ct_cls"], co["mr_cls"], co["ct_mask"], co["mr_mask"])
+        gen_loss, gen_reg = adv.gen_losses(co["ct_cls"], co["ct_mask"])
+        for got, key in ((dis_loss, "dis_loss"), (dis_reg, "dis_reg"), (gen_loss, "gen_loss"), (gen_reg, "gen_reg")):
+            assert float(got) == pytest.approx(case[key], rel=1e-12, abs=1e-18), (key, lam)
+        del adv
+
+
+def test_oracle_supervised_losses_equal_the_reference_code():
+    """source_segmenter.py:241-273 executed numerically by the reference vs the oracle's numpy and torch forms"""
+    import numpy as np
+    from oracle import tf14_numpy as N, tf14_torch as T
+    s = REF["source_segmenter"]["losses_numeric"]
+    logits = np.array(s["logits"], dtype=np.float64)
+    y = np.eye(5)[np.array(s["labels"])]
+    assert N.softmax_weighted_loss(logits, y) == pytest.approx(s["weighted_loss"], rel=1e-12)
+    assert N.dice_loss(logits, y) == pytest.approx(s["dice_loss"], rel=1e-12)
+    lt, yt = torch.from_numpy(logits), torch.from_numpy(y)
+    assert float(T.softmax_weighted_loss(lt, yt)) == pytest.approx(s["weighted_loss"], rel=1e-12)
+    assert float(T.dice_loss(lt, yt)) == pytest.approx(s["dice_loss"], rel=1e-12)
+    assert (np.exp(logits) / np.exp(logits).sum(-1, keepdims=True)).min() < 0.005          # the clip is exercised
+
+
+# ------------------------------------------------------------------------------------------------
+# the training schedule and the per-step feeds (adversarial.py:767-946, executed verbatim against a recording Session)
+# ------------------------------------------------------------------------------------------------
+def test_training_schedule_and_step_feeds_match_the_reference(tmp_path):
+    from pnp_b200 import adversarial as A, optim, runtime as rt, _C
+    sched = REF["schedule"]
+    ref_ops = []
+    for e in sched["events"]:
+        if e["op"] == "dis_optimizer":
+            ref_ops.append("D")
+        elif e["op"] == "clip_op":
+            assert ref_ops and ref_ops[-1] == "D" and e["n"] == 26            # every discriminator update is followed by the clip
+            ref_ops[-1] = "D+clip"
+        elif e["op"] == "gen_optimizer":
+            ref_ops.append("G")
+    # step 0 trains nothing; dis_sub_iter grows by dis_sub_iter_inc every iter_upd_interval steps
+    assert ref_ops == ["D+clip", "D+clip", "G"] * 2 + ["D+clip", "D+clip", "D+clip", "G"] * 2
+    d_feeds = [e["feeds"] for e in sched["events"] if e["op"] == "dis_optimizer"]
+    g_feeds = [e["feeds"] for e in sched["events"] if e["op"] == "gen_optimizer"]
+    assert all(f == {"mr": "batch", "ct": "batch", "mr_front_bn": False, "joint_bn": False, "ct_front_bn": False, "cls_bn": True,
+                     "keep_prob": 0.75} for f in d_feeds)
+    assert all(f == {"ct": "batch", "mr_front_bn": False, "joint_bn": False, "ct_front_bn": True, "cls_bn": False, "keep_prob": 0.75}
+               for f in g_feeds)
+    assert [e for e in sched["events"] if e["op"] == "assign_lr"] == [{"op": "assign_lr", "value": 3e-4}]      # lr_update
+
+    # ---- the product's loop with recording steps
+    net = A.Full_DRN(3, 5, B, cost_kwargs=dict(COST), network_config=dict(CFG))
+    tr = A.Trainer(net, num_cls=5, batch_size=B, opt_kwargs={"learning_rate": 3e-4}, train_config=dict(sched["train_config"]))
+    got = []
+    tr.d_step = lambda mr, ct, keep_prob=0.75, apply=True: got.append(("D+clip", keep_prob, tuple(mr.shape), tuple(ct.shape)))
+    tr.g_step = lambda ct, keep_prob=0.75, apply=True: got.append(("G", keep_prob, tuple(ct.shape)))
+    wd_before = tr.dis_optimizer.seg_wd.clone()
+    tr.train(output_path=str(tmp_path), restore=True, restored_path=str(tmp_path), **sched["train_args"])
+    assert [g[0] for g in got] == ref_ops
+    assert all(g[1] == 0.75 for g in got) and all(g[2] == (B, 256, 256, 3) for g in got)
+    assert tr.dis_sub_iter == 4 and tr.gen_sub_iter == 1
+    assert torch.equal(tr.dis_optimizer.seg_wd, wd_before)          # the objective keeps its construction-time 1/dis_sub_iter
+
+    # ---- which BN switches the product's two steps use: run them up to the segmenter calls
+    calls = []
+
+    class _Stop(Exception):
+        pass
+
+    def probe(n_expected):
+        def segment(x, stream, keep_prob, front_bn, joint_bn=False):
+            calls.append({"stream": stream, "keep_prob": keep_prob, "front_bn": front_bn, "joint_bn": joint_bn})
+            if len(calls) == n_expected:
+                raise _Stop()
+            return {}
+        return segment
+    tr2 = A.Trainer(A.Full_DRN(3, 5, B, cost_kwargs=dict(COST), network_config=dict(CFG)), num_cls=5, batch_size=B,
+                    opt_kwargs={"learning_rate": 3e-4}, train_config=dict(sched["train_config"]))
+    saved = (optim.call, _C.call, rt.stream)
+    optim.call = _C.call = lambda *a, **k: None                      # no kernels: only the Python control flow is exercised
+    rt.stream = lambda: None
+    x = torch.empty(B, 256, 256, 3, device="meta")
+    try:
+        tr2.net.segment = probe(2)
+        with pytest.raises(_Stop):
+            tr2.d_step(x, x, 0.75)
+        d_calls, calls = calls, []
+        tr2.net.segment = probe(1)
+        with pytest.raises(_Stop):
+            tr2.g_step(x, 0.75)
+        g_calls = calls
+    finally:
+        optim.call, _C.call, rt.stream = saved
+    assert d_calls == [{"stream": "mr", "keep_prob": 0.75, "front_bn": d_feeds[0]["mr_front_bn"], "joint_bn": d_feeds[0]["joint_bn"]},
+                       {"stream": "ct", "keep_prob": 0.75, "front_bn": d_feeds[0]["ct_front_bn"], "joint_bn": d_feeds[0]["joint_bn"]}]
+    assert g_calls == [{"stream": "ct", "keep_prob": 0.75, "front_bn": g_feeds[0]["ct_front_bn"], "joint_bn": g_feeds[0]["joint_bn"]}]
