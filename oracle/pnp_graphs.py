@@ -7,9 +7,12 @@ their training steps, built on oracle/tf14_torch.py:
                          discriminator, mask critic, WGAN losses), :633-656 (RMSProp x2 + clip),
                          :840-882 (feed conventions of the D step and the G step)
 
-PARITY UNPINNED (see oracle/tf14_numpy.py): the reference has no tests/golden vectors and TF-1.4
-cannot run in this image; the reference's own modules do not even import (source_segmenter.py:611
-syntax error, adversarial.py:101-102 attribute typo).  This restates the *intended* graph.
+PARITY STATUS (see oracle/tf14_numpy.py and DESIGN.md section 2): TF-1.4 cannot run in this image and the reference's own
+modules do not run as they are (source_segmenter.py:611 syntax error, adversarial.py:102 attribute typo), so the op
+NUMERICS here are an unpinned restatement.  The loss arithmetic (dis_losses / gen_losses) is pinned to the reference's
+adversarial.py:445-476 executed numerically (tests/test_reference_graph_trace.py); the architecture, variable tables,
+optimizer wiring and step feeds of the reference -- obtained by executing its graph code under a recording tensorflow
+shim -- are pinned on the PRODUCT side, and the GPU model-level parity tests tie the product to this oracle.
 
 Variables are keyed by the TF variable names the reference would create (the checkpoint naming
 contract of lists/half_zip_*_vars, lists/*_bn_list), so the same numpy dict initialises both this

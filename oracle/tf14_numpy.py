@@ -9,11 +9,11 @@ reference calls (call sites cited per function) and are pinned only by hand-deri
 tests (tests/test_oracle_kat.py) and by cross-checking against the independent torch-CPU form in
 oracle/tf14_torch.py.
 
-PINNED EXCEPTION (the parts of the reference that CAN run here): phase_shift_literal / PS_literal /
-PS_closed_form and label_decomp are checked bit-exactly against outputs of the reference's own
-ops.py:3-27 and lib.py:75-92 (executed under a six-op numpy shim of tensorflow; fixtures and the
-generating script in tests/golden/, test in tests/test_reference_golden.py).  Everything that is
-defined by TensorFlow kernels (conv, batch norm, losses, optimizers) remains unpinned.
+PINNED TO EXECUTED REFERENCE CODE (tests/golden/, generator scripts committed; tests/test_reference_golden.py,
+tests/test_reference_graph_trace.py): phase_shift_literal / PS_literal / PS_closed_form and label_decomp bit-exactly
+against the reference's own ops.py:3-27 and lib.py:75-92; softmax_weighted_loss and dice_loss against
+source_segmenter.py:241-273 evaluated numerically.  Everything that is defined by TensorFlow kernels (conv padding
+offsets, batch norm, dropout scaling, Adam / RMSProp) remains UNPINNED restatement.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
 this package.  The product path (medical-cross-modality-domain-adaptation_b200/) never does.

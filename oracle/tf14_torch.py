@@ -3,9 +3,10 @@ ORACLE (test infrastructure, NOT product code) -- torch-CPU restatement of the r
 layers.py / ops.py operator surface with TensorFlow-1.4 semantics, differentiable through torch
 autograd so that backward passes and optimizer steps can be checked too.
 
-PARITY UNPINNED (see oracle/tf14_numpy.py header): no reference tests / golden vectors exist and
-TF-1.4 cannot run here; this form is cross-checked against the naive numpy form and hand-derived
-known-answer tests only.
+PARITY UNPINNED for the TF-kernel numerics (see oracle/tf14_numpy.py header): no reference tests / golden vectors exist
+and TF-1.4 cannot run here; this form is cross-checked against the naive numpy form and hand-derived known-answer
+tests.  PS, softmax_weighted_loss and dice_loss ARE pinned to the reference's own code executed in this container
+(tests/test_reference_golden.py, tests/test_reference_graph_trace.py).
 
 Tensors are NHWC at the interface (like the reference) and permuted to NCHW internally for
 torch.nn.functional.conv2d.  Weights are HWIO.  dtype follows the inputs (fp32 for timing /
