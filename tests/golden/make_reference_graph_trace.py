@@ -628,6 +628,8 @@ def main():
     trace["var_groups"], trace["optimizer"], trace["cost_numeric"] = trace_training_wiring(tf, adv, net, trace["weight_lists"])
     trace["schedule"] = trace_training_schedule(tf, adv, net)
     trace["source_segmenter"] = trace_source_segmenter(tf)
+    G_adv_order = [v["name"] for v in trace["variables"]]
+    trace["transplant"] = trace_transplant(tf, adv, net, G_adv_order, [v["name"] for v in trace["source_segmenter"]["variables"]])
     with open(OUT, "w") as f:
         json.dump(trace, f, indent=0, sort_keys=True)
     print("wrote %s: %d + %d events, %d + %d variables" % (OUT, len(trace["events"]), len(trace["source_segmenter"]["events"]),
@@ -859,6 +861,62 @@ def trace_training_schedule(tf, adv, net):
         if saved[2] is not None:
             tf.assign = saved[2]
     return {"train_config": cfg_in, "train_args": {"training_iters": 5, "epochs": 1, "dropout": 0.75}, "events": log}
+
+
+def trace_transplant(tf, adv, net, adv_names, baseline_names):
+    """adversarial.py:503-531 (restore, no_gan), :706-741 (_adapt_copy_weights, both modes), :743-765 (_load_batch_norm_weights)
+    executed on the variable-name lists the reference ships under lists/ and on the traced variable tables"""
+    def read(fn):
+        with open(os.path.join(REF, "lists", fn)) as f:
+            return [ln.split("\n")[0] for ln in f.readlines() if len(ln) >= 3]        # lib._read_lists, lib.py:7-20
+    strip = lambda n: n.split(":")[0]
+    pairs = []
+    graph = types.SimpleNamespace(get_tensor_by_name=lambda n: ("tensor", n))
+    tf.get_default_graph = lambda: graph
+    saved_assign = getattr(tf, "assign", None)
+    tf.assign = lambda dst, src: types.SimpleNamespace(eval=lambda: pairs.append((dst, src)))
+    out = {}
+    me = types.SimpleNamespace(mr_var_list=read("half_zip_mri_vars"), adapt_var_list=read("half_zip_ct_vars"),
+                               old_bn_list=read("old_bn_list"), new_bn_list=read("pred_bn_list"))
+    adv.Trainer._adapt_copy_weights(me, internal=False)
+    out["adapt_copy"] = [[strip(d[1]), strip(s_[1])] for d, s_ in pairs]
+    # internal = True: correspondence by creation order of the 'group*' and 'adapt*' variables
+    del pairs[:]
+    tf.contrib.framework.get_variables = lambda: [_VarObj({"name": n}) for n in adv_names]
+    me2 = types.SimpleNamespace()
+    try:
+        adv.Trainer._adapt_copy_weights(me2, internal=True)
+        out["adapt_copy_internal"] = [[strip(d.name), strip(s_.name)] for d, s_ in pairs]
+    except ValueError as e:
+        out["adapt_copy_internal_error"] = str(e)          # 'group' matches group_1..10: 153 names vs 101 adapt names
+    del pairs[:]
+    tf.train.get_checkpoint_state = lambda path: None
+    tf.contrib.framework.load_variable = lambda path, name: ("ckpt", name)
+    adv.Trainer._load_batch_norm_weights(me, "./ckpt")
+    out["bn_copy"] = [[s_[1], strip(d[1])] for d, s_ in pairs]          # [old name in the baseline checkpoint, new variable]
+    out["bn_copy_dict_len"] = len(me.copy_bn_dict)
+    # restore(no_gan=True) from a baseline-segmenter checkpoint (its variables + Adam slots)
+    ckpt = {n: None for n in baseline_names}
+    ckpt.update({n + "/Adam": None for n in baseline_names if n.endswith("Variable") or "Variable_" in n})
+    ckpt["beta1_power"] = None
+    restored = []
+
+    class Saver(object):
+        def __init__(self, var_list=None):
+            self.var_list = var_list
+
+        def restore(self, sess, path):
+            restored.append([strip(v.name) for v in self.var_list])
+    tf.train.Saver = Saver
+    tf.get_collection_ref = lambda name: []
+    tf.global_variables = lambda: [_VarObj({"name": n}) for n in adv_names]
+    tf.pywrap_tensorflow = types.SimpleNamespace(NewCheckpointReader=lambda path: types.SimpleNamespace(get_variable_to_shape_map=lambda: ckpt))
+    rc = adv.Full_DRN.restore(net, "sess", "./ckpt/model", no_gan=True)
+    assert rc == 0 and len(restored) == 1
+    out["restore_no_gan"] = {"checkpoint_names": sorted(ckpt), "restored": restored[0]}
+    if saved_assign is not None:
+        tf.assign = saved_assign
+    return out
 
 
 def trace_source_segmenter(tf):

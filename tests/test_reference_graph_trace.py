@@ -456,3 +456,53 @@ def test_training_schedule_and_step_feeds_match_the_reference(tmp_path):
     assert d_calls == [{"stream": "mr", "keep_prob": 0.75, "front_bn": d_feeds[0]["mr_front_bn"], "joint_bn": d_feeds[0]["joint_bn"]},
                        {"stream": "ct", "keep_prob": 0.75, "front_bn": d_feeds[0]["ct_front_bn"], "joint_bn": d_feeds[0]["joint_bn"]}]
     assert g_calls == [{"stream": "ct", "keep_prob": 0.75, "front_bn": g_feeds[0]["ct_front_bn"], "joint_bn": g_feeds[0]["joint_bn"]}]
+
+
+# ------------------------------------------------------------------------------------------------
+# checkpoint transplant chain (adversarial.py:503-531, 706-765 executed on the reference's lists/ and the traced tables)
+# ------------------------------------------------------------------------------------------------
+def test_transplant_chain_matches_the_reference(tmp_path):
+    import numpy as np
+    from pnp_b200 import adversarial as A, runtime as rt
+    tp = REF["transplant"]
+    strip = lambda n: n.split(":")[0]
+    net = A.Full_DRN(3, 5, B, cost_kwargs=dict(COST), network_config=dict(CFG))
+    V = rt.graph.vars
+
+    # ---- _adapt_copy_weights: CT DAM <- MR front, 101 (destination, source) pairs from lists/half_zip_*_vars
+    assert len(tp["adapt_copy"]) == 101 and "adapt_copy_internal_error" in tp          # the `internal` mode cannot work: 153 vs 101
+    with torch.no_grad():
+        for i, name in enumerate(rt.graph.order):
+            V[name].fill_(float(i + 1))
+    before = {n: float(V[n].detach().flatten()[0]) for n in rt.graph.order}
+    net.adapt_copy_weights()
+    changed = {n for n in rt.graph.order if float(V[n].detach().flatten()[0]) != before[n]}
+    assert changed == {d for d, _ in tp["adapt_copy"]}
+    for dst, src in tp["adapt_copy"]:
+        assert torch.all(V[dst] == before[src]), (dst, src)
+
+    # ---- _load_batch_norm_weights: baseline 'BatchNorm_k/*' -> 'group_g/pred_*' (lists/old_bn_list -> lists/pred_bn_list)
+    assert len(tp["bn_copy"]) == 120 == tp["bn_copy_dict_len"]
+    base = {}
+    for k, (old, new) in enumerate(tp["bn_copy"]):
+        base[strip(old)] = np.full(tuple(V[new].shape), 1000.0 + k, np.float32)
+    np.savez(str(tmp_path / "baseline.npz"), **base)
+    before = {n: float(V[n].detach().flatten()[0]) for n in rt.graph.order}
+    net.load_batch_norm_weights(str(tmp_path / "baseline.npz"))
+    changed = {n for n in rt.graph.order if float(V[n].detach().flatten()[0]) != before[n]}
+    assert changed == {new for _, new in tp["bn_copy"]}
+    for k, (old, new) in enumerate(tp["bn_copy"]):
+        assert torch.all(V[new] == 1000.0 + k), (old, new)
+
+    # ---- restore(no_gan=True) from a baseline-segmenter checkpoint: the 33 'group*' / 'output' filters, no batch norm, no slots
+    rs = tp["restore_no_gan"]
+    shapes = {v["name"]: v["shape"] for v in REF["source_segmenter"]["variables"]}
+    ck = {}
+    for k, n in enumerate(rs["checkpoint_names"]):
+        base_name = n[:-5] if n.endswith("/Adam") else n
+        ck[n] = np.full(tuple(shapes.get(base_name, [1])), 5000.0 + k, np.float32)
+    np.savez(str(tmp_path / "seg.npz"), **ck)
+    before = {n: float(V[n].detach().flatten()[0]) for n in rt.graph.order}
+    net.restore(str(tmp_path / "seg.npz"), no_gan=True)
+    changed = {n for n in rt.graph.order if float(V[n].detach().flatten()[0]) != before[n]}
+    assert changed == set(rs["restored"]) and len(changed) == 33
