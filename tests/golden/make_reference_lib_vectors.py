@@ -49,6 +49,15 @@ def _make_tf_shim():
     tf.concat = lambda values, axis: _t(np.concatenate([np.asarray(v) for v in values], axis=axis))
     tf.squeeze = lambda x: _t(np.squeeze(np.asarray(x)))
     tf.expand_dims = lambda x, axis: _t(np.expand_dims(np.asarray(x), axis))
+    # arithmetic helpers for layers.pixel_wise_softmax_2 (layers.py:134-138) and lib._dice_eval (lib.py:96-110)
+    tf.exp = lambda x: np.exp(np.asarray(x))
+    tf.reduce_sum = lambda x, axis=None, keep_dims=False: np.sum(np.asarray(x), axis=axis, keepdims=keep_dims)
+    tf.shape = lambda x: np.asarray(x).shape
+    tf.stack = lambda vals: [int(v) for v in vals]
+    tf.tile = lambda x, multiples: np.tile(np.asarray(x), [int(m) for m in multiples])
+    tf.div = lambda a, b, name=None: np.asarray(a) / np.asarray(b)
+    tf.clip_by_value = lambda x, lo, hi, name=None: np.clip(x, lo, hi)
+    tf.one_hot = lambda idx, depth, axis=-1: np.eye(depth)[np.asarray(idx)]
     return tf
 
 
@@ -64,6 +73,7 @@ def main():
     sys.modules["nibabel"] = types.ModuleType("nibabel")
     ops = _load("ops")
     lib = _load("lib")
+    layers = _load("layers")
     rng = np.random.RandomState(20260924)
     out = {}
 
@@ -100,6 +110,20 @@ def main():
     out["cm"] = cms
     out["cm_dice"] = np.stack([lib._dice(c) for c in cms])
     out["cm_jaccard"] = np.stack([lib._jaccard(c) for c in cms])
+
+    # ---- layers.pixel_wise_softmax_2: exp / sum WITHOUT max subtraction, clipped to +-1e15 (float64 here)
+    sm_x = 3.0 * rng.standard_normal((2, 5, 4, 5))
+    sm_x[0, 0, 0] = [700.0, 0.0, -700.0, 1.0, 2.0]          # large but finite in float64
+    out["sm_x"] = sm_x
+    out["sm_y"] = np.asarray(layers.pixel_wise_softmax_2(sm_x), dtype=np.float64)
+
+    # ---- lib._dice_eval on an argmax prediction and one-hot labels
+    de_pred = rng.randint(0, 5, size=(2, 6, 5))
+    de_lab = rng.randint(0, 5, size=(2, 6, 5))
+    de_lab[1] = 2                                             # classes absent from the labels of a slice
+    mean, arr = lib._dice_eval(de_pred, np.eye(5)[de_lab], 5)
+    out["de_pred"], out["de_lab"] = de_pred, de_lab
+    out["de_mean"], out["de_arr"] = np.float64(mean), np.asarray(arr, dtype=np.float64)
 
     np.savez_compressed(OUT, **out)
     print("wrote %s (%d arrays, %.1f KB)" % (OUT, len(out), os.path.getsize(OUT) / 1e3))

@@ -71,3 +71,25 @@ def test_oracle_dice_eval_consistent_with_reference_confusion_dice():
     mean, arr = N.dice_eval(pred, N.label_decomp(5, lab).astype(np.float64), 5)
     np.testing.assert_allclose(np.array(arr), P._dice(cm), rtol=1e-7)      # (the 1e-7 epsilon of lib.py:100)
     np.testing.assert_allclose(mean, P._dice(cm).mean(), rtol=1e-7)
+
+
+def test_oracle_pixel_softmax_equals_the_reference_code():
+    """layers.py:134-138 executed numerically: no max subtraction, clip to +-1e15"""
+    from oracle import tf14_numpy as N, tf14_torch as T
+    x, want = GOLD["sm_x"], GOLD["sm_y"]
+    assert np.isfinite(want).all() and want[0, 0, 0, 0] == pytest.approx(1.0) and want[0, 0, 0, 2] == 0.0
+    np.testing.assert_allclose(N.pixel_wise_softmax_2(x), want, rtol=1e-14, atol=0)
+    np.testing.assert_allclose(T.pixel_wise_softmax_2(torch.from_numpy(x)).numpy(), want, rtol=1e-13, atol=0)
+
+
+def test_oracle_dice_eval_equals_the_reference_code():
+    """lib.py:96-110 executed numerically (tf.one_hot of the prediction, per-class 2*inse/(union+1e-7), mean over classes)"""
+    from oracle import tf14_numpy as N, tf14_torch as T
+    pred, lab = GOLD["de_pred"], GOLD["de_lab"]
+    y = np.eye(5)[lab]
+    mean, arr = N.dice_eval(pred, y, 5)
+    np.testing.assert_allclose(np.array(arr), GOLD["de_arr"], rtol=1e-14)
+    assert mean == pytest.approx(float(GOLD["de_mean"]), rel=1e-14)
+    mt, at = T.dice_eval(torch.from_numpy(pred), torch.from_numpy(y), 5)
+    np.testing.assert_allclose(np.array([float(a) for a in at]), GOLD["de_arr"], rtol=1e-12)
+    assert float(mt) == pytest.approx(float(GOLD["de_mean"]), rel=1e-12)
