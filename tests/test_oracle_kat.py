@@ -210,3 +210,25 @@ def test_oracle_layouts_match_reference_variable_lists():
     seg_names = set(n + "/" + l for n, _ in bns for l in ("beta", "gamma", "moving_mean", "moving_variance"))
     assert sorted(seg_names) == sorted(gold["old_bn_list"])
     assert sum(int(np.prod(s)) for _, s in ws) == 39302456       # SURVEY Appendix A.2 total
+
+
+def test_same_padding_agrees_with_an_independent_port_of_tensorflows_rule():
+    """The SAME-padding offsets are defined by TensorFlow's kernels, which cannot run here.  Independent evidence: the
+    `transformers` package in this image carries its own port of TF's rule for the MobileNet checkpoints
+    (`apply_tf_padding`, citing tensorflow.org 'notes on padding').  The oracle's same_pad -- and the product's host copy --
+    must place the same zeros for every (size, kernel, stride) the graphs use and a sweep around them (dilation 1)."""
+    import torch
+    tr = pytest.importorskip("transformers.models.mobilenet_v1.modeling_mobilenet_v1")
+    from oracle import tf14_numpy as N
+    from pnp_b200 import functional as F
+    for n in list(range(1, 40)) + [64, 128, 255, 256, 257]:
+        for k in (1, 3, 5, 7):
+            for s in (1, 2, 3, 4):
+                conv = torch.nn.Conv2d(1, 1, k, stride=s)
+                x = torch.ones(1, 1, n, n)
+                y = tr.apply_tf_padding(x, conv)
+                total = y.shape[-1] - n
+                before = int((y[0, 0].sum(0) > 0).float().argmax())                    # zero columns placed before the data
+                assert N.same_pad(n, k, s) == (before, total - before), (n, k, s)
+                assert tuple(F.same_pad(n, k, s)) == (before, total - before), (n, k, s)
+                assert y.shape[-1] >= k and (y.shape[-1] - k) // s + 1 == -(-n // s)            # SAME output size ceil(n / s)
