@@ -177,6 +177,15 @@ class Trainer(object):
         self.global_step += 1
         return wce, dice
 
+    def output_minibatch_stats(self, batch_x, batch_y):
+        """source_segmenter.py:525-539: the tensorboard pass on the training batch feeds x, y and keep_prob 1 ONLY -- both BN
+        switches stay at their placeholder default True, so this forward runs batch-statistics BN and (updates_collections=None)
+        moves the moving averages once more.  Reproduced because it changes the trained model's moving statistics."""
+        with torch.no_grad():
+            logits = self.net.forward(batch_x, keep_prob=1.0, main_bn=True, adapt_bn=True)
+            wce, dice = self.net.losses(logits, batch_y)
+        return self.net.cost_value(wce, dice)
+
     def feed(self, images, raw_labels):
         """host batch -> device tensors (the feed_dict copy) + on-device one-hot (lib._label_decomp)"""
         dev = rt.device()
@@ -210,7 +219,7 @@ class Trainer(object):
                 x, y = self.feed(images, raw_y)
                 wce, dice = self.train_step(x, y, dropout)
                 if step % display_step == 0:
-                    loss = self.net.cost_value(wce, dice)
+                    loss = self.output_minibatch_stats(x, y)
                     logging.info("Training at step %s epoch %s , loss is %0.4f" % (step, epoch, loss))
                     logging.info("Time elapsed %s seconds" % (time.time() - start))
                 if step % self.checkpoint_space == 0 and step > 10000:

@@ -919,6 +919,114 @@ def trace_transplant(tf, adv, net, adv_names, baseline_names):
     return out
 
 
+def trace_segmenter_schedule(tf, mod, net):
+    """source_segmenter.Trainer (__init__, _get_optimizer, _initialize, train, output_minibatch_stats, val_stats:
+    source_segmenter.py:312-570) executed verbatim against a recording Session; only next_batch (TFRecord queue) is replaced."""
+    log = []
+    names = {id(net.x): "x", id(net.y): "y", id(net.main_bn): "main_bn", id(net.adapt_bn): "adapt_bn", id(net.keep_prob): "keep_prob"}
+
+    class _Feed(object):
+        def __init__(self, kind):
+            self.kind = kind
+
+        def value(self):
+            return np.zeros((BATCH, 256, 256, 4), np.float32) if self.kind == "data" else [b"file:0"] * BATCH
+
+        def eval(self):
+            return self.value()
+
+    class Session(object):
+        graph = "graph"
+
+        def __init__(self, config=None):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def run(self, fetches, feed_dict=None):
+            feeds = {names[id(k)]: ("batch" if isinstance(v, np.ndarray) else v) for k, v in (feed_dict or {}).items()}
+            fl = list(fetches) if isinstance(fetches, (list, tuple)) else [fetches]
+            if fl and fl[0] == "adam_op":
+                log.append({"op": "optimizer", "feeds": feeds})
+                return None, 0.0, me.learning_rate_node
+            if "scalar_summary" in fl and "train_images" in fl:
+                log.append({"op": "minibatch_stats", "feeds": feeds})
+            elif "scalar_summary" in fl and "val_images" in fl:
+                log.append({"op": "val_stats", "feeds": feeds, "detail": len(fl) == 5})
+            elif fl and isinstance(fl[0], tuple) and fl[0] and fl[0][0] == "assign_lr":
+                log.append({"op": "assign_lr", "value": fl[0][1]})
+                return None
+            out = []
+            for f in fl:
+                if isinstance(f, _Feed):
+                    out.append(f.value())
+                elif isinstance(f, Sym) and f.src == "cm":
+                    out.append(np.zeros((5, 5)))
+                else:
+                    out.append(0.0)
+            return out if isinstance(fetches, (list, tuple)) else out[0]
+    tf.Session = Session
+    tf.ConfigProto = lambda: types.SimpleNamespace(gpu_options=types.SimpleNamespace(allow_growth=False))
+    merged = {"n": 0}
+
+    def merge(lst):
+        merged["n"] += 1
+        return {1: "scalar_summary", 2: "train_images", 3: "val_images"}[merged["n"]]
+    writer = lambda *a, **k: types.SimpleNamespace(add_summary=lambda s_, step: None, flush=lambda: None)
+    tf.summary = types.SimpleNamespace(scalar=lambda n, v: ("s", n), image=lambda n, v: ("i", n), merge=merge, FileWriter=writer)
+    opt_log = []
+
+    class AdamOptimizer(object):
+        def __init__(self, learning_rate=None, **kw):
+            self.cfg = {"kind": "AdamOptimizer", "learning_rate": learning_rate, "kwargs": dict(kw)}
+
+        def minimize(self, loss, global_step=None, var_list=None):
+            rec = dict(self.cfg)
+            rec["objective_src"] = loss.src
+            rec["var_list"] = None if var_list is None else len(var_list)
+            opt_log.append(rec)
+            return "adam_op"
+    train = types.ModuleType("tensorflow.train")
+    train.AdamOptimizer = AdamOptimizer
+    train.string_input_producer = lambda lst, num_epochs=None, shuffle=True: "queue"
+    train.Coordinator = lambda: types.SimpleNamespace(request_stop=lambda: None, join=lambda threads: None)
+    train.get_checkpoint_state = lambda path: None
+    train.start_queue_runners = lambda sess=None, coord=None, start=True: []
+    tf.train = train
+    saved_var = tf.Variable
+    class _Scalar(float):
+        def eval(self):
+            return float(self)
+    tf.Variable = lambda initial, trainable=True, name=None: (saved_var(initial, trainable, name) if isinstance(initial, _Init)
+                                                               else (_Scalar(initial) if np.isscalar(initial) else "var"))
+    tf.assign = lambda var, val: ("assign_lr", float(val))
+    tf.global_variables_initializer = lambda: "init_glb"
+    tf.variables_initializer = lambda v: "init_loc"
+    tf.local_variables = lambda: []
+    tf.trainable_variables = lambda: [_VarObj(G.vars[n]) for n in G.order if G.vars[n]["trainable"]]
+    net.cost.src, net.regularizer_loss.src = "cost", "regularizer_loss"
+
+    class Me(mod.Trainer):
+        def next_batch(self, input_queue, **k):                 # source_segmenter.py:331-355: TFRecord queue plumbing
+            return _Feed("data"), _Feed("fid")
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="pnp_segsched_")
+    os.chdir(tmp)
+    try:
+        # the arguments train_segmenter.py:60-75 passes, with a short loop
+        me = Me(net, train_list=["a"], val_list=["b"], num_cls=5, batch_size=BATCH, opt_kwargs={"learning_rate": 1e-3},
+                checkpoint_space=1500, optimizer="adam", lr_update_flag=False)
+        me.train(output_path="./out", training_iters=7, epochs=1, restore=True, restored_path="./out")
+    finally:
+        os.chdir(cwd)
+        tf.Variable = saved_var
+    return {"optimizer": opt_log, "events": log, "train_args": {"training_iters": 7, "epochs": 1, "display_step_default": 5, "dropout_default": 0.75}}
+
+
 def trace_source_segmenter(tf):
     """source_segmenter.py does not parse (SyntaxError at :611, inside Trainer.test_eval).  Everything before `class Trainer`
     (line 303) -- the module preamble and class Full_DRN in full -- is compiled and executed verbatim."""
@@ -933,7 +1041,8 @@ def trace_source_segmenter(tf):
         syntax_error = {"line": e.lineno, "msg": e.msg}
     lines = src.split("\n")
     cut = next(i for i, ln in enumerate(lines) if ln.startswith("class Trainer"))
-    head = "\n".join(lines[:cut]) + "\n"
+    cut2 = next(i for i, ln in enumerate(lines) if ln.strip().startswith("def test_eval"))     # the method holding the syntax error
+    head = "\n".join(lines[:cut2]) + "\n"            # module preamble, class Full_DRN, class Trainer up to (not incl.) test_eval
     REC = Recorder()
     Sym._n = 0
     G.reset()
@@ -965,8 +1074,9 @@ def trace_source_segmenter(tf):
         wce = float(mod.Full_DRN._softmax_weighted_loss(me, logits))
         dice = float(mod.Full_DRN._dice_loss_fun(me, logits))
     losses = {"logits": logits.tolist(), "labels": lab.tolist(), "weighted_loss": wce, "dice_loss": dice}
-    return {"syntax_error": syntax_error, "executed_lines": cut, "events": REC.events, "variables": [G.vars[n] for n in G.order],
-            "losses_numeric": losses,
+    schedule = trace_segmenter_schedule(tf, mod, net)
+    return {"syntax_error": syntax_error, "executed_lines": cut, "executed_lines_trainer": cut2, "events": REC.events,
+            "variables": [G.vars[n] for n in G.order], "losses_numeric": losses, "schedule": schedule,
             "conv_weights": [s.var["name"] for s in net.conv_weights],
             "ctor_args": {"main_trainable": False, "adapt_trainable": True}}
 

@@ -506,3 +506,73 @@ def test_transplant_chain_matches_the_reference(tmp_path):
     net.restore(str(tmp_path / "seg.npz"), no_gan=True)
     changed = {n for n in rt.graph.order if float(V[n].detach().flatten()[0]) != before[n]}
     assert changed == set(rs["restored"]) and len(changed) == 33
+
+
+# ------------------------------------------------------------------------------------------------
+# source segmenter training (source_segmenter.py:312-570, class Trainer up to test_eval executed verbatim)
+# ------------------------------------------------------------------------------------------------
+def test_segmenter_training_schedule_feeds_and_adam_match_the_reference(tmp_path):
+    from pnp_b200 import source_segmenter as S, optim, runtime as rt, _C
+    ref = REF["source_segmenter"]
+    sched = ref["schedule"]
+    assert ref["executed_lines_trainer"] == 571                       # everything before `def test_eval` (syntax error at :611)
+    # ---- Adam on cost + regularizer_loss over every trainable variable
+    (adam,) = sched["optimizer"]
+    assert adam == {"kind": "AdamOptimizer", "learning_rate": 1e-3, "kwargs": {}, "objective_src": "add(cost,regularizer_loss)", "var_list": None}
+    net = S.Full_DRN(3, 5, B, cost_kwargs={"cross_flag": True, "miu_cross": 1.0, "dice_flag": True, "miu_dice": 1.0, "regularizer": 1e-4})
+    tr = S.Trainer(net, train_list=[], val_list=[], num_cls=5, batch_size=B, opt_kwargs={"learning_rate": 1e-3}, checkpoint_space=1500,
+                   optimizer="adam", lr_update_flag=False)
+    names = {id(v): k for k, v in rt.graph.vars.items()}
+    trainable = [v["name"] for v in ref["variables"] if v["kind"] != "batch_norm" or v["name"].endswith(("beta", "gamma"))]
+    assert sorted(names[id(v)] for v in tr.trainables) == sorted(trainable)          # defaults: main/adapt trainable True
+    assert tr.optimizer.get_lr() == pytest.approx(1e-3) and (tr.optimizer.b1, tr.optimizer.b2, tr.optimizer.eps) == (0.9, 0.999, 1e-8)
+    # d(reg_coeff * sum l2_loss(conv_weights))/dw = reg_coeff * multiplicity * w   (wr4_4 twice, wr4_3 never)
+    wd = dict(zip((names[id(v)] for v in tr.trainables), net.weight_decay_table(tr.trainables)))
+    for n, c in wd.items():
+        assert c == pytest.approx(1e-4 * ref["conv_weights"].count(n)), n
+    assert wd["group_4/Variable_3"] == pytest.approx(2e-4) and wd["group_4/Variable_2"] == 0.0
+
+    # ---- per-step feeds
+    evs = sched["events"]
+    train_feeds = [e["feeds"] for e in evs if e["op"] == "optimizer"]
+    stats_feeds = [e["feeds"] for e in evs if e["op"] == "minibatch_stats"]
+    val_feeds = [e["feeds"] for e in evs if e["op"] == "val_stats"]
+    assert all(f == {"x": "batch", "y": "batch", "main_bn": True, "adapt_bn": True, "keep_prob": 0.75} for f in train_feeds)
+    assert all(f == {"x": "batch", "y": "batch", "keep_prob": 1.0} for f in stats_feeds)       # BN switches at their default: True
+    assert all(f == {"x": "batch", "y": "batch", "main_bn": False, "adapt_bn": False, "keep_prob": 1.0} for f in val_feeds)
+
+    # ---- schedule: one Adam step per iteration, the stats pass (and validation) every display_step = 5 iterations, after it
+    ref_ops = [e["op"] for e in evs if e["op"] != "val_stats"]          # (no validation source in the product's loop)
+    assert ref_ops == ["optimizer", "minibatch_stats"] + ["optimizer"] * 5 + ["minibatch_stats", "optimizer"]
+    got = []
+    tr.train_step = lambda x, y, keep_prob=0.75: got.append(("optimizer", keep_prob)) or (0.0, 0.0)
+    tr.output_minibatch_stats = lambda x, y: got.append(("minibatch_stats", None)) or 0.0
+    tr.feed = lambda images, raw: (images, raw)
+    tr.train(output_path=str(tmp_path), training_iters=7, epochs=1, restore=True, restored_path=str(tmp_path))
+    assert [g[0] for g in got] == ref_ops and all(g[1] == 0.75 for g in got if g[0] == "optimizer")
+
+    # ---- the BN switches the product's three passes use
+    calls = []
+
+    class _Stop(Exception):
+        pass
+
+    def forward(x, keep_prob=1.0, main_bn=True, adapt_bn=True, return_taps=False):
+        calls.append({"keep_prob": keep_prob, "main_bn": main_bn, "adapt_bn": adapt_bn})
+        raise _Stop()
+    tr2 = S.Trainer(S.Full_DRN(3, 5, B, cost_kwargs={"cross_flag": True, "miu_cross": 1.0, "dice_flag": True, "miu_dice": 1.0}),
+                    train_list=[], val_list=[], num_cls=5, batch_size=B, opt_kwargs={"learning_rate": 1e-3}, optimizer="adam")
+    tr2.net.forward = forward
+    saved = (optim.call, _C.call, rt.stream)
+    optim.call = _C.call = lambda *a, **k: None
+    rt.stream = lambda: None
+    x = torch.empty(B, 256, 256, 3, device="meta")
+    try:
+        for fn in (lambda: tr2.train_step(x, x, 0.75), lambda: tr2.output_minibatch_stats(x, x), lambda: tr2.val_stats(x, x)):
+            with pytest.raises(_Stop):
+                fn()
+    finally:
+        optim.call, _C.call, rt.stream = saved
+    assert calls == [{"keep_prob": 0.75, "main_bn": True, "adapt_bn": True},
+                     {"keep_prob": 1.0, "main_bn": True, "adapt_bn": True},
+                     {"keep_prob": 1.0, "main_bn": False, "adapt_bn": False}]
