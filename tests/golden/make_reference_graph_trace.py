@@ -627,6 +627,7 @@ def main():
                               ("mr_front_weights", "ct_front_weights", "cls_weights", "m_cls_weights", "joint_weights")}}
     trace["var_groups"], trace["optimizer"], trace["cost_numeric"] = trace_training_wiring(tf, adv, net, trace["weight_lists"])
     trace["schedule"] = trace_training_schedule(tf, adv, net)
+    trace["input_pipeline"] = trace_input_pipeline(tf, adv)
     trace["source_segmenter"] = trace_source_segmenter(tf)
     G_adv_order = [v["name"] for v in trace["variables"]]
     trace["transplant"] = trace_transplant(tf, adv, net, G_adv_order, [v["name"] for v in trace["source_segmenter"]["variables"]])
@@ -861,6 +862,50 @@ def trace_training_schedule(tf, adv, net):
         if saved[2] is not None:
             tf.assign = saved[2]
     return {"train_config": cfg_in, "train_args": {"training_iters": 5, "epochs": 1, "dropout": 0.75}, "events": log}
+
+
+def pipeline_example():
+    """the synthetic single-slice example both sides decode (tests rebuild it from this formula)"""
+    i, j, c = np.meshgrid(np.arange(256), np.arange(256), np.arange(3), indexing="ij")
+    data = (1000.0 * c + (i * 256 + j) % 997).astype(np.float32)
+    label = ((i * 3 + j * 5 + c * 2) % 5).astype(np.float32)
+    return data, label
+
+
+def trace_input_pipeline(tf, adv):
+    """Trainer.next_batch (adversarial.py:607-631) evaluated numerically on one parsed example: which bytes become the image
+    and which channel of the stored label volume becomes the label map"""
+    data, label = pipeline_example()
+    feats = {"dsize_dim0": 256, "dsize_dim1": 256, "dsize_dim2": 3, "lsize_dim0": 256, "lsize_dim1": 256, "lsize_dim2": 3,
+             "data_vol": data.tobytes(), "label_vol": label.tobytes()}
+    seen = {}
+
+    def parse_single_example(serialized, features):
+        seen["feature_keys"] = sorted(features)
+        return feats
+    saved = {k: getattr(tf, k, None) for k in ("reshape", "slice", "concat", "cast")}
+    tf.TFRecordReader = lambda: types.SimpleNamespace(read=lambda q: ("fid", "serialized"))
+    tf.parse_single_example = parse_single_example
+    tf.cast = lambda x, dtype: x
+    tf.decode_raw = lambda b, dtype: np.frombuffer(b, dtype="<f4" if dtype == tf.float32 else None)
+    tf.reshape = lambda x, shape: np.reshape(x, shape)
+    tf.slice = lambda x, begin, size: x[tuple(slice(b, b + s_) for b, s_ in zip(begin, size))]
+    tf.concat = lambda vals, axis, name=None: np.concatenate(vals, axis=axis)
+
+    def shuffle_batch(tensors, batch_size, capacity, num_threads, min_after_dequeue):
+        seen["shuffle_batch"] = {"batch_size": batch_size, "capacity": capacity, "num_threads": num_threads, "min_after_dequeue": min_after_dequeue}
+        return [np.stack([t] * batch_size) if isinstance(t, np.ndarray) else [t] * batch_size for t in tensors]
+    tf.train.shuffle_batch = shuffle_batch
+    me = types.SimpleNamespace(batch_size=BATCH)
+    pair, fid = adv.Trainer.next_batch(me, "queue")
+    for k, v in saved.items():
+        if v is not None:
+            setattr(tf, k, v)
+    assert pair.shape == (BATCH, 256, 256, 4)
+    return {"feature_keys": seen["feature_keys"], "shuffle_batch": seen["shuffle_batch"], "pair_shape": list(pair.shape),
+            "sample_rows": [0, 37, 128, 255], "sample_cols": [0, 41, 200, 255],
+            "samples": pair[0][np.ix_([0, 37, 128, 255], [0, 41, 200, 255])].tolist(),
+            "channel_sums": [float(pair[0, :, :, c].astype(np.float64).sum()) for c in range(4)]}
 
 
 def trace_transplant(tf, adv, net, adv_names, baseline_names):

@@ -576,3 +576,28 @@ def test_segmenter_training_schedule_feeds_and_adam_match_the_reference(tmp_path
     assert calls == [{"keep_prob": 0.75, "main_bn": True, "adapt_bn": True},
                      {"keep_prob": 1.0, "main_bn": True, "adapt_bn": True},
                      {"keep_prob": 1.0, "main_bn": False, "adapt_bn": False}]
+
+
+# ------------------------------------------------------------------------------------------------
+# input pipeline (adversarial.py:607-631 evaluated numerically on one parsed example)
+# ------------------------------------------------------------------------------------------------
+def test_tfrecord_decoding_matches_the_reference_pipeline(tmp_path):
+    import numpy as np
+    from pnp_b200 import tfrecord as R
+    ip = REF["input_pipeline"]
+    assert ip["feature_keys"] == sorted(["dsize_dim0", "dsize_dim1", "dsize_dim2", "lsize_dim0", "lsize_dim1", "lsize_dim2", "data_vol", "label_vol"])
+    assert ip["pair_shape"] == [B, 256, 256, 4] and ip["shuffle_batch"]["batch_size"] == B
+    # the same synthetic example (formula of make_reference_graph_trace.pipeline_example)
+    i, j, c = np.meshgrid(np.arange(256), np.arange(256), np.arange(3), indexing="ij")
+    data = (1000.0 * c + (i * 256 + j) % 997).astype(np.float32)
+    label = ((i * 3 + j * 5 + c * 2) % 5).astype(np.float32)
+    path = str(tmp_path / "one.tfrecords")
+    R.write_record(path, [R.encode_example(data, label)])
+    src = R.TFRecordSource([path], 1, seed=0)
+    x, y = src.next()
+    pair = np.concatenate([x.numpy()[0], y.numpy()[0][..., None].astype(np.float32)], axis=2)      # [256,256,4] like pair_feed
+    rows, cols = ip["sample_rows"], ip["sample_cols"]
+    np.testing.assert_array_equal(pair[np.ix_(rows, cols)], np.array(ip["samples"], dtype=np.float32))
+    for ch in range(4):
+        assert float(pair[:, :, ch].astype(np.float64).sum()) == ip["channel_sums"][ch], ch
+    np.testing.assert_array_equal(y.numpy()[0], label[:, :, 1].astype(np.int64))                   # tf.slice(label_vol, [0,0,1], [256,256,1])
