@@ -12,7 +12,8 @@ modules do not run as they are (source_segmenter.py:611 syntax error, adversaria
 NUMERICS here are an unpinned restatement.  The loss arithmetic (dis_losses / gen_losses) is pinned to the reference's
 adversarial.py:445-476 executed numerically (tests/test_reference_graph_trace.py); the architecture, variable tables,
 optimizer wiring and step feeds of the reference -- obtained by executing its graph code under a recording tensorflow
-shim -- are pinned on the PRODUCT side, and the GPU model-level parity tests tie the product to this oracle.
+shim -- are pinned both on the PRODUCT side and for the graphs of this file (layer lists, variable layouts, L2 lists:
+test_oracle_graphs_match_the_reference_trace / test_oracle_segmenter_matches_the_reference_trace).
 
 Variables are keyed by the TF variable names the reference would create (the checkpoint naming
 contract of lists/half_zip_*_vars, lists/*_bn_list), so the same numpy dict initialises both this

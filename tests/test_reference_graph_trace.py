@@ -601,3 +601,172 @@ def test_tfrecord_decoding_matches_the_reference_pipeline(tmp_path):
     for ch in range(4):
         assert float(pair[:, :, ch].astype(np.float64).sum()) == ip["channel_sums"][ch], ch
     np.testing.assert_array_equal(y.numpy()[0], label[:, :, 1].astype(np.int64))                   # tf.slice(label_vol, [0,0,1], [256,256,1])
+
+
+# ------------------------------------------------------------------------------------------------
+# the ORACLE's graphs against the same reference trace (closes reference -> oracle on the CPU; the GPU tests close oracle -> kernels)
+# ------------------------------------------------------------------------------------------------
+class _OracleTracer(object):
+    """recording stand-ins for the primitives of oracle/tf14_torch.py; the composite layers above them run unmodified"""
+
+    def __init__(self, T, wname, bnname):
+        self.T, self.wname, self.bnname = T, wname, bnname
+        self.events, self.open, self.cur, self.pad = [], None, None, None
+        self.keep = []
+
+    def _new(self, shape):
+        y = torch.empty(*shape, device="meta")
+        self.keep.append(y)
+        return y
+
+    def close(self):
+        if self.open is not None:
+            self.events.append(self.open)
+            self.open = None
+
+    def conv2d_raw(self, x, w, stride=1, dilation=1, padding="SAME"):
+        self.close()
+        kh, kw, ci, co = w.shape
+        assert ci == x.shape[3]
+        if padding == "SYMMETRIC":
+            ho = (x.shape[1] + 2 * (kh // 2) - ((kh - 1) * dilation + 1)) // stride + 1
+            wo = (x.shape[2] + 2 * (kw // 2) - ((kw - 1) * dilation + 1)) // stride + 1
+        else:
+            assert padding == "SAME"
+            ho, wo = -(-x.shape[1] // stride), -(-x.shape[2] // stride)
+        y = self._new((x.shape[0], ho, wo, co))
+        self.open = {"op": "conv", "w": self.wname[id(w)], "wshape": list(w.shape), "stride": stride, "dil": dilation, "padding": padding,
+                     "in": list(x.shape[1:]), "out": [ho, wo, co], "keep": None, "bn": None, "bn_train": None, "skip": "none", "act": "none"}
+        self.cur, self.pad = id(y), None
+        return y
+
+    def dropout(self, x, keep_prob, mask=None):
+        assert self.open is not None and id(x) == self.cur and self.open["bn"] is None
+        self.open["keep"] = float(keep_prob)
+        y = self._new(x.shape)
+        self.cur = id(y)
+        return y
+
+    def batch_norm(self, x, bn, is_training):
+        assert self.open is not None and id(x) == self.cur
+        self.open["bn"], self.open["bn_train"] = self.bnname[id(bn)], bool(is_training)
+        y = self._new(x.shape)
+        self.cur = id(y)
+        return y
+
+    def channel_pad_skip(self, x):
+        self.pad = x.shape[-1] // 2
+        return self._new(tuple(x.shape[:3]) + (2 * x.shape[3],))
+
+    def act(self, x, leak):
+        assert self.open is not None
+        if id(x) != self.cur:                      # x is `xs + h`: the residual add of layers.py:164-166 / 186-189
+            self.open["skip"] = ("pad%d" % self.pad) if self.pad else "identity"
+        self.open["act"] = "lrelu0.2" if leak else "relu"
+        self.close()
+        y = self._new(x.shape)
+        self.pad = None
+        return y
+
+    def max_pool2d(self, x, n=2):
+        self.close()
+        self.events.append({"op": "maxpool", "k": n, "stride": n, "in": list(x.shape[1:]), "out": [x.shape[1] // n, x.shape[2] // n, x.shape[3]]})
+        return self._new((x.shape[0], x.shape[1] // n, x.shape[2] // n, x.shape[3]))
+
+    def PS(self, X, r, n_channel, batch_size):
+        self.close()
+        assert batch_size == B and X.shape[3] == r * r * n_channel
+        self.events.append({"op": "PS", "r": r, "n_channel": n_channel, "in": list(X.shape[1:]), "out": [X.shape[1] * r, X.shape[2] * r, n_channel]})
+        return self._new((X.shape[0], X.shape[1] * r, X.shape[2] * r, n_channel))
+
+
+def test_oracle_graphs_match_the_reference_trace():
+    from oracle import pnp_graphs as PG, tf14_torch as T
+    adv = PG.OracleAdversarial({}, B, critic_keep_prob=0.75)
+    wname, bnname = {}, {id(bn): k for k, bn in adv.ps.bn.items()}
+    for k in list(adv.ps.w):
+        t = torch.empty(adv.ps.w[k].shape, device="meta")
+        adv.ps.w[k] = t
+        wname[id(t)] = k
+    tr = _OracleTracer(T, wname, bnname)
+    names = ("conv2d_raw", "dropout", "batch_norm", "channel_pad_skip", "act", "max_pool2d", "PS")
+    saved = {k: getattr(T, k) for k in names}
+    for k in names:
+        setattr(T, k, getattr(tr, k))
+    try:
+        got = {}
+
+        def run(label, fn):
+            tr.events = []
+            r = fn()
+            tr.close()
+            got[label] = tr.events
+            return r
+        x = torch.empty(B, 256, 256, 3, device="meta")
+        run("mr", lambda: adv.segment(x, "mr", KEEP_PH, front_bn=True, joint_bn=False))
+        ct = run("ct", lambda: adv.segment(x, "ct", KEEP_PH, front_bn=False, joint_bn=True))
+        run("cls", lambda: adv.classifier(ct["c4_2"], ct["c6_2"], ct["b7"], ct["c9_2"], ct["logits"]))
+        run("mask", lambda: adv.mask_critic(ct["logits"]))
+    finally:
+        for k, v in saved.items():
+            setattr(T, k, v)
+
+    keys = ("w", "wshape", "stride", "dil", "padding", "in", "out", "keep", "bn", "bn_train", "act", "skip")
+
+    def compare(ref_list, got_list, bn_switch, what):
+        ref_list = [e for e in ref_list if e["op"] != "fc"]              # the oracle's matmul is a plain torch `@`
+        assert len(ref_list) == len(got_list), (what, len(ref_list), len(got_list))
+        for i, (r, g) in enumerate(zip(ref_list, got_list)):
+            r = _norm_ref(r, bn_switch)
+            assert r["op"] == g["op"], (what, i)
+            for k in (keys if r["op"] == "conv" else ("r", "n_channel", "in", "out") if r["op"] == "PS" else ("k", "stride", "in", "out")):
+                assert r[k] == g[k], "%s layer %d (%s): %s reference %r vs oracle %r" % (what, i, r.get("w"), k, r[k], g[k])
+    zipn = _ref_events("create_zip_network#1")
+    compare(zipn[:24], got["mr"][:24], {"ph:main_batchnorm_training_switch": True}, "oracle MR front")
+    compare(zipn[24:], got["ct"][:24], {"ph:adapt_batchnorm_training_switch": False}, "oracle CT front")
+    compare(_ref_events("create_second_half#1"), got["ct"][24:], {"ph:joint_batchnorm_training_switch": True}, "oracle second half (CT)")
+    compare(_ref_events("create_second_half#2"), got["mr"][24:], {"ph:joint_batchnorm_training_switch": False}, "oracle second half (MR)")
+    compare(_ref_events("create_classifier#1"), got["cls"], {}, "oracle feature discriminator")
+    compare(_ref_events("create_mask_critic#1"), got["mask"], {}, "oracle mask critic")
+    # variable tables of the oracle's layout() against the reference's
+    ws, bns = PG.OracleAdversarial.layout(5)
+    ref_w = {v["name"]: v["shape"] for v in REF["variables"] if v["kind"] != "batch_norm"}
+    assert {n: list(s) for n, s in ws} == ref_w
+    ref_bn = {v["name"].rsplit("/", 1)[0]: v["shape"][0] for v in REF["variables"] if v["kind"] == "batch_norm"}
+    assert dict(bns) == ref_bn
+
+
+def test_oracle_segmenter_matches_the_reference_trace():
+    from oracle import pnp_graphs as PG, tf14_torch as T
+    seg = PG.OracleSegmenter({}, B)
+    wname, bnname = {}, {id(bn): k for k, bn in seg.ps.bn.items()}
+    for k in list(seg.ps.w):
+        t = torch.empty(seg.ps.w[k].shape, device="meta")
+        seg.ps.w[k] = t
+        wname[id(t)] = k
+    tr = _OracleTracer(T, wname, bnname)
+    names = ("conv2d_raw", "dropout", "batch_norm", "channel_pad_skip", "act", "max_pool2d", "PS")
+    saved = {k: getattr(T, k) for k in names}
+    for k in names:
+        setattr(T, k, getattr(tr, k))
+    try:
+        seg.forward(torch.empty(B, 256, 256, 3, device="meta"), keep_prob=KEEP_PH, bn_train=True)
+        tr.close()
+    finally:
+        for k, v in saved.items():
+            setattr(T, k, v)
+    ref = REF["source_segmenter"]["events"]
+    assert len(ref) == len(tr.events) == 37
+    sw = {"ph:adapt_batchnorm_training_switch": True, "ph:main_batchnorm_training_switch": True}      # the oracle has one switch
+    for i, (r, g) in enumerate(zip(ref, tr.events)):
+        r = _norm_ref(r, sw)
+        assert r["op"] == g["op"], i
+        for k in (("w", "wshape", "stride", "dil", "padding", "in", "out", "keep", "bn", "bn_train", "act", "skip") if r["op"] == "conv"
+                  else ("r", "n_channel", "in", "out") if r["op"] == "PS" else ("k", "stride", "in", "out")):
+            assert r[k] == g[k], "segmenter layer %d (%s): %s reference %r vs oracle %r" % (i, r.get("w"), k, r[k], g[k])
+    # variable layout and the L2 list (with the wr4_4 / wr4_3 quirk)
+    ws, bns = PG.OracleSegmenter.layout(5)
+    rv = REF["source_segmenter"]["variables"]
+    assert {n: list(s) for n, s in ws} == {v["name"]: v["shape"] for v in rv if v["kind"] != "batch_norm"}
+    assert dict(bns) == {v["name"].rsplit("/", 1)[0]: v["shape"][0] for v in rv if v["kind"] == "batch_norm"}
+    assert sorted(seg.l2_names) == sorted(REF["source_segmenter"]["conv_weights"])
