@@ -249,13 +249,21 @@ class Full_DRN(object):
         return self.reg_coeff * (float(F.l2_loss_sum(uniq).item()) + 2 * float(F.l2_loss_sum(back).item()))
 
     # ---- checkpoint naming contract --------------------------------------------------------------------------
-    def restore(self, model_path, no_gan=False, clear_rms=False, skip_keywords=("Adam", "RMS", "cls")):
-        """adversarial.py:503-574.  no_gan: only 'group*'/'output*' conv weights (no BN) from a baseline
-        segmenter checkpoint; otherwise every known variable except names containing a skip keyword when
-        clear_rms is set (optimizer slots are not stored in our checkpoints at all)."""
+    def restore(self, model_path, no_gan=False, clear_rms=False, skip_keywords=None):
+        """adversarial.py:503-574, on a .npz checkpoint keyed by TF variable names (optimizer slots are never stored).
+        no_gan:    only the 'group*' / 'output*' filters of a baseline segmenter checkpoint (no batch norm)   (:514-531)
+        clear_rms: every stored variable except the RMSProp slots                                             (:533-550)
+        default:   a full restore; if the checkpoint lacks ANY variable of the graph (where tf.train.Saver.restore raises) the
+                   relaxed branch loads what is stored except names containing a `restore_skip_kwd` keyword -- the feature
+                   discriminator and mask critic ('cls') then start from their initialisation                 (:552-573)"""
         d = dict(np.load(model_path))
         if no_gan:
             d = {k: v for k, v in d.items() if (k.startswith("group") or k.startswith("output")) and "/Variable" in k}
+        elif clear_rms:
+            d = {k: v for k, v in d.items() if "RMS" not in k}
+        elif any(n not in d for n in rt.graph.order):
+            kws = skip_keywords if skip_keywords is not None else self.network_config.get("restore_skip_kwd", ("Adam", "RMS", "cls"))
+            d = {k: v for k, v in d.items() if not any(kw in k for kw in kws)}
         return rt.load_state_dict(d, strict=False)
 
     def load_batch_norm_weights(self, baseline_path):

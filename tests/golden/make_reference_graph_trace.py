@@ -580,7 +580,8 @@ def main():
         _load("lib")
         adv = _load("adversarial")
 
-        cfg = {"mr_front_trainable": False, "ct_front_trainable": True, "joint_trainable": False, "cls_trainable": True, "m_cls_trainable": True}
+        cfg = {"mr_front_trainable": False, "ct_front_trainable": True, "joint_trainable": False, "cls_trainable": True, "m_cls_trainable": True,
+               "restore_skip_kwd": ["Adam", "RMS", "cls"]}                     # train_gan.py:39-46 (train-gan phase)
         cost_kwargs = {"regularizer": 1e-4, "gan_regularizer": 1e-4, "miu_dis": 1e-3, "miu_gen": 2e-3, "lambda_mask_loss": 0.1}
 
         # mark sections by wrapping the four graph-construction methods
@@ -630,7 +631,8 @@ def main():
     trace["input_pipeline"] = trace_input_pipeline(tf, adv)
     trace["source_segmenter"] = trace_source_segmenter(tf)
     G_adv_order = [v["name"] for v in trace["variables"]]
-    trace["transplant"] = trace_transplant(tf, adv, net, G_adv_order, [v["name"] for v in trace["source_segmenter"]["variables"]])
+    trace["transplant"] = trace_transplant(tf, adv, net, G_adv_order, [v["name"] for v in trace["source_segmenter"]["variables"]],
+                                           {v["name"]: v["trainable"] for v in trace["variables"]})
     with open(OUT, "w") as f:
         json.dump(trace, f, indent=0, sort_keys=True)
     print("wrote %s: %d + %d events, %d + %d variables" % (OUT, len(trace["events"]), len(trace["source_segmenter"]["events"]),
@@ -908,7 +910,7 @@ def trace_input_pipeline(tf, adv):
             "channel_sums": [float(pair[0, :, :, c].astype(np.float64).sum()) for c in range(4)]}
 
 
-def trace_transplant(tf, adv, net, adv_names, baseline_names):
+def trace_transplant(tf, adv, net, adv_names, baseline_names, adv_trainable):
     """adversarial.py:503-531 (restore, no_gan), :706-741 (_adapt_copy_weights, both modes), :743-765 (_load_batch_norm_weights)
     executed on the variable-name lists the reference ships under lists/ and on the traced variable tables"""
     def read(fn):
@@ -959,6 +961,37 @@ def trace_transplant(tf, adv, net, adv_names, baseline_names):
     rc = adv.Full_DRN.restore(net, "sess", "./ckpt/model", no_gan=True)
     assert rc == 0 and len(restored) == 1
     out["restore_no_gan"] = {"checkpoint_names": sorted(ckpt), "restored": restored[0]}
+
+    # ---- the other branches of restore (adversarial.py:533-574) on GAN checkpoints.  The live graph also holds the RMSProp slots
+    trainable = [n for n in adv_names if adv_trainable[n] and ("cls" in n or "adapt" in n)]
+    slots = [n + sfx for n in trainable for sfx in ("/RMSProp", "/RMSProp_1")]
+    graph_vars = list(adv_names) + slots
+    tf.global_variables = lambda: [_VarObj({"name": n}) for n in graph_vars]
+    tf.contrib.framework.get_variables = lambda: [_VarObj({"name": n}) for n in graph_vars]
+
+    class StrictSaver(object):
+        """tf.train.Saver.restore fails when a variable of its list is missing from the checkpoint"""
+
+        def __init__(self, var_list=None):
+            self.var_list = var_list
+
+        def restore(self, sess, path):
+            names = [strip(v.name) for v in self.var_list]
+            missing = [n for n in names if n not in ckpt_now]
+            if missing:
+                raise KeyError("not found in checkpoint: %s" % missing[0])
+            restored.append(names)
+    tf.train.Saver = StrictSaver
+    cases = {}
+    full = {n: None for n in graph_vars}
+    partial = {n: None for n in graph_vars if "mask_cls" not in n}          # e.g. a checkpoint written before the mask critic existed
+    for label, ck, kw in (("full_default", full, {}), ("full_clear_rms", full, {"clear_rms": True}), ("partial_default", partial, {})):
+        ckpt_now = ck
+        tf.pywrap_tensorflow = types.SimpleNamespace(NewCheckpointReader=lambda path, ck=ck: types.SimpleNamespace(get_variable_to_shape_map=lambda: ck))
+        del restored[:]
+        adv.Full_DRN.restore(net, "sess", "./ckpt/model", **kw)
+        cases[label] = {"checkpoint_names": sorted(ck), "restored": sorted(restored[-1]), "skip_kwd": list(net.network_config["restore_skip_kwd"])}
+    out["restore_gan"] = cases
     if saved_assign is not None:
         tf.assign = saved_assign
     return out

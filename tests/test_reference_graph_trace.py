@@ -770,3 +770,24 @@ def test_oracle_segmenter_matches_the_reference_trace():
     assert {n: list(s) for n, s in ws} == {v["name"]: v["shape"] for v in rv if v["kind"] != "batch_norm"}
     assert dict(bns) == {v["name"].rsplit("/", 1)[0]: v["shape"][0] for v in rv if v["kind"] == "batch_norm"}
     assert sorted(seg.l2_names) == sorted(REF["source_segmenter"]["conv_weights"])
+
+
+def test_gan_checkpoint_restore_branches_match_the_reference(tmp_path):
+    """adversarial.py:533-574: clear_rms, the full restore, and the relaxed branch a partial checkpoint falls into"""
+    import numpy as np
+    from pnp_b200 import adversarial as A, runtime as rt
+    cases = REF["transplant"]["restore_gan"]
+    for label, kw in (("full_default", {}), ("full_clear_rms", {"clear_rms": True}), ("partial_default", {})):
+        case = cases[label]
+        net = A.Full_DRN(3, 5, B, cost_kwargs=dict(COST), network_config=dict(CFG, restore_skip_kwd=case["skip_kwd"]))
+        V = rt.graph.vars
+        stored = [n for n in case["checkpoint_names"] if "RMSProp" not in n]      # this checkpoint format carries no optimizer slots
+        np.savez(str(tmp_path / (label + ".npz")), **{n: np.full(tuple(V[n].shape), 7.5, np.float32) for n in stored})
+        with torch.no_grad():
+            for n in rt.graph.order:
+                V[n].fill_(-1.0)
+        net.restore(str(tmp_path / (label + ".npz")), **kw)
+        changed = sorted(n for n in rt.graph.order if float(V[n].detach().flatten()[0]) == 7.5)
+        want = sorted(n for n in case["restored"] if "RMSProp" not in n)
+        assert changed == want, (label, len(changed), len(want))
+    assert len(cases["partial_default"]["restored"]) == 254 and not any("cls" in n for n in cases["partial_default"]["restored"])
