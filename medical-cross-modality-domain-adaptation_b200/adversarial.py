@@ -258,13 +258,19 @@ class Full_DRN(object):
                    discriminator and mask critic ('cls') then start from their initialisation                 (:552-573)"""
         d = dict(np.load(model_path))
         if no_gan:
-            d = {k: v for k, v in d.items() if (k.startswith("group") or k.startswith("output")) and "/Variable" in k}
+            # :518-525 -- graph variables present in the checkpoint, minus adapt / cls / Adam names, that contain 'group' or
+            # 'output' (a baseline checkpoint names its batch norm 'BatchNorm_k/*', so only the 33 filters qualify; a GAN
+            # checkpoint would also hand over its 'group*/pred_*' statistics)
+            d = {k: v for k, v in d.items() if k in rt.graph.vars and not any(s_ in k for s_ in ("adapt", "cls", "Adam"))
+                 and ("group" in k or "output" in k)}
         elif clear_rms:
             d = {k: v for k, v in d.items() if "RMS" not in k}
         elif any(n not in d for n in rt.graph.order):
             kws = skip_keywords if skip_keywords is not None else self.network_config.get("restore_skip_kwd", ("Adam", "RMS", "cls"))
             d = {k: v for k, v in d.items() if not any(kw in k for kw in kws)}
-        return rt.load_state_dict(d, strict=False)
+        self.last_restored = d           # Trainer.train hands the same filtered view to the optimizer slots
+        return rt.load_state_dict({k: v for k, v in d.items() if k in rt.graph.vars or (k.endswith(":0") and k[:-2] in rt.graph.vars)},
+                                  strict=False)
 
     def load_batch_norm_weights(self, baseline_path):
         """adversarial.py:743-765: baseline 'BatchNorm_k/*' -> 'group_g/pred_*' in creation order
@@ -440,18 +446,24 @@ class Trainer(object):
         try:
             self._gx_mr = mr_example.clone()
             self._gx_ct = ct_example.clone()
+            self._gx_ct_g = ct_example.clone()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(warmup):
                     self.d_step(self._gx_mr, self._gx_ct, keep_prob)
-                    self.g_step(self._gx_ct, keep_prob)
+                    self.g_step(self._gx_ct_g, keep_prob)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            # the per-variable operand caches (bf16 weight planes, transposed SIMT weights) are keyed by a HOST-side version
+            # counter: a hit during capture would record no split kernel and freeze the warm-up buffers into the graph, i.e.
+            # every replay would run on pre-capture weights.  Drop them so the captured step re-derives them from the live
+            # arenas, and keep the variables' versions moving on every replay (joint_step) for eager code that runs later.
+            self._invalidate_operand_caches()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 d = self.d_step(self._gx_mr, self._gx_ct, keep_prob)
-                gg = self.g_step(self._gx_ct, keep_prob)
+                gg = self.g_step(self._gx_ct_g, keep_prob)
             self._graph, self._graph_out, self._graph_kp = g, (d, gg), keep_prob
             return True
         except Exception as e:      # noqa: BLE001 -- any capture problem => eager path, loudly
@@ -461,15 +473,58 @@ class Trainer(object):
             torch.cuda.synchronize()
             return False
 
-    def joint_step(self, mr_batch, ct_batch, keep_prob=0.75):
-        """one full adversarial step (D update + clip, then G update); replays the captured graph when there is one"""
+    def _invalidate_operand_caches(self):
+        for v in self.d_vars + self.g_vars:
+            v.__dict__.pop("_pnp_planes", None)
+            v.__dict__.pop("_pnp_wT", None)
+
+    def joint_step(self, mr_batch, ct_batch, keep_prob=0.75, ct_batch_g=None):
+        """one full adversarial step (D update + clip, then G update); replays the captured graph when there is one.
+        `ct_batch_g`: the fresh CT batch the reference dequeues for the generator update (adversarial.py:869-873);
+        None re-uses the D step's CT batch."""
         if getattr(self, "_graph", None) is not None and keep_prob == self._graph_kp:
             self._gx_mr.copy_(mr_batch, non_blocking=True)
             self._gx_ct.copy_(ct_batch, non_blocking=True)
+            self._gx_ct_g.copy_(ct_batch if ct_batch_g is None else ct_batch_g, non_blocking=True)
             self._graph.replay()
             self.global_step += 2
+            # the replay changed both arenas on the device: eager code that follows must not trust its cached operands
+            self.d_arena.bump_versions()
+            self.g_arena.bump_versions()
             return self._graph_out
-        return self.d_step(mr_batch, ct_batch, keep_prob), self.g_step(ct_batch, keep_prob)
+        return self.d_step(mr_batch, ct_batch, keep_prob), self.g_step(ct_batch if ct_batch_g is None else ct_batch_g, keep_prob)
+
+    # ---- checkpoint contents: tf.train.Saver() stores every global variable -- model variables, both optimizers' slots,
+    #      learning_rate_node and global_step (adversarial.py:640,662,929) ---------------------------------------------
+    def checkpoint_state(self):
+        self.dp.average_moving_stats(rt.global_variables())
+        st = rt.state_dict()
+        st.update(self.dis_optimizer.slot_state())
+        st.update(self.gen_optimizer.slot_state())
+        st["pnp/learning_rate"] = np.float32(self.dis_optimizer.get_lr())       # TF names these two scalars 'Variable_k' by
+        st["pnp/global_step"] = np.int64(self.global_step)                      # creation order; stable keys here
+        return st
+
+    def load_optimizer_state(self, d, clear_rms=False):
+        """what a tf.train.Saver restore brings back besides the model: RMSProp slots (unless clear_rms, whose name filter
+        'RMS' drops them, :541), the learning-rate variable and global_step"""
+        n = 0
+        if not clear_rms:
+            n = self.dis_optimizer.load_slot_state(d) + self.gen_optimizer.load_slot_state(d)
+        if "pnp/learning_rate" in d:
+            lr = float(d["pnp/learning_rate"])
+            self.dis_optimizer.set_lr(lr)
+            self.gen_optimizer.set_lr(lr)
+        if "pnp/global_step" in d:
+            self.global_step = int(d["pnp/global_step"])
+        return n
+
+    def save(self, save_path, output_path):
+        st = self.checkpoint_state()
+        def write():
+            _save(st, save_path, global_step=self.global_step)
+            _save(st, os.path.join(output_path, "latest"))
+        self.dp.save_checkpoint(write)
 
     @staticmethod
     def loss_value(terms):
@@ -489,6 +544,13 @@ class Trainer(object):
                 self.net.load_batch_norm_weights(ck)
                 print("initializing from baseline model!")
                 self.net.adapt_copy_weights()
+            else:
+                self.load_optimizer_state(self.net.last_restored, clear_rms=cfg.get("clear_rms", False))
+        # data parallel: every replica continues from rank 0's variables (weights, frozen parts, BN statistics, slots)
+        self.dp.broadcast_variables(rt.global_variables())
+        for opt_ in (self.dis_optimizer, self.gen_optimizer):
+            self.dp.broadcast_params(opt_.ms)
+            self.dp.broadcast_params(opt_.mom)
         if self.lr_update_flag:
             self.dis_optimizer.set_lr(self.LR_refresh)
             self.gen_optimizer.set_lr(self.LR_refresh)
@@ -526,8 +588,7 @@ class Trainer(object):
                 if step % display_step == 0:
                     logging.info("Training step %s epoch %s finished, %.3f s" % (step, epoch, time.time() - start))
                 if step % ckpt_space == 0 and step != 0:
-                    _save(rt.state_dict(), save_path, global_step=self.global_step)
-                    _save(rt.state_dict(), os.path.join(output_path, "latest"))
+                    self.save(save_path, output_path)
                     lr = self.dis_optimizer.get_lr() * decay
                     self.dis_optimizer.set_lr(lr)
                     self.gen_optimizer.set_lr(lr)

@@ -63,6 +63,9 @@ def _indicator_eval(cm):
 
 def _save(state, model_path, global_step=None):
     """lib.py:23-29 analogue: variables keyed by TF names in one .npz (the checkpoint naming contract)."""
+    import os
     path = model_path if global_step is None else "%s-%d" % (model_path, int(global_step))
-    np.savez(path + ".npz", **state)
+    tmp = "%s.tmp.%d.npz" % (path, os.getpid())
+    np.savez(tmp, **state)            # a reader (or a second writer) never sees a half-written checkpoint
+    os.replace(tmp, path + ".npz")
     return path + ".npz"

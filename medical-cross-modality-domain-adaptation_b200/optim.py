@@ -55,6 +55,32 @@ class Arena:
         return torch.tensor([float(x) for x in values], dtype=torch.float32, device=self.theta.device)
 
 
+def _slot_views(arena, flat):
+    return [flat[o:o + n].view(v.shape) for v, (o, n) in zip(arena.vars, arena.offsets)]
+
+
+def _export_slots(arena, slots):
+    """{'<variable name>/<slot>': numpy} -- tf.train.Saver stores optimizer slots under these names"""
+    out = {}
+    for slot_name, flat in slots.items():
+        for v, view in zip(arena.vars, _slot_views(arena, flat)):
+            out["%s/%s" % (v.pnp_name, slot_name)] = view.detach().cpu().numpy().copy()
+    return out
+
+
+def _import_slots(arena, slots, d):
+    """load what is stored; returns the number of slot tensors found"""
+    found = 0
+    with torch.no_grad():
+        for slot_name, flat in slots.items():
+            for v, view in zip(arena.vars, _slot_views(arena, flat)):
+                k = "%s/%s" % (v.pnp_name, slot_name)
+                if k in d:
+                    view.copy_(torch.as_tensor(d[k], dtype=view.dtype).reshape(view.shape))
+                    found += 1
+    return found
+
+
 class Adam:
     """tf.train.AdamOptimizer(learning_rate, beta1=.9, beta2=.999, epsilon=1e-8) over an Arena."""
 
@@ -73,6 +99,20 @@ class Adam:
 
     def get_lr(self):
         return float(self.state[2].item())
+
+    def slot_state(self):
+        """tf.train.AdamOptimizer slots '<var>/Adam' (m), '<var>/Adam_1' (v) + the beta-power accumulators"""
+        d = _export_slots(self.arena, {"Adam": self.m, "Adam_1": self.v})
+        st = self.state.detach().cpu().numpy()
+        d["beta1_power"], d["beta2_power"] = st[0].astype("float32"), st[1].astype("float32")
+        return d
+
+    def load_slot_state(self, d):
+        n = _import_slots(self.arena, {"Adam": self.m, "Adam_1": self.v}, d)
+        if "beta1_power" in d and "beta2_power" in d:
+            self.state[0] = float(d["beta1_power"])
+            self.state[1] = float(d["beta2_power"])
+        return n
 
     def step(self, grad_scale=1.0):
         a = self.arena
@@ -102,6 +142,13 @@ class RMSProp:
 
     def get_lr(self):
         return float(self.lr_t.item())
+
+    def slot_state(self):
+        """tf.train.RMSPropOptimizer slots '<var>/RMSProp' (ms), '<var>/RMSProp_1' (momentum)"""
+        return _export_slots(self.arena, {"RMSProp": self.ms, "RMSProp_1": self.mom})
+
+    def load_slot_state(self, d):
+        return _import_slots(self.arena, {"RMSProp": self.ms, "RMSProp_1": self.mom}, d)
 
     def set_weight_decay(self, values):
         self.seg_wd.copy_(self.arena.seg_table(values))

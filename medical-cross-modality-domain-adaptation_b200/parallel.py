@@ -48,3 +48,39 @@ class DataParallel:
     def barrier(self):
         if self.on:
             dist.barrier()
+
+    def broadcast_variables(self, variables):
+        """every replica continues from rank 0's values: ALL graph variables (frozen weights and BN moving statistics
+        included), after construction and after every restore -- replicas must not depend on identical host seeds"""
+        if not self.on:
+            return
+        seen = set()
+        with torch.no_grad():
+            for v in variables:
+                arena = getattr(v, "_pnp_arena", None)
+                t = arena.theta if arena is not None else v
+                if id(t) in seen:
+                    continue
+                seen.add(id(t))
+                dist.broadcast(t, src=0)
+                if arena is None:
+                    v.pnp_version = getattr(v, "pnp_version", 0) + 1
+        for v in variables:
+            if getattr(v, "_pnp_arena", None) is not None:
+                v.pnp_version = getattr(v, "pnp_version", 0) + 1
+
+    def average_moving_stats(self, variables):
+        """BN moving statistics are updated from per-rank batches (no SyncBN); a checkpoint stores their mean"""
+        if not self.on:
+            return
+        with torch.no_grad():
+            for v in variables:
+                if getattr(v, "pnp_kind", "") == "bn_moving":
+                    dist.all_reduce(v, op=dist.ReduceOp.SUM)
+                    v.mul_(1.0 / self.world)
+
+    def save_checkpoint(self, save_fn):
+        """rank 0 alone writes (save_fn must write atomically); every rank waits for the file to be complete"""
+        if self.rank == 0:
+            save_fn()
+        self.barrier()

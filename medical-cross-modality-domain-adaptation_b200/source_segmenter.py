@@ -128,7 +128,8 @@ class Full_DRN(object):
     def restore(self, model_path):
         """source_segmenter.py:275-300 with relaxation: load every stored variable whose name we know."""
         d = dict(np.load(model_path))
-        missing = rt.load_state_dict(d, strict=False)
+        self.last_restored = d
+        missing = rt.load_state_dict({k: v for k, v in d.items() if k in rt.graph.vars}, strict=False)
         logging.info("Model restored from file: %s (%d unknown names skipped)" % (model_path, len(missing)))
 
 
@@ -201,10 +202,20 @@ class Trainer(object):
         os.makedirs(output_path, exist_ok=True)
         if restore and restored_path and os.path.exists(os.path.join(restored_path, "latest.npz")):
             self.net.restore(os.path.join(restored_path, "latest.npz"))
+            # tf.train.Saver() also brings back the Adam slots, the learning-rate variable and global_step (:398,:446-452)
+            d = self.net.last_restored
+            self.optimizer.load_slot_state(d)
+            if "pnp/learning_rate" in d:
+                self.optimizer.set_lr(float(d["pnp/learning_rate"]))
+            if "pnp/global_step" in d:
+                self.global_step = int(d["pnp/global_step"])
             if self.lr_update_flag:
                 self.optimizer.set_lr(self._new_LR)
         elif restore:
             print("Unable to restore, start from beginning")
+        self.dp.broadcast_variables(rt.global_variables())
+        self.dp.broadcast_params(self.optimizer.m)
+        self.dp.broadcast_params(self.optimizer.v)
         if self.source is not None:
             src = self.source
         elif self.train_list:      # the reference's lists/*_train_list of single-example TFRecord files
@@ -223,10 +234,24 @@ class Trainer(object):
                     logging.info("Training at step %s epoch %s , loss is %0.4f" % (step, epoch, loss))
                     logging.info("Time elapsed %s seconds" % (time.time() - start))
                 if step % self.checkpoint_space == 0 and step > 10000:
-                    _save(rt.state_dict(), save_path, global_step=self.global_step)
-                    _save(rt.state_dict(), os.path.join(output_path, "latest"))
+                    self.save(save_path, output_path)
                     self.optimizer.set_lr(self.optimizer.get_lr() * 0.9)
         return save_path
+
+    def checkpoint_state(self):
+        self.dp.average_moving_stats(rt.global_variables())
+        st = rt.state_dict()
+        st.update(self.optimizer.slot_state())
+        st["pnp/learning_rate"] = np.float32(self.optimizer.get_lr())
+        st["pnp/global_step"] = np.int64(self.global_step)
+        return st
+
+    def save(self, save_path, output_path):
+        st = self.checkpoint_state()
+        def write():
+            _save(st, save_path, global_step=self.global_step)
+            _save(st, os.path.join(output_path, "latest"))
+        self.dp.save_checkpoint(write)
 
     def val_stats(self, batch_x, batch_y):
         """source_segmenter.py:541-570: inference-mode forward (BN moving stats, keep_prob 1)"""
