@@ -437,41 +437,77 @@ class Trainer(object):
             cm = F.confusion_counts(out["logits"], ct_labels_onehot)
         return {"dice_eval": float(dice), "dice_arr": [float(a) for a in arr], "confusion_matrix": cm.cpu().numpy()}
 
-    # ---- the joint adversarial step as ONE CUDA graph ---------------------------------------------------------------
-    def capture_joint_step(self, mr_example, ct_example, keep_prob=0.75, warmup=2):
-        """Capture `d_step(mr, ct)` + `g_step(ct)` (forward, backward, all-reduce, optimizer, clip: ~1.4 k kernel launches)
-        into one CUDA graph on static input buffers.  Dropout seeds, optimizer hyper-state and BN statistics live in device
-        memory, so every replay is a genuinely new training step.  Returns False (and stays eager) if capture fails."""
-        self._graph = None
+    # ---- steps as CUDA graphs -----------------------------------------------------------------------------------------
+    def _capture(self, fn, warmup):
+        """Capture `fn()` (forward, backward, all-reduce, optimizer, clip: ~1 k kernel launches) into one CUDA graph.
+        Dropout seeds, optimizer hyper-state and BN statistics live in device memory, so every replay is a genuinely new
+        training step.  Returns (graph, outputs) or (None, None) -- loudly -- if capture fails."""
         try:
-            self._gx_mr = mr_example.clone()
-            self._gx_ct = ct_example.clone()
-            self._gx_ct_g = ct_example.clone()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(warmup):
-                    self.d_step(self._gx_mr, self._gx_ct, keep_prob)
-                    self.g_step(self._gx_ct_g, keep_prob)
+                    fn()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             # the per-variable operand caches (bf16 weight planes, transposed SIMT weights) are keyed by a HOST-side version
             # counter: a hit during capture would record no split kernel and freeze the warm-up buffers into the graph, i.e.
             # every replay would run on pre-capture weights.  Drop them so the captured step re-derives them from the live
-            # arenas, and keep the variables' versions moving on every replay (joint_step) for eager code that runs later.
+            # arenas, and keep the variables' versions moving on every replay for eager code that runs later.
             self._invalidate_operand_caches()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                d = self.d_step(self._gx_mr, self._gx_ct, keep_prob)
-                gg = self.g_step(self._gx_ct_g, keep_prob)
-            self._graph, self._graph_out, self._graph_kp = g, (d, gg), keep_prob
-            return True
+                out = fn()
+            return g, out
         except Exception as e:      # noqa: BLE001 -- any capture problem => eager path, loudly
             import warnings
             warnings.warn("CUDA-graph capture of the adversarial step failed (%s: %s); running eagerly" % (type(e).__name__, e))
-            self._graph = None
             torch.cuda.synchronize()
-            return False
+            return None, None
+
+    def capture_joint_step(self, mr_example, ct_example, keep_prob=0.75, warmup=2):
+        """`d_step(mr, ct)` + `g_step(ct_g)` as ONE graph on static input buffers (the warm-up steps are real steps)."""
+        self._gx_mr, self._gx_ct, self._gx_ct_g = mr_example.clone(), ct_example.clone(), ct_example.clone()
+        self._graph, self._graph_out = self._capture(
+            lambda: (self.d_step(self._gx_mr, self._gx_ct, keep_prob), self.g_step(self._gx_ct_g, keep_prob)), warmup)
+        self._graph_kp = keep_prob
+        return self._graph is not None
+
+    def capture_d_step(self, mr_example, ct_example, keep_prob=0.75, warmup=2):
+        """the discriminator update alone (pre-train phase; the n_D inner iterations of train-gan)"""
+        self._dx_mr, self._dx_ct = mr_example.clone(), ct_example.clone()
+        self._d_graph, self._d_graph_out = self._capture(lambda: self.d_step(self._dx_mr, self._dx_ct, keep_prob), warmup)
+        self._d_graph_kp = keep_prob
+        return self._d_graph is not None
+
+    def capture_g_step(self, ct_example, keep_prob=0.75, warmup=2):
+        self._gsx_ct = ct_example.clone()
+        self._g_graph, self._g_graph_out = self._capture(lambda: self.g_step(self._gsx_ct, keep_prob), warmup)
+        self._g_graph_kp = keep_prob
+        return self._g_graph is not None
+
+    def d_step_replay(self, mr_batch, ct_batch, keep_prob=0.75):
+        if getattr(self, "_d_graph", None) is None or keep_prob != self._d_graph_kp:
+            return self.d_step(mr_batch, ct_batch, keep_prob)
+        self._dx_mr.copy_(mr_batch, non_blocking=True)
+        self._dx_ct.copy_(ct_batch, non_blocking=True)
+        self._d_graph.replay()
+        self.global_step += 1
+        self.d_arena.bump_versions()
+        return self._d_graph_out
+
+    def g_step_replay(self, ct_batch, keep_prob=0.75):
+        if getattr(self, "_g_graph", None) is None or keep_prob != self._g_graph_kp:
+            return self.g_step(ct_batch, keep_prob)
+        self._gsx_ct.copy_(ct_batch, non_blocking=True)
+        self._g_graph.replay()
+        self.global_step += 1
+        self.g_arena.bump_versions()
+        return self._g_graph_out
+
+    def release_graphs(self):
+        for n in ("_graph", "_graph_out", "_d_graph", "_d_graph_out", "_g_graph", "_g_graph_out"):
+            setattr(self, n, None)
 
     def _invalidate_operand_caches(self):
         for v in self.d_vars + self.g_vars:

@@ -27,13 +27,17 @@ def label_maps(B, seed, size=256, num_cls=5):
 class SyntheticSource:
     """yields (images [B,256,256,3] fp32, labels [B,256,256] int64) as pinned host tensors"""
 
-    def __init__(self, batch_size, seed=1234, shift=0.0, scale=1.0, size=256, num_cls=5, pool=4):
+    def __init__(self, batch_size, seed=1234, shift=0.0, scale=1.0, size=256, num_cls=5, pool=4, contrast=0.0):
+        """contrast > 0 adds a per-class intensity ((class - (num_cls-1)/2) * contrast / 2) to the noise, so that the labels can be
+        learned from the images (the held-out Dice gate trains on this); 0 = pure z-scored noise (the throughput workloads)"""
         self.B, self.size, self.num_cls = batch_size, size, num_cls
         g = torch.Generator().manual_seed(seed)
         self.pool = []
         for i in range(pool):
             x = torch.randn(batch_size, size, size, 3, generator=g) * scale + shift
             y = torch.from_numpy(label_maps(batch_size, seed + 99 + i, size, num_cls))
+            if contrast:
+                x = x + ((y.to(torch.float32) - (num_cls - 1) / 2.0) * (contrast / 2.0)).unsqueeze(-1)
             if torch.cuda.is_available():
                 x, y = x.pin_memory(), y.pin_memory()
             self.pool.append((x, y))

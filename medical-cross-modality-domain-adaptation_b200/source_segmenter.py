@@ -178,6 +178,43 @@ class Trainer(object):
         self.global_step += 1
         return wce, dice
 
+    def capture_train_step(self, x_example, y_example, keep_prob=0.75, warmup=2):
+        """the Adam step as ONE CUDA graph on static input buffers (the warm-up steps are real steps)"""
+        self._gx, self._gy = x_example.clone(), y_example.clone()
+        self._graph = None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self.train_step(self._gx, self._gy, keep_prob)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for v in self.trainables:          # see adversarial.Trainer._capture: no stale operand caches inside the graph
+                v.__dict__.pop("_pnp_planes", None)
+                v.__dict__.pop("_pnp_wT", None)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.train_step(self._gx, self._gy, keep_prob)
+            self._graph, self._graph_out, self._graph_kp = g, out, keep_prob
+            return True
+        except Exception as e:      # noqa: BLE001
+            import warnings
+            warnings.warn("CUDA-graph capture of the segmenter step failed (%s: %s); running eagerly" % (type(e).__name__, e))
+            torch.cuda.synchronize()
+            self._graph = None
+            return False
+
+    def train_step_replay(self, batch_x, batch_y, keep_prob=0.75):
+        if getattr(self, "_graph", None) is None or keep_prob != self._graph_kp:
+            return self.train_step(batch_x, batch_y, keep_prob)
+        self._gx.copy_(batch_x, non_blocking=True)
+        self._gy.copy_(batch_y, non_blocking=True)
+        self._graph.replay()
+        self.global_step += 1
+        self.arena.bump_versions()
+        return self._graph_out
+
     def output_minibatch_stats(self, batch_x, batch_y):
         """source_segmenter.py:525-539: the tensorboard pass on the training batch feeds x, y and keep_prob 1 ONLY -- both BN
         switches stay at their placeholder default True, so this forward runs batch-statistics BN and (updates_collections=None)
