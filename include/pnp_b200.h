@@ -91,6 +91,26 @@ int pnp_conv2d_tc_fwd(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t
                       float* y, const pnp_conv_geom* g, int nterms, const pnp_dropout_cfg* drop,
                       int accumulate, double* bn_sum, double* bn_sumsq, void* stream);
 
+/* Forward convolution with a FUSED epilogue: y = act(dropout(conv) * scale[c] + shift[c] + skip) -- inference-mode batch norm
+ * (tf.contrib.layers.batch_norm(is_training=False), layers.py:95-100: scale = gamma*rsqrt(moving_var+eps), shift = beta -
+ * moving_mean*scale), the residual add with channel-pad skip (layers.py:160-166) and the activation (layers.py:12-14) applied
+ * to the accumulator before it leaves the SM; optionally also emits the bf16 (hi, lo) operand planes of y for the next tcgen05
+ * convolution (y itself may then be NULL).  This is the whole frozen-segmenter forward of the D step and the evaluation path
+ * (adversarial.py:840-862, 993-1052): one kernel per layer, no z round trip.  ep == NULL: identical to pnp_conv2d_tc_fwd.
+ * Batch statistics (bn_sum/bn_sumsq) are statistics of z and cannot be combined with a fused epilogue. */
+typedef struct {
+  const float* scale;   /* [Cout] or NULL */
+  const float* shift;   /* [Cout] or NULL (both or neither) */
+  const float* skip;    /* [B,Ho,Wo,skip_C] fp32 or NULL */
+  int skip_C, skip_off; /* skip is added to channels [skip_off, skip_off + skip_C) */
+  int act;              /* PNP_ACT_* */
+  uint16_t* y_hi;       /* optional [B,Ho,Wo,Cout] bf16 planes of y */
+  uint16_t* y_lo;       /* required with y_hi when nterms == 3 */
+} pnp_tc_epilogue;
+int pnp_conv2d_tc_fwd_fused(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo,
+                            float* y, const pnp_conv_geom* g, int nterms, const pnp_dropout_cfg* drop, int accumulate,
+                            double* bn_sum, double* bn_sumsq, const pnp_tc_epilogue* ep, void* stream);
+
 /* dx[B,H,W,Cin] (+)= conv^T(dy, w) on tcgen05.  g is the FORWARD geometry; stride s > 1 is decomposed into s*s
  * stride-1 phase convolutions (no multiplications by the zeros a transposed convolution would insert). */
 int pnp_conv2d_tc_dgrad(const uint16_t* dy_hi, const uint16_t* dy_lo, const uint16_t* w_hi, const uint16_t* w_lo,
@@ -110,6 +130,19 @@ int pnp_bn_stats(const float* z, long long M, int C, double* sum, double* sumsq,
 int pnp_bn_finalize(const double* sum, const double* sumsq, long long M, int C, const float* gamma,
                     const float* beta, float* moving_mean, float* moving_var, int training,
                     float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* pnp_bn_finalize + pnp_bn_act_apply in ONE launch: every CTA derives scale/shift from the fp64 batch sums (training) or the
+ * moving statistics into shared memory; CTA 0 performs the moving-average update and writes mean / invstd (optional, for the
+ * backward pass).  y may be NULL when only the planes are wanted.  C <= 1024. */
+int pnp_bn_apply_fused(const float* z, const double* sum, const double* sumsq, long long M, int C, const float* gamma,
+                       const float* beta, float* moving_mean, float* moving_var, int training, const float* skip, int Cs,
+                       int skip_off, int act, float* y, uint16_t* y_hi, uint16_t* y_lo, float* mean_out, float* invstd_out,
+                       void* stream);
+/* pnp_bn_bwd_finalize + pnp_bn_bwd_apply in ONE launch (dgamma += sum_gx, dbeta += sum_g by CTA 0; sums may be NULL for a
+ * frozen inference-mode batch norm: dz = gamma * invstd * g) */
+int pnp_bn_bwd_apply_fused(const float* g, const float* z, const float* mean, const float* invstd, const float* gamma,
+                           const double* sum_g, const double* sum_gx, long long M, int C, int training,
+                           const pnp_dropout_cfg* drop, float* dgamma, float* dbeta, float* dz, uint16_t* dz_hi,
+                           uint16_t* dz_lo, void* stream);
 /* y = act(z*scale + shift + skip);  skip (optional) has Cs channels placed at channel offset skip_off.
  * y_hi / y_lo (optional): also emit the bf16 (hi, lo) operand planes of y for the next tcgen05 convolution */
 int pnp_bn_act_apply(const float* z, const float* scale, const float* shift, const float* skip, int Cs,

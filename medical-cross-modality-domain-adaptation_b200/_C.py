@@ -21,6 +21,12 @@ class DropCfg(ctypes.Structure):
     _fields_ = [("seed_ptr", c_void_p), ("stream", c_ull), ("keep", c_float)]
 
 
+class TcEpilogue(ctypes.Structure):
+    """pnp_tc_epilogue"""
+    _fields_ = [("scale", c_void_p), ("shift", c_void_p), ("skip", c_void_p), ("skip_C", c_int), ("skip_off", c_int), ("act", c_int),
+                ("y_hi", c_void_p), ("y_lo", c_void_p)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -45,11 +51,14 @@ SIGNATURES = {
     "pnp_split_weight_bf16": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "pnp_split_bf16_pad": [P, P, P, c_ll, c_int, c_int, P],
     "pnp_conv2d_tc_fwd": [P, P, P, P, P, _GEOM, c_int, _DROP, c_int, P, P, P],
+    "pnp_conv2d_tc_fwd_fused": [P, P, P, P, P, _GEOM, c_int, _DROP, c_int, P, P, ctypes.POINTER(TcEpilogue), P],
     "pnp_conv2d_tc_dgrad": [P, P, P, P, P, _GEOM, c_int, c_int, P],
     "pnp_conv2d_tc_wgrad": [P, P, P, P, P, _GEOM, c_int, c_int, P],
     "pnp_bn_stats": [P, c_ll, c_int, P, P, P],
     "pnp_bn_finalize": [P, P, c_ll, c_int, P, P, P, P, c_int, P, P, P, P, P],
     "pnp_bn_act_apply": [P, P, P, P, c_int, c_int, c_int, P, P, P, c_ll, c_int, P],
+    "pnp_bn_apply_fused": [P, P, P, c_ll, c_int, P, P, P, P, c_int, P, c_int, c_int, c_int, P, P, P, P, P, P],
+    "pnp_bn_bwd_apply_fused": [P, P, P, P, P, P, P, c_ll, c_int, c_int, _DROP, P, P, P, P, P, P],
     "pnp_bn_bwd_reduce": [P, P, P, P, P, c_int, P, P, P, c_ll, c_int, P],
     "pnp_bn_bwd_finalize": [P, P, c_ll, c_int, P, P, P, P],
     "pnp_bn_bwd_apply": [P, P, P, P, P, P, c_int, _DROP, P, P, P, c_ll, c_int, P],

@@ -387,6 +387,7 @@ class Trainer(object):
         self._set_mode("D")
         self.d_arena.zero_grad()
         rt.rng.advance()
+        rt.scratch.begin_step()
         with torch.no_grad():
             fm = net.segment(mr_batch, "mr", keep_prob, front_bn=False, joint_bn=False)
             fc_ = net.segment(ct_batch, "ct", keep_prob, front_bn=False, joint_bn=False)
@@ -414,6 +415,7 @@ class Trainer(object):
         self._set_mode("G")
         self.g_arena.zero_grad()
         rt.rng.advance()
+        rt.scratch.begin_step()
         fc_ = net.segment(ct_batch, "ct", keep_prob, front_bn=True, joint_bn=False)
         ct_cls = net.classify(fc_)
         ct_m = net.create_mask_critic(fc_["logits"]) if net.lambda_mask_loss != 0 else None
@@ -513,6 +515,7 @@ class Trainer(object):
         for v in self.d_vars + self.g_vars:
             v.__dict__.pop("_pnp_planes", None)
             v.__dict__.pop("_pnp_wT", None)
+            v.__dict__.pop("_pnp_bncoef", None)      # inference-mode BN coefficients of the DAM (its statistics move in the G step)
 
     def joint_step(self, mr_batch, ct_batch, keep_prob=0.75, ct_batch_g=None):
         """one full adversarial step (D update + clip, then G update); replays the captured graph when there is one.

@@ -611,20 +611,7 @@ bool geom_ok(const pnp_conv_geom* g) {
          g->kw > 0 && g->stride > 0 && g->dil > 0 && g->pad_t >= 0 && g->pad_l >= 0;
 }
 
-PnpDropout make_drop(const pnp_dropout_cfg* d) {
-  PnpDropout r;
-  r.seed_ptr = nullptr;
-  r.stream = 0;
-  r.keep = 1.f;
-  r.inv_keep = 1.f;
-  if (d && d->seed_ptr && d->keep < 1.0f) {
-    r.seed_ptr = d->seed_ptr;
-    r.stream = d->stream;
-    r.keep = d->keep;
-    r.inv_keep = 1.0f / d->keep;
-  }
-  return r;
-}
+PnpDropout make_drop(const pnp_dropout_cfg* d) { return pnp_make_drop(d); }
 
 }  // namespace
 

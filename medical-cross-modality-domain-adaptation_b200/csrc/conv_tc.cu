@@ -169,6 +169,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+__device__ __forceinline__ void split1(float x, uint16_t& hi, uint16_t& lo) {
+  __nv_bfloat16 h = __float2bfloat16_rn(x);
+  __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = __bfloat16_as_ushort(h);
+  lo = __bfloat16_as_ushort(l);
+}
+
 constexpr int MAX_TAPS = 25;
 struct TcArgs {
   int B, OH, OW, Cout;        // full output tensor [B, OH, OW, Cout]
@@ -186,6 +193,15 @@ struct TcArgs {
   PnpDropout drop;
   double* bn_sum;
   double* bn_sumsq;
+  // fused epilogue (forward only): y = act(z * ep_scale[c] + ep_shift[c] + skip) -- inference-mode batch norm, the residual
+  // add with channel-pad skip and the activation folded into the convolution; optional bf16 (hi, lo) planes of y for the next
+  // tcgen05 convolution; out may be null when only the planes are wanted
+  const float* ep_scale;
+  const float* ep_shift;
+  const float* ep_skip;
+  int ep_skip_c, ep_skip_off, ep_act;
+  uint16_t* out_hi;
+  uint16_t* out_lo;
   // phases: a strided data gradient is s*s independent stride-1 convolutions ("phases"), each over its own subset of the
   // taps (every tap belongs to exactly one phase) and its own output sub-grid; all of them run in ONE persistent launch.
   int total_tiles;            // all phases, all (m, n) tiles, times ksplit
@@ -248,10 +264,18 @@ struct TcCfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  // epilogue: 4 warps cover the 128 accumulator rows (TMEM lane quarter = warp_id % 4); tiles >= 64 columns wide use a second
+  // set of 4 warps on the other half of the columns -- a forward epilogue (dropout mask, BN partial statistics, stores) on ONE
+  // warp per SM sub-partition ran longer than the tile's MMAs (r1: fwd 256^2 64->64 at 135 TFLOP/s vs its dgrad at 231)
+  static constexpr int EPI_WARPS = BLOCK_N >= 64 ? 8 : 4;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int EW = BLOCK_N < 32 ? 16 : 32;                 // accumulator columns per tcgen05.ld
+  static constexpr int CW = BLOCK_N / (EPI_WARPS / 4);              // columns per epilogue warp
+  static constexpr int NCH = CW / EW;                               // chunks per epilogue warp and tile
 };
 
 template <int BLOCK_N, int NTERMS, int BK>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__((TcCfg<BLOCK_N, NTERMS, BK>::THREADS), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                float* __restrict__ out, TcArgs a) {
@@ -285,8 +309,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     mbar_init(smem_u32(&tmem_full[0]), 1);
     mbar_init(smem_u32(&tmem_full[1]), 1);
-    mbar_init(smem_u32(&tmem_empty[0]), 128);      // the 128 epilogue threads release an accumulator
-    mbar_init(smem_u32(&tmem_empty[1]), 128);
+    mbar_init(smem_u32(&tmem_empty[0]), 32 * Cfg::EPI_WARPS);      // every epilogue thread releases an accumulator
+    mbar_init(smem_u32(&tmem_empty[1]), 32 * Cfg::EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 1) tcgen05_alloc(smem_u32(tmem_holder), 2 * Cfg::TMEM_COLS);
@@ -379,8 +403,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
     }
   } else {
-    // ================= epilogue warps 2..5 =================
-    const int q = warp & 3;                 // TMEM lane quarter owned by this warp
+    // ================= epilogue warps 2 .. 2+EPI_WARPS =================
+    constexpr int EW = Cfg::EW, NCH = Cfg::NCH;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read (hardware rule: warp_id % 4)
+    const int cb = ((warp - 2) >> 2) * Cfg::CW;     // first accumulator column of this warp
     const int m = q * 32 + lane;            // accumulator row = pixel index inside the tile
     const int per_img = a.th * a.tw;
     const int ni = m / per_img;
@@ -388,8 +414,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int yy = rem / a.tw;
     const int xx = rem - yy * a.tw;
     const bool drop_on = a.drop.seed_ptr != nullptr;
+    const bool bn_on = a.bn_sum != nullptr;
     unsigned long long seed = 0ull;
     if (drop_on) seed = *a.drop.seed_ptr;
+    // BN partial statistics stay in registers (fp64) across all tiles of this CTA that share an n-tile: lane L owns column
+    // L of each of its NCH chunks; one fp64 atomic per column per CTA instead of one per tile (r1: 16 k same-address atomics
+    // per channel and layer on the 256x256 maps)
+    double acc_s[NCH], acc_q[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { acc_s[c] = 0.0; acc_q[c] = 0.0; }
+    int stat_n0 = -1;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -399,13 +433,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const bool valid = (ni < a.tn) && (img < a.B) && (u < tc.U) && (v_ < tc.V);
       const int oy = u * a.out_mul + tc.py, ox = v_ * a.out_mul + tc.px;
       const long long pix = ((long long)img * a.OH + oy) * a.OW + ox;
-      float* orow = out + pix * a.Cout + n0;
+      if (bn_on && n0 != stat_n0) {
+        if (stat_n0 >= 0 && lane < EW) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            atomicAdd(a.bn_sum + stat_n0 + cb + c * EW + lane, acc_s[c]);
+            atomicAdd(a.bn_sumsq + stat_n0 + cb + c * EW + lane, acc_q[c]);
+            acc_s[c] = 0.0; acc_q[c] = 0.0;
+          }
+        }
+        stat_n0 = n0;
+      }
 
       mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
       tcgen05_fence_after();
-      constexpr int EW = BLOCK_N < 32 ? 16 : 32;      // accumulator columns handled per pass
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += EW) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int c0 = cb + c * EW;                  // column inside the tile
+        const long long e0 = pix * a.Cout + n0 + c0; // flat element index of this thread's first output
         uint32_t r[32];
         if (EW == 32) tcgen05_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), r);
         else tcgen05_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), r);
@@ -414,14 +459,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
         for (int i = 0; i < EW; ++i) v[i] = __uint_as_float(r[i]);
         if (drop_on && valid) {
-          const unsigned long long base4 = (unsigned long long)(pix * a.Cout + n0 + c0) >> 2;
+          const unsigned long long base8 = (unsigned long long)e0 >> 3;
 #pragma unroll
-          for (int i = 0; i < EW / 4; ++i) {
-            float4 mu = pnp_dropout_mult4(a.drop, seed, base4 + i);
-            v[4 * i] *= mu.x; v[4 * i + 1] *= mu.y; v[4 * i + 2] *= mu.z; v[4 * i + 3] *= mu.w;
+          for (int i = 0; i < EW / 8; ++i) {
+            float mu[8];
+            pnp_dropout_mult8(a.drop, seed, base8 + i, mu);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[8 * i + j] *= mu[j];
           }
         }
-        if (a.bn_sum != nullptr) {
+        if (bn_on) {
           // per-channel partial sums over this warp's 32 rows: butterfly transpose-reduce
           float s[EW], ss[EW];
 #pragma unroll
@@ -447,25 +494,71 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
           }
           // after the butterfly lane L holds column L (mod EW) of this chunk
-          if (lane < EW) {
-            atomicAdd(a.bn_sum + n0 + c0 + lane, (double)s[0]);
-            atomicAdd(a.bn_sumsq + n0 + c0 + lane, (double)ss[0]);
-          }
+          acc_s[c] += (double)s[0];
+          acc_q[c] += (double)ss[0];
         }
         if (valid) {
-          float4* dst = reinterpret_cast<float4*>(orow + c0);
+          if (a.ep_scale != nullptr) {
+            const float4* sc4 = reinterpret_cast<const float4*>(a.ep_scale + n0 + c0);
+            const float4* sh4 = reinterpret_cast<const float4*>(a.ep_shift + n0 + c0);
 #pragma unroll
-          for (int i = 0; i < EW / 4; ++i) {
-            float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            if (a.ksplit > 1) {
-              atomicAdd(dst + i, o);
-              continue;
+            for (int i = 0; i < EW / 4; ++i) {
+              const float4 sc = __ldg(sc4 + i), sh = __ldg(sh4 + i);
+              v[4 * i] = fmaf(v[4 * i], sc.x, sh.x); v[4 * i + 1] = fmaf(v[4 * i + 1], sc.y, sh.y);
+              v[4 * i + 2] = fmaf(v[4 * i + 2], sc.z, sh.z); v[4 * i + 3] = fmaf(v[4 * i + 3], sc.w, sh.w);
             }
-            if (a.accumulate) {
-              float4 p = dst[i];
-              o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+          }
+          if (a.ep_skip != nullptr) {
+            const float* srow = a.ep_skip + pix * a.ep_skip_c - a.ep_skip_off;
+#pragma unroll
+            for (int i = 0; i < EW / 4; ++i) {
+              const int ch = n0 + c0 + 4 * i;
+              if (ch >= a.ep_skip_off && ch < a.ep_skip_off + a.ep_skip_c) {
+                const float4 sk = __ldg(reinterpret_cast<const float4*>(srow + ch));
+                v[4 * i] += sk.x; v[4 * i + 1] += sk.y; v[4 * i + 2] += sk.z; v[4 * i + 3] += sk.w;
+              }
             }
-            dst[i] = o;
+          }
+          if (a.ep_act == PNP_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < EW; ++i) v[i] = v[i] > 0.f ? v[i] : 0.f;
+          } else if (a.ep_act == PNP_ACT_LRELU) {
+#pragma unroll
+            for (int i = 0; i < EW; ++i) v[i] = v[i] > 0.f ? v[i] : 0.2f * v[i];
+          }
+          if (out != nullptr) {
+            float4* dst = reinterpret_cast<float4*>(out + e0);
+#pragma unroll
+            for (int i = 0; i < EW / 4; ++i) {
+              float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              if (a.ksplit > 1) {
+                atomicAdd(dst + i, o);
+                continue;
+              }
+              if (a.accumulate) {
+                float4 p = dst[i];
+                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+              }
+              dst[i] = o;
+            }
+          }
+          if (a.out_hi != nullptr) {
+            uint4* dh = reinterpret_cast<uint4*>(a.out_hi + e0);
+            uint4* dl = a.out_lo ? reinterpret_cast<uint4*>(a.out_lo + e0) : nullptr;
+#pragma unroll
+            for (int i = 0; i < EW / 8; ++i) {
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint16_t h0, l0, h1, l1;
+                split1(v[8 * i + 2 * j], h0, l0);
+                split1(v[8 * i + 2 * j + 1], h1, l1);
+                h[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                l[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+              }
+              dh[i] = make_uint4(h[0], h[1], h[2], h[3]);
+              if (dl) dl[i] = make_uint4(l[0], l[1], l[2], l[3]);
+            }
           }
         }
       }
@@ -473,6 +566,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       mbar_arrive(smem_u32(&tmem_empty[acc]));       // this thread is done reading accumulator `acc`
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+    if (bn_on && stat_n0 >= 0 && lane < EW) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        atomicAdd(a.bn_sum + stat_n0 + cb + c * EW + lane, acc_s[c]);
+        atomicAdd(a.bn_sumsq + stat_n0 + cb + c * EW + lane, acc_q[c]);
+      }
     }
   }
   __syncthreads();
@@ -486,12 +586,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // operand preparation
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split1(float x, uint16_t& hi, uint16_t& lo) {
-  __nv_bfloat16 h = __float2bfloat16_rn(x);
-  __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-  hi = __bfloat16_as_ushort(h);
-  lo = __bfloat16_as_ushort(l);
-}
 
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, long long n) {
@@ -872,7 +966,7 @@ int launch_tc(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensor
   const int num_sms = sm_count();
   const long long tiles = a.total_tiles;
   dim3 grid((unsigned)(tiles < num_sms ? tiles : num_sms));     // persistent: one CTA per SM walks the tile list
-  conv_tc_kernel<BLOCK_N, NTERMS, BK><<<grid, 192, Cfg::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, y, a);
+  conv_tc_kernel<BLOCK_N, NTERMS, BK><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, y, a);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -892,14 +986,7 @@ int launch_wg(const CUtensorMap& mx_hi, const CUtensorMap& mx_lo, const CUtensor
   return PNP_OK;
 }
 
-PnpDropout make_drop(const pnp_dropout_cfg* d) {
-  PnpDropout r;
-  r.seed_ptr = nullptr; r.stream = 0; r.keep = 1.f; r.inv_keep = 1.f;
-  if (d && d->seed_ptr && d->keep < 1.0f) {
-    r.seed_ptr = d->seed_ptr; r.stream = d->stream; r.keep = d->keep; r.inv_keep = 1.0f / d->keep;
-  }
-  return r;
-}
+PnpDropout make_drop(const pnp_dropout_cfg* d) { return pnp_make_drop(d); }
 
 // one launch of the generalized tap-table convolution: A planes [B, AH, AW, Cin] -> out [B, OH, OW, Cout]
 int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_stride, const uint16_t* w_hi, const uint16_t* w_lo,
@@ -962,7 +1049,8 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
     for (int p = 0; p < a.nphases; ++p) min_taps = a.ph[p].tap_count < min_taps ? a.ph[p].tap_count : min_taps;
     const int min_kb = min_taps * a.kchunks;
     const int sms = sm_count();
-    if (a.total_tiles * 2 <= sms && min_kb >= 8) {
+    const bool fused_ep = a.ep_scale != nullptr || a.ep_skip != nullptr || a.ep_act != PNP_ACT_NONE || a.out_hi != nullptr;
+    if (!fused_ep && a.total_tiles * 2 <= sms && min_kb >= 8) {
       int ks = sms / a.total_tiles;
       if (ks > min_kb / 4) ks = min_kb / 4;
       if (ks > 32) ks = 32;
@@ -1063,10 +1151,11 @@ extern "C" int pnp_split_weight_bf16(const float* w, uint16_t* hi, uint16_t* lo,
   return PNP_OK;
 }
 
-extern "C" int pnp_conv2d_tc_fwd(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo,
-                                 float* y, const pnp_conv_geom* g, int nterms, const pnp_dropout_cfg* drop, int accumulate,
-                                 double* bn_sum, double* bn_sumsq, void* stream) {
-  if (!g || !x_hi || !w_hi || !y) return PNP_ERR_BAD_ARG;
+extern "C" int pnp_conv2d_tc_fwd_fused(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo,
+                                       float* y, const pnp_conv_geom* g, int nterms, const pnp_dropout_cfg* drop, int accumulate,
+                                       double* bn_sum, double* bn_sumsq, const pnp_tc_epilogue* ep, void* stream) {
+  if (!g || !x_hi || !w_hi) return PNP_ERR_BAD_ARG;
+  if (!y && !(ep && ep->y_hi)) return PNP_ERR_BAD_ARG;
   if (nterms != 1 && nterms != 3) return PNP_ERR_BAD_ARG;
   if (nterms == 3 && (!x_lo || !w_lo)) return PNP_ERR_BAD_ARG;
   if ((bn_sum == nullptr) != (bn_sumsq == nullptr)) return PNP_ERR_BAD_ARG;
@@ -1086,7 +1175,28 @@ extern "C" int pnp_conv2d_tc_fwd(const uint16_t* x_hi, const uint16_t* x_lo, con
   a.drop = make_drop(drop);
   a.bn_sum = bn_sum;
   a.bn_sumsq = bn_sumsq;
+  a.ep_scale = nullptr; a.ep_shift = nullptr; a.ep_skip = nullptr; a.ep_skip_c = 0; a.ep_skip_off = 0; a.ep_act = PNP_ACT_NONE;
+  a.out_hi = nullptr; a.out_lo = nullptr;
+  if (ep) {
+    if ((ep->scale == nullptr) != (ep->shift == nullptr)) return PNP_ERR_BAD_ARG;
+    if (accumulate) return PNP_ERR_BAD_ARG;                               // a fused epilogue produces final values
+    if (bn_sum && (ep->scale || ep->skip || ep->act != PNP_ACT_NONE || ep->y_hi)) return PNP_ERR_BAD_ARG;   // batch statistics are of z
+    if (ep->skip && (ep->skip_C % 4 != 0 || ep->skip_off % 4 != 0 || ep->skip_off < 0 || ep->skip_off + ep->skip_C > g->Cout))
+      return PNP_ERR_BAD_ARG;
+    if (ep->y_hi && nterms == 3 && !ep->y_lo) return PNP_ERR_BAD_ARG;
+    a.ep_scale = ep->scale; a.ep_shift = ep->shift;
+    a.ep_skip = ep->skip; a.ep_skip_c = ep->skip_C; a.ep_skip_off = ep->skip_off;
+    a.ep_act = ep->act;
+    a.out_hi = ep->y_hi; a.out_lo = ep->y_lo;
+  }
   return run_tc(x_hi, x_lo, g->H, g->W, g->stride, w_hi, w_lo, (long long)g->kh * g->kw * g->Cout, y, a, nterms, (cudaStream_t)stream);
+}
+
+extern "C" int pnp_conv2d_tc_fwd(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo,
+                                 float* y, const pnp_conv_geom* g, int nterms, const pnp_dropout_cfg* drop, int accumulate,
+                                 double* bn_sum, double* bn_sumsq, void* stream) {
+  if (!y) return PNP_ERR_BAD_ARG;
+  return pnp_conv2d_tc_fwd_fused(x_hi, x_lo, w_hi, w_lo, y, g, nterms, drop, accumulate, bn_sum, bn_sumsq, nullptr, stream);
 }
 
 // dx[B,H,W,Cin] (+)= conv^T(dy, w): `g` is the FORWARD geometry, dy planes [B,Ho,Wo,Cout], weight planes from
@@ -1113,6 +1223,8 @@ extern "C" int pnp_conv2d_tc_dgrad(const uint16_t* dy_hi, const uint16_t* dy_lo,
   a.drop = make_drop(nullptr);
   a.bn_sum = nullptr;
   a.bn_sumsq = nullptr;
+  a.ep_scale = nullptr; a.ep_shift = nullptr; a.ep_skip = nullptr; a.ep_skip_c = 0; a.ep_skip_off = 0; a.ep_act = PNP_ACT_NONE;
+  a.out_hi = nullptr; a.out_lo = nullptr;
   a.U = 0; a.V = 0;
   int np = 0, nt = 0;
   for (int py = 0; py < s; ++py)

@@ -47,14 +47,7 @@ inline int grid_for(long long work_items, int per_block) {
   return (int)b;
 }
 
-PnpDropout make_drop(const pnp_dropout_cfg* d) {
-  PnpDropout r;
-  r.seed_ptr = nullptr; r.stream = 0; r.keep = 1.f; r.inv_keep = 1.f;
-  if (d && d->seed_ptr && d->keep < 1.0f) {
-    r.seed_ptr = d->seed_ptr; r.stream = d->stream; r.keep = d->keep; r.inv_keep = 1.0f / d->keep;
-  }
-  return r;
-}
+PnpDropout make_drop(const pnp_dropout_cfg* d) { return pnp_make_drop(d); }
 
 // ------------------------------------------------------------------------------------------------
 // BN statistics: per-channel sum and sum of squares of z[M, C] (C % 4 == 0, C <= 1024)
@@ -212,6 +205,130 @@ bn_act_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale
     v.x = act_fwd(v.x, act); v.y = act_fwd(v.y, act); v.z = act_fwd(v.z, act); v.w = act_fwd(v.w, act);
     reinterpret_cast<float4*>(y)[i] = v;
     if (p_hi) store_planes(p_hi, p_lo, i, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch norm with the per-channel "finalize" step folded into the streaming kernels: every CTA derives the channel
+// coefficients it needs from the fp64 batch sums (or the moving statistics) into shared memory -- C <= 1024 values, a few
+// hundred flops -- instead of a separate one-CTA kernel per layer (r1: 500 launches of ~5 us per two steps); CTA 0 alone
+// performs the side effects (moving-average update, mean / invstd for the backward pass, dgamma / dbeta).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_apply_fused_kernel(const float* __restrict__ z, const double* __restrict__ sum, const double* __restrict__ sumsq, long long M,
+                      int C, const float* __restrict__ gamma, const float* __restrict__ beta, float* moving_mean, float* moving_var,
+                      int training, const float* __restrict__ skip, int Cs, int skip_off, int act, float* __restrict__ y,
+                      unsigned short* __restrict__ p_hi, unsigned short* __restrict__ p_lo, float* mean_out, float* invstd_out,
+                      long long n4) {
+  extern __shared__ float s_coef[];        // scale[C], shift[C]
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float mu, var;
+    double unb = 0.0;
+    if (training) {
+      double m = sum[c] / (double)M;
+      double v = sumsq[c] / (double)M - m * m;
+      if (v < 0.0) v = 0.0;
+      mu = (float)m;
+      var = (float)v;
+      unb = (M > 1) ? v * ((double)M / (double)(M - 1)) : v;
+    } else {
+      mu = moving_mean[c];
+      var = moving_var[c];
+    }
+    float is = rsqrtf(var + kBnEps);
+    is = is * (1.5f - 0.5f * (var + kBnEps) * is * is);      // one Newton step: rsqrtf is ~2 ulp, the oracle's rsqrt is correctly rounded
+    const float sc = gamma[c] * is;
+    s_coef[c] = sc;
+    s_coef[C + c] = beta[c] - mu * sc;
+    if (blockIdx.x == 0) {
+      if (training) {
+        moving_mean[c] = kBnDecay * moving_mean[c] + (1.f - kBnDecay) * mu;
+        moving_var[c] = kBnDecay * moving_var[c] + (1.f - kBnDecay) * (float)unb;
+      }
+      if (mean_out) { mean_out[c] = mu; invstd_out[c] = is; }
+    }
+  }
+  __syncthreads();
+  const int C4 = C >> 2;
+  const float4* sc4 = reinterpret_cast<const float4*>(s_coef);
+  const float4* sh4 = reinterpret_cast<const float4*>(s_coef + C);
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const int q = (int)(i % C4);
+    float4 v = __ldg(reinterpret_cast<const float4*>(z) + i);
+    const float4 sc = sc4[q], sh = sh4[q];
+    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+    v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    if (skip) {
+      const int c = q * 4 - skip_off;
+      if (c >= 0 && c < Cs) {
+        const long long m = i / C4;
+        const float4 s = __ldg(reinterpret_cast<const float4*>(skip + m * Cs + c));
+        v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+      }
+    }
+    v.x = act_fwd(v.x, act); v.y = act_fwd(v.y, act); v.z = act_fwd(v.z, act); v.w = act_fwd(v.w, act);
+    if (y) reinterpret_cast<float4*>(y)[i] = v;
+    if (p_hi) store_planes(p_hi, p_lo, i, v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_fused_kernel(const float* __restrict__ g, const float* __restrict__ z, const float* __restrict__ mean,
+                          const float* __restrict__ invstd, const float* __restrict__ gamma, const double* __restrict__ sum_g,
+                          const double* __restrict__ sum_gx, long long M, int C, int training, PnpDropout drop, float* dgamma,
+                          float* dbeta, float* __restrict__ dz, unsigned short* __restrict__ p_hi, unsigned short* __restrict__ p_lo,
+                          long long n4) {
+  extern __shared__ float s_coef[];        // k[C] = gamma*invstd, c1[C] = sum_g/M, d[C] = invstd * sum_gx/M, mu[C]
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float is = invstd[c];
+    s_coef[c] = gamma[c] * is;
+    float c1 = 0.f, c2 = 0.f, mu = 0.f;
+    if (sum_g) {
+      const double sg = sum_g[c], sgx = sum_gx[c];
+      if (blockIdx.x == 0) {
+        if (dgamma) dgamma[c] += (float)sgx;
+        if (dbeta) dbeta[c] += (float)sg;
+      }
+      c1 = (float)(sg / (double)M);
+      c2 = (float)(sgx / (double)M);
+    }
+    if (training) mu = mean[c];
+    s_coef[C + c] = c1;
+    s_coef[2 * C + c] = c2;
+    s_coef[3 * C + c] = mu;
+    s_coef[4 * C + c] = is;
+  }
+  __syncthreads();
+  const int C4 = C >> 2;
+  unsigned long long seed = 0ull;
+  const bool drop_on = drop.seed_ptr != nullptr;
+  if (drop_on) seed = *drop.seed_ptr;
+  const float4* k4 = reinterpret_cast<const float4*>(s_coef);
+  const float4* c14 = reinterpret_cast<const float4*>(s_coef + C);
+  const float4* c24 = reinterpret_cast<const float4*>(s_coef + 2 * C);
+  const float4* mu4 = reinterpret_cast<const float4*>(s_coef + 3 * C);
+  const float4* is4 = reinterpret_cast<const float4*>(s_coef + 4 * C);
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const int q = (int)(i % C4);
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    const float4 k = k4[q];
+    float4 o;
+    if (training) {
+      const float4 zv = __ldg(reinterpret_cast<const float4*>(z) + i);
+      const float4 mu = mu4[q], c1 = c14[q], c2 = c24[q], is = is4[q];
+      o.x = k.x * (gv.x - c1.x - (zv.x - mu.x) * is.x * c2.x);
+      o.y = k.y * (gv.y - c1.y - (zv.y - mu.y) * is.y * c2.y);
+      o.z = k.z * (gv.z - c1.z - (zv.z - mu.z) * is.z * c2.z);
+      o.w = k.w * (gv.w - c1.w - (zv.w - mu.w) * is.w * c2.w);
+    } else {
+      o.x = k.x * gv.x; o.y = k.y * gv.y; o.z = k.z * gv.z; o.w = k.w * gv.w;
+    }
+    if (drop_on) {
+      const float4 mk = pnp_dropout_mult4(drop, seed, (unsigned long long)i);
+      o.x *= mk.x; o.y *= mk.y; o.z *= mk.z; o.w *= mk.w;
+    }
+    reinterpret_cast<float4*>(dz)[i] = o;
+    if (p_hi) store_planes(p_hi, p_lo, i, o);
   }
 }
 
@@ -821,6 +938,39 @@ extern "C" int pnp_bn_bwd_apply(const float* g, const float* z, const float* mea
   long long n4 = M * (C / 4);
   bn_bwd_apply_kernel<<<grid_for(n4, 256), 256, 0, S_>>>(g, z, mean, invstd, gamma, coef, training, make_drop(drop), dz, dz_hi, dz_lo,
                                                             n4, C / 4);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_bn_apply_fused(const float* z, const double* sum, const double* sumsq, long long M, int C, const float* gamma,
+                                  const float* beta, float* moving_mean, float* moving_var, int training, const float* skip, int Cs,
+                                  int skip_off, int act, float* y, uint16_t* y_hi, uint16_t* y_lo, float* mean_out,
+                                  float* invstd_out, void* stream) {
+  if (!z || (!y && !y_hi) || !gamma || !beta || !moving_mean || !moving_var || M <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
+  if (training && (!sum || !sumsq)) return PNP_ERR_BAD_ARG;
+  if ((mean_out == nullptr) != (invstd_out == nullptr)) return PNP_ERR_BAD_ARG;
+  if (C % 4 != 0 || C > 1024) return PNP_ERR_UNSUPPORTED;
+  if (skip && (Cs % 4 != 0 || skip_off % 4 != 0 || skip_off < 0 || skip_off + Cs > C)) return PNP_ERR_UNSUPPORTED;
+  long long n4 = M * (C / 4);
+  bn_apply_fused_kernel<<<grid_for(n4, 256), 256, 2 * C * sizeof(float), S_>>>(z, sum, sumsq, M, C, gamma, beta, moving_mean, moving_var,
+                                                                             training, skip, Cs, skip_off, act, y, y_hi, y_lo,
+                                                                             mean_out, invstd_out, n4);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_bn_bwd_apply_fused(const float* g, const float* z, const float* mean, const float* invstd, const float* gamma,
+                                      const double* sum_g, const double* sum_gx, long long M, int C, int training,
+                                      const pnp_dropout_cfg* drop, float* dgamma, float* dbeta, float* dz, uint16_t* dz_hi,
+                                      uint16_t* dz_lo, void* stream) {
+  if (!g || !invstd || !gamma || !dz || M <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
+  if (training && (!z || !mean || !sum_g || !sum_gx)) return PNP_ERR_BAD_ARG;
+  if ((sum_g == nullptr) != (sum_gx == nullptr)) return PNP_ERR_BAD_ARG;
+  if ((dgamma || dbeta) && !sum_g) return PNP_ERR_BAD_ARG;
+  if (C % 4 != 0 || C > 1024) return PNP_ERR_UNSUPPORTED;
+  long long n4 = M * (C / 4);
+  bn_bwd_apply_fused_kernel<<<grid_for(n4, 256), 256, 5 * C * sizeof(float), S_>>>(g, z, mean, invstd, gamma, sum_g, sum_gx, M, C, training,
+                                                                                 make_drop(drop), dgamma, dbeta, dz, dz_hi, dz_lo, n4);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }

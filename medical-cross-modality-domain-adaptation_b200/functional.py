@@ -53,6 +53,11 @@ def same_pad(n, k, s, d=1):
 
 
 def _zeros_f64(n, dev):
+    """zeroed fp64 accumulators: a slice of the per-step scratch pool (ONE memset per step, runtime.Scratch) when it has room,
+    else an individual allocation + fill"""
+    t = rt.scratch.take(n, dev)
+    if t is not None:
+        return t
     t = torch.empty(n, dtype=torch.float64, device=dev)
     call("pnp_fill", ptr(t), 0.0, 2 * n, rt.stream())
     return t
@@ -197,9 +202,20 @@ def _conv_flops(g):
     return 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.kh * g.kw * g.Cin
 
 
-def conv_fwd_raw(xp, W, geom, drop=None, stats=None, keep_planes=False):
+class Epilogue:
+    """what the tcgen05 forward convolution may apply to its accumulator before it leaves the SM (pnp_conv2d_tc_fwd_fused):
+    y = act(z * scale + shift + skip), plus the bf16 operand planes of y"""
+    __slots__ = ("scale", "shift", "skip", "skip_c", "skip_off", "act", "planes")
+
+    def __init__(self, scale=None, shift=None, skip=None, skip_off=0, act=ACT_NONE, planes=0):
+        self.scale, self.shift, self.skip, self.skip_off, self.act, self.planes = scale, shift, skip, skip_off, act, planes
+        self.skip_c = skip.shape[-1] if skip is not None else 0
+
+
+def conv_fwd_raw(xp, W, geom, drop=None, stats=None, keep_planes=False, ep=None):
     """z = conv(xp, W) [* dropout]; xp already mirror-padded if needed.  stats=(sum,sumsq) f64 buffers are filled only
-    when the tcgen05 path can fuse them.  Returns (z, stats_done, (hi, lo) bf16 planes of xp or None)."""
+    when the tcgen05 path can fuse them.  ep (an Epilogue, tcgen05 path only): the returned tensor is the layer's final y and
+    carries its planes.  Returns (z or y, stats_done, (hi, lo) bf16 planes of xp or None, epilogue applied)."""
     z = torch.empty(geom.B, geom.Ho, geom.Wo, geom.Cout, dtype=torch.float32, device=xp.device)
     nt = _tc_mode()
     if nt and _tc_candidate("fwd", geom):
@@ -208,14 +224,38 @@ def conv_fwd_raw(xp, W, geom, drop=None, stats=None, keep_planes=False):
         g_tc = geom
         fuse = stats is not None and FUSE_BN_STATS
         try:
-            _tc_launch("fwd%dx%d.%d.%d" % (geom.Ho, geom.Cin, geom.Cout, geom.kh * geom.stride), _conv_flops(geom), "pnp_conv2d_tc_fwd", ptr(planes[0]), ptr(planes[1]), ptr(whi), ptr(wlo), ptr(z),
-                       ctypes.byref(g_tc), nt, _byref(drop), 0, ptr(stats[0]) if fuse else None, ptr(stats[1]) if fuse else None,
-                       rt.stream())
-            return z, fuse, (planes if keep_planes else None)
+            tag = "fwd%dx%d.%d.%d" % (geom.Ho, geom.Cin, geom.Cout, geom.kh * geom.stride)
+            if ep is None:
+                _tc_launch(tag, _conv_flops(geom), "pnp_conv2d_tc_fwd", ptr(planes[0]), ptr(planes[1]), ptr(whi), ptr(wlo), ptr(z),
+                           ctypes.byref(g_tc), nt, _byref(drop), 0, ptr(stats[0]) if fuse else None, ptr(stats[1]) if fuse else None,
+                           rt.stream())
+                return z, fuse, (planes if keep_planes else None), False
+            yh, yl = _new_planes(z.shape, xp.device, ep.planes) if ep.planes else (None, None)
+            cep = _C.TcEpilogue(ptr(ep.scale), ptr(ep.shift), ptr(ep.skip), ep.skip_c, ep.skip_off, ep.act, ptr(yh), ptr(yl))
+            _tc_launch(tag, _conv_flops(geom), "pnp_conv2d_tc_fwd_fused", ptr(planes[0]), ptr(planes[1]), ptr(whi), ptr(wlo), ptr(z),
+                       ctypes.byref(g_tc), nt, _byref(drop), 0, None, None, ctypes.byref(cep), rt.stream())
+            if ep.planes:
+                z._pnp_planes = (ep.planes, yh, yl)
+            return z, False, (planes if keep_planes else None), True
         except _C.Unsupported:
             _tc_declined.add(_gkey("fwd", geom))
     _tc_launch("simt:fwd%dx%d.%d.%d" % (geom.Ho, geom.Cin, geom.Cout, geom.kh * geom.stride), _conv_flops(geom), "pnp_conv2d_fwd", ptr(xp), ptr(W), ptr(z), ctypes.byref(geom), _byref(drop), 0, rt.stream())
-    return z, False, None
+    return z, False, None, False
+
+
+def _bn_infer_coef(bn):
+    """[scale, shift, mean, invstd] of an inference-mode batch norm (moving statistics), cached per variable versions: a frozen
+    sub-graph (the source segmenter inside every D step) pays for them once, not once per layer call"""
+    key = tuple(getattr(t, "pnp_version", 0) for t in (bn.gamma, bn.beta, bn.moving_mean, bn.moving_var))
+    hit = bn.gamma.__dict__.get("_pnp_bncoef")
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    C = bn.gamma.numel()
+    vec = torch.empty(4, C, dtype=torch.float32, device=bn.gamma.device)
+    call("pnp_bn_finalize", None, None, 1, C, ptr(bn.gamma), ptr(bn.beta), ptr(bn.moving_mean), ptr(bn.moving_var), 0, ptr(vec[0]),
+         ptr(vec[1]), ptr(vec[2]), ptr(vec[3]), rt.stream())
+    bn.gamma.__dict__["_pnp_bncoef"] = (key, vec)
+    return vec
 
 
 def conv_dgrad_raw(dz, W, geom, into=None, dz_planes=None):
@@ -308,6 +348,10 @@ def _geometry(x_shape, w_shape, cfg):
     return p, ConvGeom(B, H, Wd, cin, Ho, Wo, cout, kh, kw, cfg.stride, cfg.dil, pt, pl)
 
 
+# fold inference-mode batch norm + skip + activation into the tcgen05 epilogue (PNP_FUSE_EPILOGUE=0: separate apply kernel)
+FUSE_EPILOGUE = os.environ.get("PNP_FUSE_EPILOGUE", "1") != "0"
+
+
 def layer_forward(x, W, cfg, skip=None, save=True):
     """returns (y, saved) -- `saved` is None when save is False (inference / frozen sub-graph)"""
     x = x.contiguous()
@@ -322,33 +366,52 @@ def layer_forward(x, W, cfg, skip=None, save=True):
     C = geom.Cout
     M = geom.B * geom.Ho * geom.Wo
     bn = cfg.bn
-    stats = None
-    if bn is not None and cfg.bn_training:
-        s = _zeros_f64(2 * C, dev)
-        stats = (s[:C], s[C:])
-    z, stats_done, x_planes = conv_fwd_raw(xp, W, geom, drop, stats, keep_planes=save and W.requires_grad)
+    keep_planes = save and W.requires_grad
+    cs = skip.shape[-1] if skip is not None else 0
     mean = invstd = None
+    # ---- (a) everything after the convolution folded into its epilogue: an inference-mode batch norm whose parameters take
+    #          no gradient (the frozen segmenter inside the D / G steps, evaluation), or a plain activation / skip
+    bn_frozen = bn is not None and not cfg.bn_training and not (save and (bn.gamma.requires_grad or bn.beta.requires_grad))
+    foldable = FUSE_EPILOGUE and _tc_will_run("fwd", geom) and (bn_frozen or (bn is None and (cfg.act != ACT_NONE or skip is not None)))
+    if foldable:
+        coef = _bn_infer_coef(bn) if bn is not None else None
+        ep = Epilogue(coef[0] if bn is not None else None, coef[1] if bn is not None else None, skip, cfg.skip_off, cfg.act,
+                      _want_planes(C))
+        y, _, x_planes, applied = conv_fwd_raw(xp, W, geom, drop, None, keep_planes, ep)
+        if applied:
+            if not save:
+                return y, None
+            saved = {"cfg": cfg, "geom": geom, "p": p, "x_shape": tuple(x.shape), "xp": xp, "xs": x_planes, "W": W, "drop": drop_info,
+                     "z": None, "y": y if cfg.act != ACT_NONE else None, "mean": coef[2] if bn is not None else None,
+                     "invstd": coef[3] if bn is not None else None, "skip_c": cs}
+            return y, saved
+        z, stats_done = y, False            # the launcher declined the tensor-core path: z is the plain convolution
+        stats = None
+    else:
+        stats = None
+        if bn is not None and cfg.bn_training:
+            s = _zeros_f64(2 * C, dev)
+            stats = (s[:C], s[C:])
+        z, stats_done, x_planes, _ = conv_fwd_raw(xp, W, geom, drop, stats, keep_planes)
+    # ---- (b) batch norm (+ skip, activation) as one streaming pass over z; the per-channel finalize lives inside it
     if bn is not None:
-        vec = torch.empty(4, C, dtype=torch.float32, device=dev)
-        scale, shift, mean, invstd = vec[0], vec[1], vec[2], vec[3]
         if cfg.bn_training and not stats_done:
             call("pnp_bn_stats", ptr(z), M, C, ptr(stats[0]), ptr(stats[1]), rt.stream())
-        call("pnp_bn_finalize", ptr(stats[0]) if stats else None, ptr(stats[1]) if stats else None, M, C, ptr(bn.gamma),
-             ptr(bn.beta), ptr(bn.moving_mean), ptr(bn.moving_var), 1 if cfg.bn_training else 0, ptr(scale), ptr(shift),
-             ptr(mean), ptr(invstd), rt.stream())
+        vec = torch.empty(2, C, dtype=torch.float32, device=dev)
+        mean, invstd = vec[0], vec[1]
         if cfg.bn_training:
             bn.moving_mean.pnp_version = getattr(bn.moving_mean, "pnp_version", 0) + 1
+            bn.moving_var.pnp_version = getattr(bn.moving_var, "pnp_version", 0) + 1
         y = torch.empty_like(z)
-        cs = skip.shape[-1] if skip is not None else 0
         nt = _want_planes(C)
         yh, yl = _new_planes(z.shape, dev, nt) if nt else (None, None)
-        call("pnp_bn_act_apply", ptr(z), ptr(scale), ptr(shift), ptr(skip), cs, cfg.skip_off, cfg.act, ptr(y), ptr(yh), ptr(yl), M, C,
-             rt.stream())
+        call("pnp_bn_apply_fused", ptr(z), ptr(stats[0]) if stats else None, ptr(stats[1]) if stats else None, M, C, ptr(bn.gamma),
+             ptr(bn.beta), ptr(bn.moving_mean), ptr(bn.moving_var), 1 if cfg.bn_training else 0, ptr(skip), cs, cfg.skip_off, cfg.act,
+             ptr(y), ptr(yh), ptr(yl), ptr(mean), ptr(invstd), rt.stream())
         if nt:
             y._pnp_planes = (nt, yh, yl)
     elif cfg.act != ACT_NONE or skip is not None:
         y = torch.empty_like(z)
-        cs = skip.shape[-1] if skip is not None else 0
         call("pnp_bn_act_apply", ptr(z), None, None, ptr(skip), cs, cfg.skip_off, cfg.act, ptr(y), None, None, M, C, rt.stream())
     else:
         y = z
@@ -357,7 +420,7 @@ def layer_forward(x, W, cfg, skip=None, save=True):
     saved = {
         "cfg": cfg, "geom": geom, "p": p, "x_shape": tuple(x.shape), "xp": xp, "xs": x_planes, "W": W, "drop": drop_info,
         "z": z if (bn is not None) else None, "y": y if cfg.act != ACT_NONE else None,
-        "mean": mean, "invstd": invstd, "skip_c": skip.shape[-1] if skip is not None else 0,
+        "mean": mean, "invstd": invstd, "skip_c": cs,
     }
     return y, saved
 
@@ -376,19 +439,18 @@ def layer_backward(sv, dy, need_dx=True, dx_into=None, want_dskip=False):
     if bn is not None:
         need_dparam = bn.gamma.requires_grad or bn.beta.requires_grad
         coef = None
+        dgamma = dbeta = None
         if cfg.bn_training or need_dparam:
             g = torch.empty(dy.shape, dtype=torch.float32, device=dev)
             g_owned = True
             sums = _zeros_f64(2 * C, dev)
             call("pnp_bn_bwd_reduce", ptr(dy), ptr(y), ptr(sv["z"]), ptr(sv["mean"]), ptr(sv["invstd"]), cfg.act, ptr(g),
                  ptr(sums[:C]), ptr(sums[C:]), M, C, rt.stream())
-            coef = torch.empty(2 * C, dtype=torch.float32, device=dev)
-            dgamma = dbeta = None
+            coef = sums
             if bn.gamma.requires_grad:
                 dgamma = _grad_slot(bn.gamma)
             if bn.beta.requires_grad:
                 dbeta = _grad_slot(bn.beta)
-            call("pnp_bn_bwd_finalize", ptr(sums[:C]), ptr(sums[C:]), M, C, ptr(dgamma), ptr(dbeta), ptr(coef), rt.stream())
         elif cfg.act != ACT_NONE:
             g = torch.empty(dy.shape, dtype=torch.float32, device=dev)
             g_owned = True
@@ -399,8 +461,9 @@ def layer_backward(sv, dy, need_dx=True, dx_into=None, want_dskip=False):
         nt = _tc_mode()
         want = nt and FUSE_SPLIT and ((W.requires_grad and _tc_will_run("wgrad", geom)) or (need_dx and _tc_will_run("dgrad", geom)))
         dzh, dzl = _new_planes(dy.shape, dev, nt) if want else (None, None)
-        call("pnp_bn_bwd_apply", ptr(g), ptr(sv["z"]), ptr(sv["mean"]), ptr(sv["invstd"]), ptr(bn.gamma), ptr(coef),
-             1 if cfg.bn_training else 0, _byref(drop), ptr(dz), ptr(dzh), ptr(dzl), M, C, rt.stream())
+        call("pnp_bn_bwd_apply_fused", ptr(g), ptr(sv["z"]), ptr(sv["mean"]), ptr(sv["invstd"]), ptr(bn.gamma),
+             ptr(coef[:C]) if coef is not None else None, ptr(coef[C:]) if coef is not None else None, M, C,
+             1 if cfg.bn_training else 0, _byref(drop), ptr(dgamma), ptr(dbeta), ptr(dz), ptr(dzh), ptr(dzl), rt.stream())
         if want:
             dz._pnp_planes = (nt, dzh, dzl)
     else:

@@ -170,6 +170,7 @@ class Trainer(object):
         batch_x [B,256,256,3] fp32, batch_y [B,256,256,num_cls] one-hot fp32, both on the device."""
         self.arena.zero_grad()
         rt.rng.advance()
+        rt.scratch.begin_step()
         logits = self.net.forward(batch_x, keep_prob=keep_prob, main_bn=True, adapt_bn=True)
         wce, dice = self.net.losses(logits, batch_y)
         torch.autograd.backward([wce, dice], [self._g_cross, self._g_dice])
@@ -193,6 +194,7 @@ class Trainer(object):
             for v in self.trainables:          # see adversarial.Trainer._capture: no stale operand caches inside the graph
                 v.__dict__.pop("_pnp_planes", None)
                 v.__dict__.pop("_pnp_wT", None)
+                v.__dict__.pop("_pnp_bncoef", None)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 out = self.train_step(self._gx, self._gy, keep_prob)

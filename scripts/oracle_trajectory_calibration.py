@@ -57,7 +57,7 @@ def adv(n, B=2):
     o32 = OracleAdversarial(P, B, **kw)
     o64 = OracleAdversarial(P, B, dtype=torch.float64, **kw)
     mr, ct = synthetic_images(B, 1234), synthetic_images(B, 4321, 0.3, 0.8)
-    rec = {"dis32": [], "dis64": [], "gen32": [], "gen64": [], "scale": []}
+    rec = {"dis32": [], "dis64": [], "gen32": [], "gen64": [], "scale": [], "dis_err": [], "gen_err": []}
     for s in range(n):
         t0 = time.time()
         d32, d64 = o32.d_step(mr, ct, 1.0), o64.d_step(mr.double(), ct.double(), 1.0)
@@ -68,7 +68,8 @@ def adv(n, B=2):
             g32["gen_loss"], g64["gen_loss"], abs(g32["gen_loss"] - g64["gen_loss"]) / max(abs(g64["gen_loss"]), sc),
             time.time() - t0), flush=True)
         for k, v in (("dis32", d32["dis_loss"]), ("dis64", d64["dis_loss"]), ("gen32", g32["gen_loss"]), ("gen64", g64["gen_loss"]),
-                     ("scale", sc)):
+                     ("scale", sc), ("dis_err", abs(d32["dis_loss"] - d64["dis_loss"]) / max(abs(d64["dis_loss"]), sc)),
+                     ("gen_err", abs(g32["gen_loss"] - g64["gen_loss"]) / max(abs(g64["gen_loss"]), sc))):
             rec[k].append(v)
     return rec
 

@@ -458,3 +458,97 @@ def test_dropout_statistics_and_backward_consistency():
     y3 = L.conv2d(xg.detach(), wg, 0.75)        # same seed + first call site => same mask through the TC epilogue
     assert torch.equal(y3 != 0, y.detach() != 0)
     rt.set_conv_backend("auto")
+
+
+# (B, H, W, Cin, Cout, stride, dil, inc_dim skip) -- one case per accumulator tile width of the tcgen05 kernel
+FUSED_EP_CASES = [
+    (8, 32, 32, 256, 512, 1, 1, True),     # N = 256 tile (8 epilogue warps x 4 chunks), channel-pad skip
+    (3, 32, 32, 64, 128, 1, 2, True),      # N = 128, dilated
+    (2, 64, 64, 64, 64, 1, 1, False),      # N = 64, same-width skip
+    (2, 64, 64, 32, 32, 1, 1, False),      # N = 32 (4 epilogue warps)
+    (2, 64, 64, 16, 16, 1, 1, False),      # N = 16 (16-column tcgen05.ld)
+    (4, 32, 32, 64, 64, 2, 1, None),       # strided, no skip
+]
+
+
+@pytest.mark.parametrize("case", FUSED_EP_CASES)
+@pytest.mark.parametrize("keep_prob", [1.0, 0.75])
+def test_fused_epilogue_equals_separate_bn_apply(case, keep_prob):
+    """inference-mode BN + skip + leaky relu folded into the tcgen05 epilogue (pnp_conv2d_tc_fwd_fused) == convolution followed by
+    the streaming pnp_bn_apply_fused pass: same fp32 operations in the same order (y to 1e-6, its bf16 planes must re-compose y to
+    2^-16); the backward pass (which no longer has z) must give the same gradients."""
+    L, ops, F, rt = _prod()
+    B, H, W, Cin, Cout, stride, dil, inc = case
+    rt.set_conv_backend("tc3")
+    x = randn((B, H, W, Cin), 61)
+    w = randn((3, 3, Cin, Cout), 62, 0.1)
+    skip = None
+    if inc is not None:
+        skip = randn((B, H, W, Cout // 2 if inc else Cout), 63)
+    r = randn((B, -(-H // stride), -(-W // stride), Cout), 64)
+    outs = []
+    for fuse in (True, False):
+        rt.reset_default_graph()
+        rt.manual_seed(77)
+        F.FUSE_EPILOGUE = fuse
+        bn = L.bn_variables("q", Cout, trainable=False)
+        g = torch.Generator().manual_seed(65)
+        with torch.no_grad():
+            bn.gamma.copy_((1 + 0.3 * torch.randn(Cout, generator=g)).to(DEV))
+            bn.beta.copy_((0.2 * torch.randn(Cout, generator=g)).to(DEV))
+            bn.moving_mean.copy_((0.1 * torch.randn(Cout, generator=g)).to(DEV))
+            bn.moving_var.copy_((0.5 + torch.rand(Cout, generator=g)).to(DEV))
+        xg, wg = _var(x), _var(w)
+        sg = _var(skip) if skip is not None else None
+        cfg = F.LayerCfg(stride=stride, dil=dil, keep_prob=keep_prob, bn=bn, bn_training=False, act=F.ACT_LRELU,
+                         skip_off=(Cout // 4 if inc else 0))
+        y = F.conv_layer(xg, wg, cfg, sg)
+        planes = getattr(y, "_pnp_planes", None)
+        y.backward(r.to(DEV))
+        outs.append((y.detach().clone(), planes, xg.grad.clone(), wg.grad.clone(), sg.grad.clone() if sg is not None else None))
+    F.FUSE_EPILOGUE = True
+    (ya, pa, dxa, dwa, dsa), (yb, pb, dxb, dwb, dsb) = outs
+    print("  fused y bit-identical to the separate pass: %s" % bool(torch.equal(ya, yb)))
+    check("y fused vs separate", ya, yb, 1e-6)
+    assert (pa is None) == (pb is None)
+    if pa is not None:
+        check("hi plane", pa[1].float(), pb[1].float(), 1e-2)
+        check("hi+lo planes", pa[1].float() + pa[2].float(), yb, 2e-5)
+    check("dx", dxa, dxb, 1e-5)
+    check("dw", dwa, dwb, 1e-5)
+    if dsa is not None:
+        check("dskip", dsa, dsb, 1e-6)
+    # and against the fp64 oracle
+    T = _oracle()
+    bno = T.BNState(Cout, torch.float64)
+    bno.gamma.data.copy_(rt.graph.vars["q/gamma"].double().cpu())
+    bno.beta.data.copy_(rt.graph.vars["q/beta"].double().cpu())
+    bno.moving_mean = rt.graph.vars["q/moving_mean"].double().cpu()
+    bno.moving_var = rt.graph.vars["q/moving_variance"].double().cpu()
+    if keep_prob == 1.0:
+        z = T.conv2d_raw(x.double(), w.double(), stride=stride, dilation=dil, padding="SAME")
+        zo = T.batch_norm(z, bno, False)
+        if skip is not None:
+            zo = zo + (T.channel_pad_skip(skip.double()) if inc else skip.double())
+        check("y vs fp64 oracle", ya, T.act(zo, True), 2e-4)
+    rt.set_conv_backend("auto")
+
+
+def test_dropout_draw_is_16_bit_exact_for_three_quarters():
+    """the dropout mask keeps an element when its 16-bit Philox draw is below keep*2^16: the kept fraction over 2^22 elements
+    must match keep_prob to binomial accuracy, for 0.75 (exactly representable) and for an awkward value"""
+    L, ops, F, rt = _prod()
+    from pnp_b200._C import call, ptr, DropCfg
+    import ctypes
+    rt.manual_seed(123)
+    n = 1 << 22
+    x = torch.ones(n, device=DEV)
+    for keep in (0.75, 0.6137):
+        y = torch.empty_like(x)
+        d = DropCfg(rt.rng.seed_ptr(), rt.rng.next_stream(), keep)
+        call("pnp_dropout_apply", ptr(x), ptr(y), n, ctypes.byref(d), rt.stream())
+        frac = float((y > 0).float().mean())
+        vals = torch.unique(y)
+        print("  keep %.4f: kept fraction %.5f, values %s" % (keep, frac, vals.tolist()))
+        assert abs(frac - keep) <= 5 * math.sqrt(keep * (1 - keep) / n) + 2.0 ** -16
+        assert len(vals) == 2 and abs(float(vals[1]) - 1.0 / keep) <= 1e-6
