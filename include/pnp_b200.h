@@ -72,6 +72,12 @@ int pnp_conv2d_dgrad(const float* dy, const float* wT, float* dx, const pnp_conv
 /* dw[kh][kw][Cin][Cout] += x (*) dy  (always accumulates: gradient arenas are zeroed per step) */
 int pnp_conv2d_wgrad(const float* x, const float* dy, float* dw, const pnp_conv_geom* g, void* stream);
 int pnp_weight_transpose(const float* w, float* wT, int taps, int Cin, int Cout, void* stream);
+/* The segmenter tail in one launch: y[B, a*r, b*r, Cout] = conv_{kh x kw, SYMMETRIC}(PS_r(X), w) with X = [B, a, b, G*r*r]
+ * (ops.PS ops.py:23-27 + tf.pad SYMMETRIC + tf.nn.conv2d VALID, source_segmenter.py:200-207 / adversarial.py:312-316): the
+ * phase shift and the mirror padding are index maps applied by the tile loader.  w HWIO [kh][kw][G][Cout], Cout in {5, 8},
+ * odd kernels up to 5x5.  order_b1: the reference's batch_size == 1 sub-pixel order (ops.py:11-20). */
+int pnp_ps_mirror_conv_fwd(const float* X, const float* w, float* y, int B, int a, int b, int G, int r, int kh, int kw,
+                           int Cout, int order_b1, void* stream);
 
 /* ---- convolution, tcgen05 + TMA tensor-core path (conv_tc.cu) ----------------------------------
  * Same math as pnp_conv2d_fwd for convolutions whose Cin and Cout are each a multiple of 64, or exactly 32 or 16 (any stride /

@@ -53,7 +53,24 @@ def build(force=False, verbose=True):
             list(ex.map(run, jobs))
     if force or jobs or _stale(LIB, objs):
         run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-cudart", "static"])
+    build_io(force, run)
     return LIB
+
+
+IO_LIB = os.path.join(HERE, "libpnp_io.so")
+
+
+def build_io(force=False, run=None):
+    """libpnp_io.so: the host-side TFRecord decoder (plain C, gcc; no CUDA dependency) -- include/pnp_io.h"""
+    src = os.path.join(CSRC, "tfrecord_io.c")
+    hdr = os.path.join(os.path.dirname(HERE), "include", "pnp_io.h")
+    if force or _stale(IO_LIB, [src, hdr]):
+        cmd = [os.environ.get("CC", "gcc"), "-O3", "-std=c11", "-fPIC", "-shared", "-Wall", "-o", IO_LIB, src]
+        if run is None:
+            subprocess.run(cmd, check=True)
+        else:
+            run(cmd)
+    return IO_LIB
 
 
 if __name__ == "__main__":

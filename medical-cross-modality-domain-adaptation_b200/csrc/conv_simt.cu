@@ -606,6 +606,94 @@ __global__ void weight_transpose_kernel(const float* __restrict__ w, float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Segmenter tail in ONE kernel:  logits = conv5x5_SYMMETRIC( PS_r( X ) )     (source_segmenter.py:200-207, ops.py:23-27)
+// X = conv10 output [B, a, b, G*r*r]; the phase shift (depth-to-space) and the mirror padding are pure index maps, so the
+// tile loader gathers straight from X:
+//     flat[n, Y, X_, g] = X[n, Y/r, X_/r, g*r*r + (X_%r)*r + (Y%r)]      (batch >= 2; the B == 1 order swaps the two residues)
+//     padded[py, px]    = flat[mirror(py - p), mirror(px - p)]            (tf.pad SYMMETRIC: edge included)
+// which removes the [B, 256, 256, 40] round trip through HBM twice over (r1: phase_shift 166 us + mirror_pad 108 us + conv 190 us
+// per call, three calls per adversarial step).  Lanes run along Y%r first, then X_%r: for r = 8 a warp reads 128 contiguous bytes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int mirror_i(int i, int n) { return i < 0 ? (-i - 1) : (i >= n ? 2 * n - 1 - i : i); }
+
+template <int NO>
+__global__ void __launch_bounds__(256)
+ps_mirror_conv_kernel(const float* __restrict__ X, const float* __restrict__ w, float* __restrict__ y, int B, int a, int b, int G,
+                      int r, int kh, int kw, int order_b1) {
+  constexpr int T = 32, CC = 8, HALO = T + 4;            // kernels up to 5x5
+  __shared__ float s_x[CC][HALO][HALO + 1];
+  __shared__ float s_w[25][CC][NO];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * T, y0 = blockIdx.y * T, n = blockIdx.z;
+  const int H = a * r, W = b * r, rr = r * r;
+  const int ph = kh / 2, pw = kw / 2;
+  const int hh = T + kh - 1, hw = T + kw - 1;
+  const int nby = (hh + 7) >> 3, nbx = (hw + 3) >> 2;      // loader patches of 8 (y) x 4 (x) halo pixels = one warp
+  const long long Ctot = (long long)G * rr;
+  float acc[4][NO];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int o = 0; o < NO; ++o) acc[j][o] = 0.f;
+  const float* Xn = X + (long long)n * a * b * Ctot;
+  for (int c0 = 0; c0 < G; c0 += CC) {
+    __syncthreads();
+    const int total = nby * nbx * 32 * CC;
+    for (int e = threadIdx.x; e < total; e += 256) {
+      const int ly = e & 7, lx = (e >> 3) & 3;
+      int rest = e >> 5;
+      const int c = rest % CC;
+      rest /= CC;
+      const int bx = rest % nbx, by = rest / nbx;
+      const int py = by * 8 + ly, px = bx * 4 + lx;
+      if (py < hh && px < hw) {
+        float v = 0.f;
+        if (c0 + c < G) {
+          const int Y = mirror_i(y0 + py - ph, H), Xc = mirror_i(x0 + px - pw, W);
+          const int iy = Y / r, qy = Y - iy * r, ix = Xc / r, qx = Xc - ix * r;
+          const int sub = order_b1 ? (qy * r + qx) : (qx * r + qy);
+          v = __ldg(Xn + ((long long)iy * b + ix) * Ctot + (long long)(c0 + c) * rr + sub);
+        }
+        s_x[c][py][px] = v;
+      }
+    }
+    for (int p = threadIdx.x; p < kh * kw * CC * NO; p += 256) {
+      const int o = p % NO, c = (p / NO) % CC, t = p / (NO * CC);
+      s_w[t][c][o] = (c0 + c < G) ? __ldg(w + ((long long)t * G + c0 + c) * NO + o) : 0.f;
+    }
+    __syncthreads();
+    for (int ky = 0; ky < kh; ++ky)
+      for (int kx = 0; kx < kw; ++kx) {
+        const int t = ky * kw + kx;
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+          float wv[NO];
+#pragma unroll
+          for (int o = 0; o < NO; ++o) wv[o] = s_w[t][c][o];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float av = s_x[c][ty + 8 * j + ky][tx + kx];
+#pragma unroll
+            for (int o = 0; o < NO; ++o) acc[j][o] = fmaf(av, wv[o], acc[j][o]);
+          }
+        }
+      }
+  }
+  const int ox = x0 + tx;
+  if (ox < W) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int oy = y0 + ty + 8 * j;
+      if (oy < H) {
+        float* dst = y + (((long long)n * H + oy) * W + ox) * NO;
+#pragma unroll
+        for (int o = 0; o < NO; ++o) dst[o] = acc[j][o];
+      }
+    }
+  }
+}
+
 bool geom_ok(const pnp_conv_geom* g) {
   return g && g->B > 0 && g->H > 0 && g->W > 0 && g->Cin > 0 && g->Ho > 0 && g->Wo > 0 && g->Cout > 0 && g->kh > 0 &&
          g->kw > 0 && g->stride > 0 && g->dil > 0 && g->pad_t >= 0 && g->pad_l >= 0;
@@ -639,6 +727,19 @@ extern "C" int pnp_conv2d_fwd(const float* x, const float* w, float* y, const pn
     return PNP_OK;
   }
   return dispatch_gather<false>(x, w, y, a, (cudaStream_t)stream);
+}
+
+extern "C" int pnp_ps_mirror_conv_fwd(const float* X, const float* w, float* y, int B, int a, int b, int G, int r, int kh, int kw,
+                                      int Cout, int order_b1, void* stream) {
+  if (!X || !w || !y || B <= 0 || a <= 0 || b <= 0 || G <= 0 || r <= 0) return PNP_ERR_BAD_ARG;
+  if (kh > 5 || kw > 5 || kh < 1 || kw < 1 || (kh & 1) == 0 || (kw & 1) == 0 || B > 65535) return PNP_ERR_UNSUPPORTED;
+  if (kh / 2 > a * r || kw / 2 > b * r) return PNP_ERR_UNSUPPORTED;
+  dim3 grid(pnp_cdiv(b * r, 32), pnp_cdiv(a * r, 32), B);
+  if (Cout == 5) ps_mirror_conv_kernel<5><<<grid, 256, 0, (cudaStream_t)stream>>>(X, w, y, B, a, b, G, r, kh, kw, order_b1);
+  else if (Cout == 8) ps_mirror_conv_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(X, w, y, B, a, b, G, r, kh, kw, order_b1);
+  else return PNP_ERR_UNSUPPORTED;
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
 }
 
 extern "C" int pnp_conv2d_dgrad(const float* dy, const float* wT, float* dx, const pnp_conv_geom* g,

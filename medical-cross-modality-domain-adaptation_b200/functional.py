@@ -642,6 +642,51 @@ def phase_shift(X, r, n_channel, batch_size):
     return _PhaseShiftFn.apply(X, r, n_channel, 1 if batch_size == 1 else 0)
 
 
+class _TailFn(torch.autograd.Function):
+    """The segmenter tail PS(r) -> SYMMETRIC pad -> k x k convolution (source_segmenter.py:200-207) as ONE kernel: the phase
+    shift and the mirror padding are index maps inside the convolution's tile loader (pnp_ps_mirror_conv_fwd).  Used when the
+    output filter takes no gradient (every adversarial step, evaluation); the gradient w.r.t. X runs through the stand-alone
+    kernels (transposed conv -> mirror-pad fold -> inverse phase shift)."""
+
+    @staticmethod
+    def forward(ctx, X, w, r, G, order_b1):
+        X = X.contiguous()
+        B, a, b, C = X.shape
+        kh, kw, cin, cout = w.shape
+        if C != G * r * r or cin != G:
+            raise ValueError("tail: %d channels cannot be split into %d groups of %d (filter expects %d)" % (C, G, r * r, cin))
+        y = torch.empty(B, a * r, b * r, cout, dtype=X.dtype, device=X.device)
+        flops = 2.0 * B * a * r * b * r * cout * kh * kw * cin
+        _tc_launch("simt:tail%dx%d.%d.%d" % (a * r, cin, cout, kh), flops, "pnp_ps_mirror_conv_fwd", ptr(X), ptr(w), ptr(y), B, a, b, G, r,
+                   kh, kw, cout, order_b1, rt.stream())
+        ctx.w = w
+        ctx.meta = (B, a, b, G, r, order_b1)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, a, b, G, r, o = ctx.meta
+        w = ctx.w
+        kh, kw, cin, cout = w.shape
+        p = kh // 2
+        H, W = a * r, b * r
+        geom = ConvGeom(B, H + 2 * p, W + 2 * p, cin, H, W, cout, kh, kw, 1, 1, 0, 0)
+        dxp = conv_dgrad_raw(dy.contiguous(), w, geom)
+        dflat = torch.empty(B, H, W, cin, dtype=dy.dtype, device=dy.device)
+        call("pnp_mirror_pad_bwd", ptr(dxp), ptr(dflat), B, H, W, cin, p, rt.stream())
+        dX = torch.empty(B, a, b, G * r * r, dtype=dy.dtype, device=dy.device)
+        call("pnp_phase_shift_bwd", ptr(dflat), ptr(dX), B, a, b, G, r, G, 0, 1, o, rt.stream())
+        return dX, None, None, None, None
+
+
+# PNP_FUSE_TAIL=0: phase shift, mirror pad and output convolution as three kernels
+FUSE_TAIL = os.environ.get("PNP_FUSE_TAIL", "1") != "0"
+
+
+def tail_ps_conv(X, w, r, n_channel, batch_size):
+    return _TailFn.apply(X, w, r, n_channel, 1 if batch_size == 1 else 0)
+
+
 class _DiscInputFn(torch.autograd.Function):
     """adversarial.py:325-335 in one gather: [PS(c4,2) x3 | PS(c6,4) | PS(b7,8) | PS(c9,8) | logits | argmax]"""
 

@@ -125,6 +125,11 @@ class SegmenterTail:
         self.weights = [self.w10, self.w11]
 
     def run(self, c9, keep_prob, batch_size):
+        from . import functional as F
         conv10 = L.conv2d(c9, self.w10, keep_prob_=keep_prob, padding='SYMMETRIC')
+        if F.FUSE_TAIL and not self.w11.requires_grad and self.w11.shape[3] in (5, 8):
+            # frozen output filter (adversarial steps, evaluation): PS + mirror pad + convolution in one kernel
+            ops._check(conv10, batch_size)
+            return F.tail_ps_conv(conv10, self.w11, 8, self.num_cls * 8, batch_size)
         flat = ops.PS(conv10, r=8, n_channel=self.num_cls * 8, batch_size=batch_size)
         return L.conv2d(flat, self.w11, keep_prob_=1., padding='SYMMETRIC')

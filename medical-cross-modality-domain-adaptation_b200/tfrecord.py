@@ -8,30 +8,23 @@ Each example carries 8 features: dsize_dim0/1/2, lsize_dim0/1/2 (int64) and data
 (:341) -- harmless because both are 3.
 """
 import struct
+import threading
 
 import numpy as np
 import torch
 
-# ---- CRC32C (Castagnoli), table driven -----------------------------------------------------------------------------
-_POLY = 0x82F63B78
-_TABLE = []
-for _i in range(256):
-    _c = _i
-    for _ in range(8):
-        _c = (_c >> 1) ^ _POLY if _c & 1 else _c >> 1
-    _TABLE.append(_c)
+from . import _io
 
 
+# ---- CRC32C (Castagnoli): libpnp_io.so (SSE4.2 crc32 instruction, slicing-by-8 fallback) -----------------------------
 def crc32c(data):
-    c = 0xFFFFFFFF
-    for b in data:
-        c = _TABLE[(c ^ b) & 0xFF] ^ (c >> 8)
-    return c ^ 0xFFFFFFFF
+    data = bytes(data)
+    return int(_io.lib.pnp_crc32c(data, len(data)))
 
 
 def masked_crc(data):
-    c = crc32c(data)
-    return ((((c >> 15) | (c << 17)) & 0xFFFFFFFF) + 0xA282EAD8) & 0xFFFFFFFF
+    data = bytes(data)
+    return int(_io.lib.pnp_masked_crc32c(data, len(data)))
 
 
 # ---- protobuf wire helpers --------------------------------------------------------------------------------------------
@@ -139,16 +132,60 @@ def decode_slice(payload, raw_size=(256, 256, 3)):
     return vol.copy(), lab[:, :, 1].astype(np.int64)
 
 
+def load_slice(path, record_index=0, check_crc=True, raw_size=(256, 256, 3), image=None, label=None):
+    """one example of a TFRecord file -> (image float32 [H,W,C], label int64 [H,W]) decoded natively
+    (pnp_tfrecord_load_file: framing + CRC + protobuf + decode_raw + the reference's slicing), into the given arrays"""
+    H, W, C = raw_size
+    if image is None:
+        image = np.empty(raw_size, np.float32)
+    if label is None:
+        label = np.empty((H, W), np.int64)
+    rc = _io.lib.pnp_tfrecord_load_file(path.encode(), record_index, 1 if check_crc else 0, image.ctypes.data, label.ctypes.data,
+                                        H, W, C, 1)
+    _io.check(rc, path)
+    return image, label
+
+
 class TFRecordSource:
     """Drop-in for data.SyntheticSource: shuffled batches (images [B,256,256,3] fp32, labels [B,256,256] int64) in pinned
-    host memory from a list of single-example TFRecord files (lists/*_list), like tf.train.shuffle_batch."""
+    host memory from a list of single-example TFRecord files (lists/*_list), like the reference's input pipeline
+    (source_segmenter.py:331-355): `num_threads` reader threads (reference: 4 QueueRunner threads) walk a shuffled file order
+    and decode natively with the GIL released into a shuffle buffer of `capacity` examples; next() draws a batch at random once
+    more than `min_after_dequeue` examples would remain (tf.train.shuffle_batch(capacity=120, min_after_dequeue=30)) and hands
+    it out in one of two alternating pinned buffers, so the previous batch's host->device copy may still be in flight.
+    num_threads=0: synchronous, deterministic order (tests)."""
 
-    def __init__(self, file_list, batch_size, seed=0):
+    def __init__(self, file_list, batch_size, seed=0, num_threads=4, capacity=120, min_after_dequeue=30, check_crc=True,
+                 raw_size=(256, 256, 3)):
         self.files = list(file_list)
+        if not self.files:
+            raise ValueError("empty TFRecord file list")
         self.B = batch_size
+        self.raw_size = tuple(raw_size)
+        self.check_crc = check_crc
         self.rng = np.random.RandomState(seed)
         self.order = self.rng.permutation(len(self.files))
         self.pos = 0
+        self.capacity = max(capacity, min_after_dequeue + batch_size)
+        self.min_after = min_after_dequeue
+        H, W, C = self.raw_size
+        pin = torch.cuda.is_available()
+        self._out = [(torch.empty(batch_size, H, W, C, dtype=torch.float32, pin_memory=pin),
+                      torch.empty(batch_size, H, W, dtype=torch.int64, pin_memory=pin)) for _ in range(2)]
+        self._flip = 0
+        self.examples_read = 0
+        self._threads = []
+        self._stop = False
+        self._error = None
+        if num_threads > 0:
+            self._lock = threading.Lock()
+            self._cv = threading.Condition(self._lock)
+            self._free = [(np.empty(self.raw_size, np.float32), np.empty((H, W), np.int64)) for _ in range(self.capacity)]
+            self._ready = []
+            for _ in range(num_threads):
+                t = threading.Thread(target=self._worker, daemon=True)
+                t.start()
+                self._threads.append(t)
 
     def _next_file(self):
         if self.pos >= len(self.order):
@@ -158,20 +195,68 @@ class TFRecordSource:
         self.pos += 1
         return f
 
+    def _worker(self):
+        try:
+            while True:
+                with self._cv:
+                    while not self._free and not self._stop:
+                        self._cv.wait()
+                    if self._stop:
+                        return
+                    slot = self._free.pop()
+                    path = self._next_file()
+                load_slice(path, 0, self.check_crc, self.raw_size, slot[0], slot[1])      # native, GIL released
+                with self._cv:
+                    self._ready.append(slot)
+                    self.examples_read += 1
+                    self._cv.notify_all()
+        except Exception as e:      # noqa: BLE001 -- surface reader errors in next() instead of dying silently
+            with self._cv:
+                self._error = e
+                self._cv.notify_all()
+
     def next(self):
-        xs, ys = [], []
-        while len(xs) < self.B:
-            for payload in read_records(self._next_file()):
-                x, y = decode_slice(payload)
-                xs.append(x)
-                ys.append(y)
-                if len(xs) == self.B:
-                    break
-        x = torch.from_numpy(np.stack(xs))
-        y = torch.from_numpy(np.stack(ys))
-        if torch.cuda.is_available():
-            x, y = x.pin_memory(), y.pin_memory()
+        x, y = self._out[self._flip]
+        self._flip ^= 1
+        if not self._threads:
+            for i in range(self.B):
+                load_slice(self._next_file(), 0, self.check_crc, self.raw_size, x[i].numpy(), y[i].numpy())
+                self.examples_read += 1
+            return x, y
+        need = min(self.min_after + self.B, self.capacity)
+        with self._cv:
+            while len(self._ready) < need and self._error is None:
+                self._cv.wait()
+            if self._error is not None:
+                raise self._error
+            picks = []
+            for _ in range(self.B):
+                j = int(self.rng.randint(len(self._ready)))
+                self._ready[j], self._ready[-1] = self._ready[-1], self._ready[j]
+                picks.append(self._ready.pop())
+        xn, yn = x.numpy(), y.numpy()
+        for i, (im, lb) in enumerate(picks):
+            xn[i] = im
+            yn[i] = lb
+        with self._cv:
+            self._free.extend(picks)
+            self._cv.notify_all()
         return x, y
+
+    def close(self):
+        if self._threads:
+            with self._cv:
+                self._stop = True
+                self._cv.notify_all()
+            for t in self._threads:
+                t.join(timeout=2)
+            self._threads = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---- writer (tests / synthetic dataset export) ---------------------------------------------------------------------

@@ -255,6 +255,98 @@ def test_tfrecord_reader_round_trip_and_reference_slicing(tmp_path):
         list(tfr.read_records(files[0]))
 
 
+def test_io_library_exports_every_declared_symbol_and_crc32c_known_answers():
+    """include/pnp_io.h <-> libpnp_io.so <-> _io.SIGNATURES, and the CRC32C known-answer vectors of RFC 3720 B.4 on BOTH
+    code paths (SSE4.2 instruction / slicing-by-8 tables)"""
+    from pnp_b200 import _io
+    hdr = open(os.path.join(ROOT, "include", "pnp_io.h")).read()
+    declared = sorted(set(re.findall(r"\b(pnp_[a-z0-9_]+)\s*\(", hdr)))
+    lib = ctypes.CDLL(_io.LIB_PATH)
+    assert declared and not [n for n in declared if not hasattr(lib, n)]
+    assert set(declared) == set(_io.SIGNATURES), set(declared) ^ set(_io.SIGNATURES)
+    kat = [(b"123456789", 0xE3069283), (bytes(32), 0x8A9136AA), (b"\xff" * 32, 0x62A8AB43), (bytes(range(32)), 0x46DD794E),
+           (bytes(range(31, -1, -1)), 0x113FDB5C), (b"", 0x00000000)]
+    for data, want in kat:
+        assert _io.lib.pnp_crc32c(data, len(data)) == want, (data[:8], hex(want))
+        assert _io.lib.pnp_crc32c_sw(data, len(data)) == want
+    rng = np.random.RandomState(3)
+    for n in (1, 7, 8, 9, 63, 1000, 65537):          # unaligned heads / tails
+        buf = rng.bytes(n + 3)
+        for off in (0, 1, 3):
+            view = buf[off:off + n]
+            assert _io.lib.pnp_crc32c(view, n) == _io.lib.pnp_crc32c_sw(view, n)
+    assert _io.lib.pnp_masked_crc32c(b"123456789", 9) == ((((0xE3069283 >> 15) | (0xE3069283 << 17)) & 0xFFFFFFFF) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def test_native_tfrecord_decoder_matches_the_python_parser_and_rejects_corruption(tmp_path):
+    """pnp_tfrecord_load_file (C: framing + CRC + protobuf + decode_raw + middle-slice label) == the hand-written Python parser
+    that is itself pinned to the reference's next_batch (test_reference_graph_trace.py); multi-record files; error codes"""
+    from pnp_b200 import tfrecord as tfr, _io
+    rng = np.random.RandomState(1)
+    exs = [(rng.randn(256, 256, 3).astype(np.float32), rng.randint(0, 5, (256, 256, 3)).astype(np.float32)) for _ in range(3)]
+    multi = str(tmp_path / "multi.tfrecords")
+    tfr.write_record(multi, [tfr.encode_example(i, l) for i, l in exs])
+    raw = open(multi, "rb").read()
+    assert _io.lib.pnp_tfrecord_count(raw, len(raw)) == 3
+    for k, payload in enumerate(tfr.read_records(multi)):
+        xi, yi = tfr.decode_slice(payload)
+        xn, yn = tfr.load_slice(multi, k)
+        assert np.array_equal(xi, xn) and np.array_equal(yi, yn) and yn.dtype == np.int64
+        assert np.array_equal(yn, exs[k][1][:, :, 1].astype(np.int64))
+    with pytest.raises(IOError, match="index"):
+        tfr.load_slice(multi, 3)
+    bad = bytearray(raw)
+    bad[5000] ^= 0x01
+    p2 = str(tmp_path / "bad.tfrecords")
+    open(p2, "wb").write(bytes(bad))
+    with pytest.raises(IOError, match="CRC"):
+        tfr.load_slice(p2, 0)
+    tfr.load_slice(p2, 0, check_crc=False)                   # the flipped bit sits inside the image bytes: decodable without the check
+    open(p2, "wb").write(raw[:100000])
+    with pytest.raises(IOError, match="truncated"):
+        tfr.load_slice(p2, 0)
+    with pytest.raises(IOError, match="open"):
+        tfr.load_slice(str(tmp_path / "missing.tfrecords"), 0)
+    other = str(tmp_path / "other.tfrecords")                # a valid record that does not follow the schema
+    tfr.write_record(other, [b"\x0a\x02\x0a\x00"])
+    with pytest.raises(IOError, match="schema"):
+        tfr.load_slice(other, 0)
+
+
+def test_threaded_tfrecord_source_shuffles_and_delivers_every_example(tmp_path):
+    """4 reader threads + shuffle buffer (tf.train.shuffle_batch semantics): every file is delivered, batches are assembled in
+    alternating pinned buffers, a reader error surfaces in next()"""
+    from pnp_b200 import tfrecord as tfr
+    files = []
+    for i in range(12):
+        img = np.full((256, 256, 3), float(i), np.float32)
+        lab = np.full((256, 256, 3), float(i % 5), np.float32)
+        p = str(tmp_path / ("e%02d.tfrecords" % i))
+        tfr.write_record(p, [tfr.encode_example(img, lab)])
+        files.append(p)
+    src = tfr.TFRecordSource(files, batch_size=4, seed=5, num_threads=4, capacity=8, min_after_dequeue=4)
+    seen, orders = [], []
+    for _ in range(9):                                        # 36 examples = 3 epochs of 12
+        x, y = src.next()
+        ids = [int(v) for v in x[:, 0, 0, 0]]
+        assert all(int(y[j, 0, 0]) == ids[j] % 5 for j in range(4))
+        seen += ids
+        orders.append(ids)
+    src.close()
+    assert set(seen) == set(range(12)) and max(seen.count(i) for i in range(12)) <= 4
+    assert orders[0] != sorted(orders[0]) or orders[1] != sorted(orders[1])            # shuffled
+    # synchronous mode is deterministic
+    a = tfr.TFRecordSource(files, 4, seed=7, num_threads=0)
+    b = tfr.TFRecordSource(files, 4, seed=7, num_threads=0)
+    assert torch.equal(a.next()[0], b.next()[0])
+    os.remove(files[3])
+    bad = tfr.TFRecordSource(files, 4, seed=5, num_threads=2, capacity=8, min_after_dequeue=4)
+    with pytest.raises(IOError):
+        for _ in range(8):
+            bad.next()
+    bad.close()
+
+
 def test_conv_routing_table_matches_the_kernel_contract():
     """host-side routing (functional._tc_candidate) against the channel contract documented in include/pnp_b200.h:
     forward / data gradient on tcgen05 when Cin and Cout are each 64k, 32 or 16; weight gradient when Cin in {32, 64k}

@@ -552,3 +552,28 @@ def test_dropout_draw_is_16_bit_exact_for_three_quarters():
         print("  keep %.4f: kept fraction %.5f, values %s" % (keep, frac, vals.tolist()))
         assert abs(frac - keep) <= 5 * math.sqrt(keep * (1 - keep) / n) + 2.0 ** -16
         assert len(vals) == 2 and abs(float(vals[1]) - 1.0 / keep) <= 1e-6
+
+
+@pytest.mark.parametrize("B", [1, 2, 3])
+def test_tail_ps_mirror_conv_equals_three_kernels(B):
+    """pnp_ps_mirror_conv_fwd (phase shift + SYMMETRIC pad folded into the output convolution's tile loader) == ops.PS ->
+    layers.conv2d(padding='SYMMETRIC') as separate kernels == the fp64 oracle; gradient w.r.t. the feature map too.
+    B == 1 exercises the reference's transposed sub-pixel order (ops.py:11-20)."""
+    L, ops, F, rt = _prod()
+    T = _oracle()
+    a = b = 6                    # 48 x 48 output: two tiles per axis, mirrored borders on all sides
+    G, r, nc = 40, 8, 5
+    X = randn((B, a, b, G * r * r), 71)
+    w = randn((5, 5, G, nc), 72, 0.1)
+    rr = randn((B, a * r, b * r, nc), 73)
+    Xo, wo = X.double().requires_grad_(True), w.double()
+    yo = T.conv2d(T.PS(Xo, r, G, B), wo, 1.0, padding="SYMMETRIC")
+    (yo * rr.double()).sum().backward()
+    Xg, wg = _var(X), _var(w, False)
+    y = F.tail_ps_conv(Xg, wg, r, G, B)
+    check("fused tail vs oracle", y, yo, 1e-5)
+    y.backward(rr.to(DEV))
+    check("dX", Xg.grad, Xo.grad, 1e-5)
+    Xs = _var(X, False)
+    ys = L.conv2d(ops.PS(Xs, r, n_channel=G, batch_size=B), wg, 1.0, padding="SYMMETRIC")
+    check("fused tail vs separate kernels", y, ys, 1e-6)

@@ -61,6 +61,13 @@ class _Tracer(object):
         h = self._conv(x, W1, cfg1, "none")
         return self._conv(h, W2, cfg2, ("pad%d" % cfg2.skip_off) if cfg2.skip_off else "identity")
 
+    def tail_ps_conv(self, X, w, r, n_channel, batch_size):
+        # the product's seventh kernel entry point: ops.PS -> conv2d(padding='SYMMETRIC', keep_prob 1) in one launch
+        # (functional._TailFn, numerically pinned by tests/test_ops_gpu.py::test_tail_ps_mirror_conv_equals_three_kernels);
+        # structurally it IS the reference's two calls (source_segmenter.py:200-207), so it is recorded as such
+        flat = self.phase_shift(X, r, n_channel, batch_size)
+        return self.conv_layer(flat, w, self.F.LayerCfg(padding="SYMMETRIC", keep_prob=1.0))
+
     def max_pool2(self, x):
         self.events.append({"op": "maxpool", "k": 2, "stride": 2, "in": list(x.shape[1:]), "out": [x.shape[1] // 2, x.shape[2] // 2, x.shape[3]]})
         y = torch.empty(x.shape[0], x.shape[1] // 2, x.shape[2] // 2, x.shape[3], device="meta")
@@ -115,7 +122,7 @@ def product():
     from pnp_b200 import adversarial as A, functional as F, runtime as rt
     net = A.Full_DRN(3, 5, B, cost_kwargs=dict(COST), network_config=dict(CFG))
     tr = _Tracer(F, rt)
-    saved = {k: getattr(F, k) for k in ("conv_layer", "res_block", "max_pool2", "phase_shift", "disc_input", "fc")}
+    saved = {k: getattr(F, k) for k in ("conv_layer", "res_block", "max_pool2", "phase_shift", "disc_input", "fc", "tail_ps_conv")}
     for k in saved:
         setattr(F, k, getattr(tr, k))
     try:
@@ -251,7 +258,7 @@ def product_segmenter():
     args = REF["source_segmenter"]["ctor_args"]
     net = S.Full_DRN(3, 5, B, cost_kwargs={"cross_flag": True, "miu_cross": 1.0, "dice_flag": True, "miu_dice": 1.0, "regularizer": 1e-4}, **args)
     tr = _Tracer(F, rt)
-    saved = {k: getattr(F, k) for k in ("conv_layer", "res_block", "max_pool2", "phase_shift", "disc_input", "fc")}
+    saved = {k: getattr(F, k) for k in ("conv_layer", "res_block", "max_pool2", "phase_shift", "disc_input", "fc", "tail_ps_conv")}
     for k in saved:
         setattr(F, k, getattr(tr, k))
     try:
