@@ -189,6 +189,10 @@ int pnp_phase_shift_fwd(const float* X, float* out, int B, int a, int b, int G, 
 int pnp_phase_shift_bwd(const float* dout, float* dX, int B, int a, int b, int G, int r, int Ctot, int coff,
                         int ntile, int order_b1, void* stream);
 /* out[..., coff:coff+C] = logits ; out[..., coff+C] = float(argmax logits)  (adversarial.py:334-335) */
+/* The whole discriminator input (adversarial.py:325-335) in one gather: out[B,H,W,Ctot] = [PS_r(src_0) tiled ntile_0 times | ... |
+ * logits | float(argmax logits)], src_s = [B, a_s, b_s, G_s*r*r] with a_s*r == H; up to 4 sources, Ctot % 4 == 0, Ctot <= 64. */
+int pnp_disc_input_fwd(const float* const* srcs, const int* a, const int* b, const int* G, const int* ntile, int nsrc,
+                       const float* logits, int NC, float* out, int B, int H, int W, int r, int order_b1, void* stream);
 int pnp_logits_argmax_concat(const float* logits, float* out, long long P, int C, int Ctot, int coff, void* stream);
 /* out[m, 0:C] (+)= in[m, coff:coff+C]  -- strided channel slice used by the gather's backward */
 /* (pnp_channel_slice above) */

@@ -308,7 +308,9 @@ class Full_DRN(object):
                     if o1[0] in ("r", "R", "d"):
                         for sa, sb in zip(o1[3], o2[3]):
                             for leaf in ("beta", "gamma", "moving_mean", "moving_variance"):
-                                rt.graph.vars["%s/%s/%s" % (s2, sb, leaf)].copy_(rt.graph.vars["%s/%s/%s" % (s1, sa, leaf)])
+                                dst = rt.graph.vars["%s/%s/%s" % (s2, sb, leaf)]
+                                dst.copy_(rt.graph.vars["%s/%s/%s" % (s1, sa, leaf)])
+                                dst.pnp_version += 1           # cached inference-mode BN coefficients key on the versions
 
 
 class Trainer(object):

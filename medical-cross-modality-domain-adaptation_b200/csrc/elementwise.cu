@@ -581,6 +581,57 @@ phase_shift_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dX, i
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The discriminator input (adversarial.py:325-335) in ONE gather: [PS(c4) x3 | PS(c6) | PS(b7) | PS(c9) | logits | argmax]
+// -> [B, H, W, Ctot].  One thread per (pixel, 4 output channels): the 128-byte pixel rows are written once, fully coalesced
+// (r1: five partial-row scatter launches + one concat per call).
+// ------------------------------------------------------------------------------------------------
+struct DiscPlan {
+  const float* src[4];
+  int a[4], b[4], G[4];
+  signed char ch_src[64];     // per output channel: source id 0..3, -1 = logits, -2 = argmax(logits)
+  signed char ch_g[64];       // group (or logits channel)
+};
+
+__global__ void __launch_bounds__(256)
+disc_input_kernel(DiscPlan plan, const float* __restrict__ logits, int NC, float* __restrict__ out, int B, int H, int W, int Ctot,
+                  int r, int order_b1) {
+  const int Q = Ctot >> 2;
+  const long long total = (long long)B * H * W * Q;
+  const int rr = r * r;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int q = (int)(i % Q);
+    const long long pix = i / Q;
+    const int x = (int)(pix % W);
+    long long t = pix / W;
+    const int y = (int)(t % H);
+    const int n = (int)(t / H);
+    const int iy = y / r, ry = y - iy * r, ix = x / r, rx = x - ix * r;
+    const int sub = order_b1 ? (ry * r + rx) : (rx * r + ry);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int ch = q * 4 + e;
+      const int sid = plan.ch_src[ch], g = plan.ch_g[ch];
+      if (sid >= 0) {
+        v[e] = __ldg(plan.src[sid] + (((long long)n * plan.a[sid] + iy) * plan.b[sid] + ix) * ((long long)plan.G[sid] * rr) + g * rr + sub);
+      } else if (sid == -1) {
+        v[e] = __ldg(logits + pix * NC + g);
+      } else {
+        const float* l = logits + pix * NC;
+        float best = __ldg(l);
+        int arg = 0;
+        for (int c = 1; c < NC; ++c) {
+          const float lv = __ldg(l + c);
+          if (lv > best) { best = lv; arg = c; }     // tf.argmax: lowest index on ties
+        }
+        v[e] = (float)arg;
+      }
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 logits_argmax_concat_kernel(const float* __restrict__ logits, float* __restrict__ out, long long P, int C, int Ctot, int coff) {
   for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += (long long)gridDim.x * 256) {
@@ -1072,6 +1123,37 @@ extern "C" int pnp_phase_shift_bwd(const float* dout, float* dX, int B, int a, i
     return PNP_ERR_BAD_ARG;
   long long total = (long long)B * a * b * G * r * r;
   phase_shift_bwd_kernel<<<grid_for(total, 256 * 8), 256, 0, S_>>>(dout, dX, B, a, b, G, r, Ctot, coff, ntile, order_b1);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_disc_input_fwd(const float* const* srcs, const int* a, const int* b, const int* G, const int* ntile, int nsrc,
+                                  const float* logits, int NC, float* out, int B, int H, int W, int r, int order_b1, void* stream) {
+  if (!srcs || !a || !b || !G || !ntile || nsrc < 1 || nsrc > 4 || !logits || !out || B <= 0 || r <= 0 || NC <= 0 || NC > kMaxC)
+    return PNP_ERR_BAD_ARG;
+  DiscPlan plan;
+  int ch = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    if (!srcs[s] || a[s] * r != H || b[s] * r != W || G[s] <= 0 || ntile[s] < 1) return PNP_ERR_BAD_ARG;
+    plan.src[s] = srcs[s]; plan.a[s] = a[s]; plan.b[s] = b[s]; plan.G[s] = G[s];
+    for (int t = 0; t < ntile[s]; ++t)
+      for (int g = 0; g < G[s]; ++g) {
+        if (ch >= 64) return PNP_ERR_UNSUPPORTED;
+        plan.ch_src[ch] = (signed char)s; plan.ch_g[ch] = (signed char)g; ++ch;
+      }
+  }
+  for (int s = nsrc; s < 4; ++s) { plan.src[s] = nullptr; plan.a[s] = plan.b[s] = plan.G[s] = 0; }
+  for (int c = 0; c < NC; ++c) {
+    if (ch >= 64) return PNP_ERR_UNSUPPORTED;
+    plan.ch_src[ch] = -1; plan.ch_g[ch] = (signed char)c; ++ch;
+  }
+  if (ch >= 64) return PNP_ERR_UNSUPPORTED;
+  plan.ch_src[ch] = -2; plan.ch_g[ch] = 0; ++ch;
+  const int Ctot = ch;
+  if (Ctot % 4 != 0) return PNP_ERR_UNSUPPORTED;
+  for (int c = Ctot; c < 64; ++c) { plan.ch_src[c] = -1; plan.ch_g[c] = 0; }
+  const long long total = (long long)B * H * W * (Ctot / 4);
+  disc_input_kernel<<<grid_for(total, 256), 256, 0, S_>>>(plan, logits, NC, out, B, H, W, Ctot, r, order_b1);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }

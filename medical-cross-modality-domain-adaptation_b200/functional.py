@@ -703,9 +703,15 @@ class _DiscInputFn(torch.autograd.Function):
             off += G * ntile
         ctot = off + NC + 1
         out = torch.empty(B, H, W, ctot, dtype=logits.dtype, device=logits.device)
-        for t, (a, b, G, coff, ntile) in zip(srcs, plan):
-            call("pnp_phase_shift_fwd", ptr(t), ptr(out), B, a, b, G, r, ctot, coff, ntile, order_b1, rt.stream())
-        call("pnp_logits_argmax_concat", ptr(logits), ptr(out), B * H * W, NC, ctot, off, rt.stream())
+        if ctot % 4 == 0 and ctot <= 64:
+            n = len(srcs)
+            ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
+            ia = lambda k: (ctypes.c_int * n)(*[pl[k] for pl in plan])
+            call("pnp_disc_input_fwd", ptrs, ia(0), ia(1), ia(2), ia(4), n, ptr(logits), NC, ptr(out), B, H, W, r, order_b1, rt.stream())
+        else:
+            for t, (a, b, G, coff, ntile) in zip(srcs, plan):
+                call("pnp_phase_shift_fwd", ptr(t), ptr(out), B, a, b, G, r, ctot, coff, ntile, order_b1, rt.stream())
+            call("pnp_logits_argmax_concat", ptr(logits), ptr(out), B * H * W, NC, ctot, off, rt.stream())
         ctx.meta = (B, H, W, NC, r, order_b1, plan, ctot, off)
         return out
 

@@ -156,6 +156,9 @@ class _BNOnly(torch.autograd.Function):
         call("pnp_bn_finalize", ptr(stats[:C]) if training else None, ptr(stats[C:]) if training else None, M, C, ptr(bn.gamma),
              ptr(bn.beta), ptr(bn.moving_mean), ptr(bn.moving_var), 1 if training else 0, ptr(vec[0]), ptr(vec[1]), ptr(vec[2]),
              ptr(vec[3]), rt.stream())
+        if training:
+            bn.moving_mean.pnp_version = getattr(bn.moving_mean, "pnp_version", 0) + 1
+            bn.moving_var.pnp_version = getattr(bn.moving_var, "pnp_version", 0) + 1
         y = torch.empty_like(x)
         call("pnp_bn_act_apply", ptr(x), ptr(vec[0]), ptr(vec[1]), None, 0, 0, F.ACT_NONE, ptr(y), None, None, M, C, rt.stream())
         ctx.save_for_backward(x)

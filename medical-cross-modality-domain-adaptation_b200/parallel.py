@@ -78,6 +78,7 @@ class DataParallel:
                 if getattr(v, "pnp_kind", "") == "bn_moving":
                     dist.all_reduce(v, op=dist.ReduceOp.SUM)
                     v.mul_(1.0 / self.world)
+                    v.pnp_version = getattr(v, "pnp_version", 0) + 1
 
     def save_checkpoint(self, save_fn):
         """rank 0 alone writes (save_fn must write atomically); every rank waits for the file to be complete"""
