@@ -404,6 +404,20 @@ def run_ours(a):
         F.PROFILE = None
         roof = _roofline(recs_all, nprof, ms_step, a)
 
+    if a.profile and rank == 0 and world == 1:
+        # per-kernel device time of two eager steps (CUPTI through torch.profiler: lighter than ncu, same kernel names)
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(2):
+                w.step_resident(i, eager=True)
+            torch.cuda.synchronize()
+        evs = prof.key_averages()
+        tot = sum(e.device_time_total for e in evs)
+        for e in sorted(evs, key=lambda e: -e.device_time_total)[:60]:
+            print("[prof] %-110s x%4d %9.3f ms %5.1f%%" % (e.key.replace("(anonymous namespace)::", "")[:110], e.count // 2,
+                                                            e.device_time_total / 1e3 / 2, 100.0 * e.device_time_total / tot), file=sys.stderr)
+        print("[prof] total device time per step %.3f ms in %d launches" % (tot / 1e3 / 2, sum(e.count for e in evs) // 2), file=sys.stderr)
+
     dp = None
     if world > 1 and a.config in (3, 4, 5):
         dp = _dp_check(w, dist)
@@ -622,6 +636,7 @@ def main():
     ap.add_argument("--ref-budget", type=int, default=150, help="--impl reference: wall-clock budget in seconds")
     ap.add_argument("--graph", dest="graph", action="store_true", default=True, help="replay the step as one CUDA graph (default)")
     ap.add_argument("--no-graph", dest="graph", action="store_false")
+    ap.add_argument("--profile", action="store_true", help="per-kernel device-time table of two eager steps (torch.profiler) on stderr")
     a = ap.parse_args()
     if a.batch is None:
         a.batch = WORKLOADS[a.config][1]

@@ -348,6 +348,8 @@ class Trainer(object):
         self.g_arena = optim.Arena(self.g_vars)
         # clip_op: every cls var whose name contains "Variable" (conv + FC weights of D and M)
         clip = [0.03 if "Variable" in v.pnp_name else 0.0 for v in self.d_vars]
+        self.dp.attach(self.d_arena)
+        self.dp.attach(self.g_arena)
         self.dis_optimizer = optim.RMSProp(self.d_arena, lr=lr, clip=clip, **self.opt_kwargs)
         self.gen_optimizer = optim.RMSProp(self.g_arena, lr=lr, **self.opt_kwargs)
         self._refresh_weight_decay()
@@ -400,6 +402,7 @@ class Trainer(object):
             ct_m = net.create_mask_critic(fc_["logits"])
             mr_m = net.create_mask_critic(fm["logits"])
         terms = net.dis_loss_terms(ct_cls, mr_cls, ct_m, mr_m)
+        self.dp.begin_backward(self.d_arena, overlap=apply)
         torch.autograd.backward([t for t, _ in terms], [self._one, self._lam][:len(terms)])
         if apply:
             self.d_apply()
@@ -407,7 +410,7 @@ class Trainer(object):
 
     def d_apply(self):
         """the data-parallel exchange + update of a D step: ONE all-reduce over the gradient arena, then RMSProp + clip"""
-        scale = self.dp.allreduce(self.d_arena.grad)
+        scale = self.dp.finish_backward(self.d_arena)
         self.dis_optimizer.step(grad_scale=scale)
         self.global_step += 1
 
@@ -422,13 +425,14 @@ class Trainer(object):
         ct_cls = net.classify(fc_)
         ct_m = net.create_mask_critic(fc_["logits"]) if net.lambda_mask_loss != 0 else None
         terms = net.gen_loss_terms(ct_cls, ct_m)
+        self.dp.begin_backward(self.g_arena, overlap=apply)
         torch.autograd.backward([t for t, _ in terms], [self._one, self._lam][:len(terms)])
         if apply:
             self.g_apply()
         return terms
 
     def g_apply(self):
-        scale = self.dp.allreduce(self.g_arena.grad)
+        scale = self.dp.finish_backward(self.g_arena)
         self.gen_optimizer.step(grad_scale=scale)
         self.global_step += 1
 

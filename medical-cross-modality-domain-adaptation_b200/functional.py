@@ -36,7 +36,7 @@ def _tc_launch(tag, flops, name, *args):
     call(name, *args)
     e1.record()
     kern = "simt"
-    if name in ("pnp_conv2d_tc_fwd", "pnp_conv2d_tc_dgrad"):
+    if name in ("pnp_conv2d_tc_fwd", "pnp_conv2d_tc_fwd_fused", "pnp_conv2d_tc_dgrad"):
         n_, k_, s_ = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
         _C.lib.pnp_tc_last_config(ctypes.byref(n_), ctypes.byref(k_), ctypes.byref(s_))
         kern = "conv_tc_kernel<%d, %d, %d>" % (n_.value, 1 if _tc_mode() == 1 else 3, k_.value)
@@ -293,10 +293,12 @@ def conv_wgrad_raw(xp, dz, W, geom, x_planes=None, dz_planes=None):
         try:
             _tc_launch("wgr%dx%d.%d.%d" % (geom.Ho, geom.Cin, geom.Cout, geom.kh * geom.stride), _conv_flops(geom), "pnp_conv2d_tc_wgrad", ptr(xh), ptr(xl), ptr(dh), ptr(dl), ptr(W.grad),
                        ctypes.byref(geom), nt, cp if cp != geom.Cin else 0, rt.stream())
+            _grad_written(W)
             return
         except _C.Unsupported:
             _tc_declined.add(_gkey("wgrad", geom))
     _tc_launch("simt:wgr%dx%d.%d.%d" % (geom.Ho, geom.Cin, geom.Cout, geom.kh * geom.stride), _conv_flops(geom), "pnp_conv2d_wgrad", ptr(xp), ptr(dz), ptr(W.grad), ctypes.byref(geom), rt.stream())
+    _grad_written(W)
 
 
 def _tc_will_run(kind, geom):
@@ -464,6 +466,10 @@ def layer_backward(sv, dy, need_dx=True, dx_into=None, want_dskip=False):
         call("pnp_bn_bwd_apply_fused", ptr(g), ptr(sv["z"]), ptr(sv["mean"]), ptr(sv["invstd"]), ptr(bn.gamma),
              ptr(coef[:C]) if coef is not None else None, ptr(coef[C:]) if coef is not None else None, M, C,
              1 if cfg.bn_training else 0, _byref(drop), ptr(dgamma), ptr(dbeta), ptr(dz), ptr(dzh), ptr(dzl), rt.stream())
+        if dgamma is not None:
+            _grad_written(bn.gamma)
+        if dbeta is not None:
+            _grad_written(bn.beta)
         if want:
             dz._pnp_planes = (nt, dzh, dzl)
     else:
@@ -505,6 +511,14 @@ def layer_backward(sv, dy, need_dx=True, dx_into=None, want_dskip=False):
     if DEBUG_HOOK is not None:
         DEBUG_HOOK(sv, dy, g, dz, dx)
     return dx, dskip
+
+
+def _grad_written(v):
+    """a gradient contribution to `v` has been launched: data-parallel reducers start a bucket's all-reduce when its last
+    contribution of the step is in (parallel.BucketedAllReduce)"""
+    hook = getattr(v, "_pnp_grad_hook", None)
+    if hook is not None:
+        hook(v)
 
 
 def _grad_slot(v):
@@ -820,6 +834,8 @@ class _FCFn(torch.autograd.Function):
         dw = _grad_slot(w) if w.requires_grad else None
         if dx is not None or dw is not None:
             call("pnp_fc_bwd", ptr(x), ptr(w), ptr(dout.contiguous()), ptr(dx), ptr(dw), B, F, rt.stream())
+            if dw is not None:
+                _grad_written(w)
         return dx, None
 
 

@@ -158,6 +158,7 @@ class Trainer(object):
         tv = [v for v in rt.global_variables() if v.pnp_trainable]
         self.trainables = tv
         self.arena = optim.Arena(tv)
+        self.dp.attach(self.arena)
         lr = self.opt_kwargs.pop("learning_rate", 1e-3)
         self._new_LR = lr
         self.optimizer = optim.Adam(self.arena, lr=lr, weight_decay=self.net.weight_decay_table(tv), **self.opt_kwargs)
@@ -173,8 +174,9 @@ class Trainer(object):
         rt.scratch.begin_step()
         logits = self.net.forward(batch_x, keep_prob=keep_prob, main_bn=True, adapt_bn=True)
         wce, dice = self.net.losses(logits, batch_y)
+        self.dp.begin_backward(self.arena)
         torch.autograd.backward([wce, dice], [self._g_cross, self._g_dice])
-        scale = self.dp.allreduce(self.arena.grad)
+        scale = self.dp.finish_backward(self.arena)
         self.optimizer.step(grad_scale=scale)
         self.global_step += 1
         return wce, dice

@@ -375,3 +375,73 @@ def test_conv_routing_table_matches_the_kernel_contract():
     # producers emit operand planes exactly for the tensors a tcgen05 convolution can consume
     assert [bool(F._want_planes(c)) for c in (16, 32, 64, 320, 5, 40, 48)] == ([True, True, True, True, False, False, False]
                                                                                 if F._tc_mode() else [False] * 7)
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import pnp_b200  # noqa: F401
+    from pnp_b200 import parallel, optim
+    torch.manual_seed(0)
+    vs = [torch.zeros(n) for n in (3000, 10, 5000, 700, 1, 2048, 900)]
+    for i, v in enumerate(vs):
+        v.pnp_name = "v%d" % i
+    arena = optim.Arena(vs)
+    dp = parallel.DataParallel()
+    red = dp.attach(arena, n_buckets=3)
+    assert red is not None and len(red.bounds) >= 2 and red.bounds[0][0] == 0 and red.bounds[-1][1] == arena.total
+    res = []
+    for step in range(3):
+        arena.grad.zero_()
+        dp.begin_backward(arena)
+        # "backward": variables complete from the back, v5 receives two contributions per step (a shared critic weight)
+        for i in (6, 5, 5, 4, 3, 2, 1, 0):
+            vs[i].grad.add_(float(rank + 1) * (i + 1 + step))
+            v = vs[i]
+            v._pnp_grad_hook(v)
+            if step > 0 and i == 2:
+                launched_early = list(red.launched)
+        scale = dp.finish_backward(arena)
+        res.append([float(v.grad.flatten()[0]) for v in vs])
+    # passive mode: local gradients stay local until finish
+    arena.grad.zero_()
+    dp.begin_backward(arena, overlap=False)
+    for i in (6, 5, 5, 4, 3, 2, 1, 0):
+        vs[i].grad.add_(float(rank + 1))
+        vs[i]._pnp_grad_hook(vs[i])
+    local = float(vs[6].grad[0])
+    dp.finish_backward(arena)
+    out[rank] = (res, scale, launched_early, local, float(vs[6].grad[0]), red.expected)
+    # a step with an extra contribution must raise instead of reducing a half-written bucket
+    dp.begin_backward(arena)
+    err = None
+    try:
+        for i in (6, 6):
+            vs[i]._pnp_grad_hook(vs[i])
+        for i in (6,):
+            vs[i]._pnp_grad_hook(vs[i])
+    except RuntimeError as e:
+        err = str(e)
+    out["err%d" % rank] = err
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_overlapped_allreduce_gloo_world_size_2():
+    """parallel.BucketedAllReduce: calibration step = one call; later steps launch each bucket as soon as its last contribution
+    is in (before the 'backward' has finished), results equal the plain sum; passive mode keeps local gradients"""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_bucket_worker, args=(2, 29700 + os.getpid() % 2000, out), nprocs=2, join=True)
+    for r in (0, 1):
+        res, scale, launched_early, local, after, expected = out[r]
+        assert scale == 0.5 and sum(expected.values()) == 8
+        for step in range(3):
+            for i in range(7):
+                mult = 2 if i == 5 else 1
+                assert res[step][i] == 3.0 * mult * (i + 1 + step), (step, i, res[step][i])
+        assert any(launched_early), "no bucket was reduced before the backward pass ended"
+        assert local == float(r + 1) and after == 3.0
+        assert out["err%d" % r] is not None and "more gradient contributions" in out["err%d" % r]
