@@ -639,6 +639,37 @@ ps_mirror_conv_kernel(const float* __restrict__ X, const float* __restrict__ w, 
   const float* Xn = X + (long long)n * a * b * Ctot;
   for (int c0 = 0; c0 < G; c0 += CC) {
     __syncthreads();
+    if (r == 8 && !order_b1) {
+      // fast loader (r = 8, batch >= 2 sub-pixel order): one (source pixel, group) = 64 contiguous floats = the 8x8 block
+      // flat[8*iy + q][8*ix + p] = X[.., g*64 + p*8 + q].  A warp reads the 256-byte line with one float2 per lane (fully
+      // coalesced) and scatters it into the tile; blocks outside the image are the mirror images of the border blocks.
+      const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
+      const int bY0 = (y0 - ph) >> 3, bX0 = (x0 - pw) >> 3;            // first source block touched (floor: may be -1)
+      const int nbY = ((y0 - ph + hh - 1) >> 3) - bY0 + 1, nbX = ((x0 - pw + hw - 1) >> 3) - bX0 + 1;
+      const int items = nbY * nbX * CC;
+      const int p_ = ln >> 2, q_ = (ln & 3) * 2;                          // this lane's elements: (p_, q_) and (p_, q_ + 1)
+      for (int it = wid; it < items; it += 8) {
+        const int c = it % CC;
+        const int rest = it / CC;
+        const int sx = rest % nbX, sy = rest / nbX;
+        const int bY = bY0 + sy, bX = bX0 + sx;
+        const int sbY = bY < 0 ? 0 : (bY >= a ? a - 1 : bY), sbX = bX < 0 ? 0 : (bX >= b ? b - 1 : bX);
+        float2 v = make_float2(0.f, 0.f);
+        if (c0 + c < G)
+          v = __ldg(reinterpret_cast<const float2*>(Xn + ((long long)sbY * b + sbX) * Ctot + (long long)(c0 + c) * 64 + ln * 2));
+        // padded coordinate of image row Yi: itself inside the image; mirrored (edge included) for the blocks beyond the border
+        const int Xi = sbX * 8 + p_;
+        const int Xp = bX < 0 ? (-1 - Xi) : (bX >= b ? 2 * W - 1 - Xi : Xi);
+        const int px = Xp - (x0 - pw);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int Yi = sbY * 8 + q_ + e;
+          const int Yp = bY < 0 ? (-1 - Yi) : (bY >= a ? 2 * H - 1 - Yi : Yi);
+          const int py = Yp - (y0 - ph);
+          if (py >= 0 && py < hh && px >= 0 && px < hw) s_x[c][py][px] = e ? v.y : v.x;
+        }
+      }
+    } else {
     const int total = nby * nbx * 32 * CC;
     for (int e = threadIdx.x; e < total; e += 256) {
       const int ly = e & 7, lx = (e >> 3) & 3;
@@ -657,6 +688,7 @@ ps_mirror_conv_kernel(const float* __restrict__ X, const float* __restrict__ w, 
         }
         s_x[c][py][px] = v;
       }
+    }
     }
     for (int p = threadIdx.x; p < kh * kw * CC * NO; p += 256) {
       const int o = p % NO, c = (p / NO) % CC, t = p / (NO * CC);
