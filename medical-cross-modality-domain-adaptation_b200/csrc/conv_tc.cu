@@ -1009,9 +1009,12 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
   // (96 KB stages leave room for only two of them, 48 KB stages for four)
   int bk = (a.Cin % 64 == 0) ? 64 : ((a.Cin % 32 == 0) ? 32 : 16);
   {
+    // measured (r2d): fp32-grade 3-term path 4 x 48 KB stages (BK 32) beat 2 x 96 KB; the one-term bf16 path of config 5 is the
+    // other way round: 4 x 48 KB stages of BK 64 (twice the MMA work per barrier round trip) 37.5 ms/step vs 8 x 24 KB 41.1 ms
     static int bk256_env = -1;
-    if (bk256_env < 0) { const char* e = getenv("PNP_TC_BK256"); bk256_env = e ? atoi(e) : 32; }
-    if (block_n == 256 && bk256_env == 32) bk = 32;
+    if (bk256_env < 0) { const char* e = getenv("PNP_TC_BK256"); bk256_env = e ? atoi(e) : 0; }
+    const int bk256 = bk256_env ? bk256_env : (nterms == 1 ? 64 : 32);
+    if (block_n == 256 && bk256 == 32) bk = 32;
     if (block_n == 128 && bk == 32) block_n = 64;      // (no 128 x 32-wide instantiation)
   }
   a.kchunks = a.Cin / bk;

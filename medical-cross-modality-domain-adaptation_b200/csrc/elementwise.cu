@@ -597,15 +597,15 @@ __global__ void __launch_bounds__(256)
 disc_input_kernel(DiscPlan plan, const float* __restrict__ logits, int NC, float* __restrict__ out, int B, int H, int W, int Ctot,
                   int r, int order_b1) {
   const int Q = Ctot >> 2;
-  const long long total = (long long)B * H * W * Q;
+  const unsigned total = (unsigned)B * H * W * Q;          // < 2^31 (checked by the launcher): 32-bit index arithmetic throughout
   const int rr = r * r;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int q = (int)(i % Q);
-    const long long pix = i / Q;
-    const int x = (int)(pix % W);
-    long long t = pix / W;
-    const int y = (int)(t % H);
-    const int n = (int)(t / H);
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+    const int q = (int)(i % (unsigned)Q);
+    const unsigned pix = i / (unsigned)Q;
+    const int x = (int)(pix % (unsigned)W);
+    const unsigned t = pix / (unsigned)W;
+    const int y = (int)(t % (unsigned)H);
+    const int n = (int)(t / (unsigned)H);
     const int iy = y / r, ry = y - iy * r, ix = x / r, rx = x - ix * r;
     const int sub = order_b1 ? (ry * r + rx) : (rx * r + ry);
     float v[4];
@@ -614,11 +614,11 @@ disc_input_kernel(DiscPlan plan, const float* __restrict__ logits, int NC, float
       const int ch = q * 4 + e;
       const int sid = plan.ch_src[ch], g = plan.ch_g[ch];
       if (sid >= 0) {
-        v[e] = __ldg(plan.src[sid] + (((long long)n * plan.a[sid] + iy) * plan.b[sid] + ix) * ((long long)plan.G[sid] * rr) + g * rr + sub);
+        v[e] = __ldg(plan.src[sid] + (size_t)((n * plan.a[sid] + iy) * plan.b[sid] + ix) * (size_t)(plan.G[sid] * rr) + g * rr + sub);
       } else if (sid == -1) {
-        v[e] = __ldg(logits + pix * NC + g);
+        v[e] = __ldg(logits + (size_t)pix * NC + g);
       } else {
-        const float* l = logits + pix * NC;
+        const float* l = logits + (size_t)pix * NC;
         float best = __ldg(l);
         int arg = 0;
         for (int c = 1; c < NC; ++c) {
@@ -1153,6 +1153,7 @@ extern "C" int pnp_disc_input_fwd(const float* const* srcs, const int* a, const 
   if (Ctot % 4 != 0) return PNP_ERR_UNSUPPORTED;
   for (int c = Ctot; c < 64; ++c) { plan.ch_src[c] = -1; plan.ch_g[c] = 0; }
   const long long total = (long long)B * H * W * (Ctot / 4);
+  if (total >= (1LL << 31) || (long long)B * H * W * 64 >= (1LL << 31)) return PNP_ERR_UNSUPPORTED;
   disc_input_kernel<<<grid_for(total, 256), 256, 0, S_>>>(plan, logits, NC, out, B, H, W, Ctot, r, order_b1);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
