@@ -149,6 +149,16 @@ int pnp_bn_bwd_apply_fused(const float* g, const float* z, const float* mean, co
                            const double* sum_g, const double* sum_gx, long long M, int C, int training,
                            const pnp_dropout_cfg* drop, float* dgamma, float* dbeta, float* dz, uint16_t* dz_hi,
                            uint16_t* dz_lo, void* stream);
+/* The same backward pass WITHOUT the fp32 g = dy*act'(y) round trip (layers whose g nobody else needs, i.e. no residual skip
+ * hanging off them): pnp_bn_bwd_reduce_sums accumulates sum(g), sum(g*xhat) only; pnp_bn_bwd_apply_direct recomputes g from dy.
+ * The activation sign may come from the bf16 hi plane of y (y_hi) instead of y; dz may be NULL when only the planes are wanted.
+ * 24-28 instead of 32 bytes per element. */
+int pnp_bn_bwd_reduce_sums(const float* dy, const float* y, const uint16_t* y_hi, const float* z, const float* mean,
+                           const float* invstd, int act, double* sum_g, double* sum_gx, long long M, int C, void* stream);
+int pnp_bn_bwd_apply_direct(const float* dy, const float* y, const uint16_t* y_hi, int act, const float* z, const float* mean,
+                            const float* invstd, const float* gamma, const double* sum_g, const double* sum_gx, long long M, int C,
+                            int training, const pnp_dropout_cfg* drop, float* dgamma, float* dbeta, float* dz, uint16_t* dz_hi,
+                            uint16_t* dz_lo, void* stream);
 /* y = act(z*scale + shift + skip);  skip (optional) has Cs channels placed at channel offset skip_off.
  * y_hi / y_lo (optional): also emit the bf16 (hi, lo) operand planes of y for the next tcgen05 convolution */
 int pnp_bn_act_apply(const float* z, const float* scale, const float* shift, const float* skip, int Cs,

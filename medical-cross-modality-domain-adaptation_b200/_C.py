@@ -60,6 +60,8 @@ SIGNATURES = {
     "pnp_bn_act_apply": [P, P, P, P, c_int, c_int, c_int, P, P, P, c_ll, c_int, P],
     "pnp_bn_apply_fused": [P, P, P, c_ll, c_int, P, P, P, P, c_int, P, c_int, c_int, c_int, P, P, P, P, P, P],
     "pnp_bn_bwd_apply_fused": [P, P, P, P, P, P, P, c_ll, c_int, c_int, _DROP, P, P, P, P, P, P],
+    "pnp_bn_bwd_reduce_sums": [P, P, P, P, P, P, c_int, P, P, c_ll, c_int, P],
+    "pnp_bn_bwd_apply_direct": [P, P, P, c_int, P, P, P, P, P, P, c_ll, c_int, c_int, _DROP, P, P, P, P, P, P],
     "pnp_bn_bwd_reduce": [P, P, P, P, P, c_int, P, P, P, c_ll, c_int, P],
     "pnp_bn_bwd_finalize": [P, P, c_ll, c_int, P, P, P, P],
     "pnp_bn_bwd_apply": [P, P, P, P, P, P, c_int, _DROP, P, P, P, c_ll, c_int, P],

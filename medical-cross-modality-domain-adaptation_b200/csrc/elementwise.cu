@@ -34,6 +34,10 @@ __device__ __forceinline__ float act_fwd(float v, int act) {
   if (act == PNP_ACT_LRELU) return v > 0.f ? v : kLeak * v;
   return v;
 }
+__device__ __forceinline__ float4 hi4_as_float4(ushort4 h) {
+  return make_float4(__uint_as_float((unsigned)h.x << 16), __uint_as_float((unsigned)h.y << 16), __uint_as_float((unsigned)h.z << 16),
+                     __uint_as_float((unsigned)h.w << 16));
+}
 __device__ __forceinline__ float act_slope(float y, int act) {
   if (act == PNP_ACT_RELU) return y > 0.f ? 1.f : 0.f;
   if (act == PNP_ACT_LRELU) return y > 0.f ? 1.f : kLeak;
@@ -55,7 +59,8 @@ PnpDropout make_drop(const pnp_dropout_cfg* d) { return pnp_make_drop(d); }
 template <bool WITH_G>
 __global__ void __launch_bounds__(256)
 bn_reduce_kernel(const float* __restrict__ z, const float* __restrict__ dy, const float* __restrict__ yact,
-                 const float* __restrict__ mean, const float* __restrict__ invstd, int act, float* __restrict__ gout,
+                 const unsigned short* __restrict__ yact_hi, const float* __restrict__ mean, const float* __restrict__ invstd, int act,
+                 float* __restrict__ gout,
                  long long M, int C, int tpr, long long rows_per_block, double* __restrict__ out_a, double* __restrict__ out_b) {
   // WITH_G == false: out_a += sum z, out_b += sum z^2
   // WITH_G == true : g = dy*act'(y) (written to gout); out_a += sum g ; out_b += sum g*xhat
@@ -91,17 +96,23 @@ bn_reduce_kernel(const float* __restrict__ z, const float* __restrict__ dy, cons
         float4 gA = __ldg(reinterpret_cast<const float4*>(dy) + offA);
         float4 gB = __ldg(reinterpret_cast<const float4*>(dy) + offB);
         if (act != PNP_ACT_NONE) {
-          float4 yA = __ldg(reinterpret_cast<const float4*>(yact) + offA);
-          float4 yB = __ldg(reinterpret_cast<const float4*>(yact) + offB);
+          float4 yA, yB;
+          if (yact_hi) {       // the sign of y from its bf16 hi plane (round-to-nearest keeps the sign; y == 0 <=> hi == 0)
+            yA = hi4_as_float4(__ldg(reinterpret_cast<const ushort4*>(yact_hi) + offA));
+            yB = hi4_as_float4(__ldg(reinterpret_cast<const ushort4*>(yact_hi) + offB));
+          } else {
+            yA = __ldg(reinterpret_cast<const float4*>(yact) + offA);
+            yB = __ldg(reinterpret_cast<const float4*>(yact) + offB);
+          }
           gA.x *= act_slope(yA.x, act); gA.y *= act_slope(yA.y, act); gA.z *= act_slope(yA.z, act); gA.w *= act_slope(yA.w, act);
           gB.x *= act_slope(yB.x, act); gB.y *= act_slope(yB.y, act); gB.z *= act_slope(yB.z, act); gB.w *= act_slope(yB.w, act);
         }
-        reinterpret_cast<float4*>(gout)[offA] = gA;
+        if (gout) reinterpret_cast<float4*>(gout)[offA] = gA;
         a0 += gA.x; a1 += gA.y; a2 += gA.z; a3 += gA.w;
         b0 += gA.x * (zA.x - mu.x) * is.x; b1 += gA.y * (zA.y - mu.y) * is.y;
         b2 += gA.z * (zA.z - mu.z) * is.z; b3 += gA.w * (zA.w - mu.w) * is.w;
         if (hasB) {
-          reinterpret_cast<float4*>(gout)[offB] = gB;
+          if (gout) reinterpret_cast<float4*>(gout)[offB] = gB;
           a0 += gB.x; a1 += gB.y; a2 += gB.z; a3 += gB.w;
           b0 += gB.x * (zB.x - mu.x) * is.x; b1 += gB.y * (zB.y - mu.y) * is.y;
           b2 += gB.z * (zB.z - mu.z) * is.z; b3 += gB.w * (zB.w - mu.w) * is.w;
@@ -273,7 +284,8 @@ bn_apply_fused_kernel(const float* __restrict__ z, const double* __restrict__ su
 }
 
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_fused_kernel(const float* __restrict__ g, const float* __restrict__ z, const float* __restrict__ mean,
+bn_bwd_apply_fused_kernel(const float* __restrict__ g, const float* __restrict__ yact, const unsigned short* __restrict__ yact_hi,
+                          int act, const float* __restrict__ z, const float* __restrict__ mean,
                           const float* __restrict__ invstd, const float* __restrict__ gamma, const double* __restrict__ sum_g,
                           const double* __restrict__ sum_gx, long long M, int C, int training, PnpDropout drop, float* dgamma,
                           float* dbeta, float* __restrict__ dz, unsigned short* __restrict__ p_hi, unsigned short* __restrict__ p_lo,
@@ -310,7 +322,12 @@ bn_bwd_apply_fused_kernel(const float* __restrict__ g, const float* __restrict__
   const float4* is4 = reinterpret_cast<const float4*>(s_coef + 4 * C);
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     const int q = (int)(i % C4);
-    const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);      // g, or dy when the activation derivative is applied here
+    if (act != PNP_ACT_NONE) {
+      const float4 yv = yact_hi ? hi4_as_float4(__ldg(reinterpret_cast<const ushort4*>(yact_hi) + i))
+                                : __ldg(reinterpret_cast<const float4*>(yact) + i);
+      gv.x *= act_slope(yv.x, act); gv.y *= act_slope(yv.y, act); gv.z *= act_slope(yv.z, act); gv.w *= act_slope(yv.w, act);
+    }
     const float4 k = k4[q];
     float4 o;
     if (training) {
@@ -327,7 +344,7 @@ bn_bwd_apply_fused_kernel(const float* __restrict__ g, const float* __restrict__
       const float4 mk = pnp_dropout_mult4(drop, seed, (unsigned long long)i);
       o.x *= mk.x; o.y *= mk.y; o.z *= mk.z; o.w *= mk.w;
     }
-    reinterpret_cast<float4*>(dz)[i] = o;
+    if (dz) reinterpret_cast<float4*>(dz)[i] = o;
     if (p_hi) store_planes(p_hi, p_lo, i, o);
   }
 }
@@ -932,7 +949,7 @@ extern "C" int pnp_bn_stats(const float* z, long long M, int C, double* sum, dou
   int tpr, grid; long long rpb;
   int rc = reduce_launch_cfg(M, C, &tpr, &rpb, &grid);
   if (rc) return rc;
-  bn_reduce_kernel<false><<<grid, 256, 0, S_>>>(z, nullptr, nullptr, nullptr, nullptr, 0, nullptr, M, C, tpr, rpb, sum, sumsq);
+  bn_reduce_kernel<false><<<grid, 256, 0, S_>>>(z, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, M, C, tpr, rpb, sum, sumsq);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -967,7 +984,21 @@ extern "C" int pnp_bn_bwd_reduce(const float* dy, const float* y, const float* z
   int tpr, grid; long long rpb;
   int rc = reduce_launch_cfg(M, C, &tpr, &rpb, &grid);
   if (rc) return rc;
-  bn_reduce_kernel<true><<<grid, 256, 0, S_>>>(z, dy, y, mean, invstd, act, g, M, C, tpr, rpb, sum_g, sum_gx);
+  bn_reduce_kernel<true><<<grid, 256, 0, S_>>>(z, dy, y, nullptr, mean, invstd, act, g, M, C, tpr, rpb, sum_g, sum_gx);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+/* sums only: g = dy * act'(y) is NOT written (pnp_bn_bwd_apply_direct recomputes it); the activation sign comes from y or from
+ * the bf16 hi plane of y */
+extern "C" int pnp_bn_bwd_reduce_sums(const float* dy, const float* y, const uint16_t* y_hi, const float* z, const float* mean,
+                                      const float* invstd, int act, double* sum_g, double* sum_gx, long long M, int C, void* stream) {
+  if (!dy || !z || !mean || !invstd || !sum_g || !sum_gx) return PNP_ERR_BAD_ARG;
+  if (act != PNP_ACT_NONE && !y && !y_hi) return PNP_ERR_BAD_ARG;
+  int tpr, grid; long long rpb;
+  int rc = reduce_launch_cfg(M, C, &tpr, &rpb, &grid);
+  if (rc) return rc;
+  bn_reduce_kernel<true><<<grid, 256, 0, S_>>>(z, dy, y, y_hi, mean, invstd, act, nullptr, M, C, tpr, rpb, sum_g, sum_gx);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1020,8 +1051,29 @@ extern "C" int pnp_bn_bwd_apply_fused(const float* g, const float* z, const floa
   if ((dgamma || dbeta) && !sum_g) return PNP_ERR_BAD_ARG;
   if (C % 4 != 0 || C > 1024) return PNP_ERR_UNSUPPORTED;
   long long n4 = M * (C / 4);
-  bn_bwd_apply_fused_kernel<<<grid_for(n4, 256), 256, 5 * C * sizeof(float), S_>>>(g, z, mean, invstd, gamma, sum_g, sum_gx, M, C, training,
-                                                                                 make_drop(drop), dgamma, dbeta, dz, dz_hi, dz_lo, n4);
+  bn_bwd_apply_fused_kernel<<<grid_for(n4, 256), 256, 5 * C * sizeof(float), S_>>>(g, nullptr, nullptr, PNP_ACT_NONE, z, mean, invstd, gamma,
+                                                                                 sum_g, sum_gx, M, C, training, make_drop(drop), dgamma,
+                                                                                 dbeta, dz, dz_hi, dz_lo, n4);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+/* as pnp_bn_bwd_apply_fused, but from dy: g = dy * act'(y) is recomputed on the fly (activation sign from y or from its bf16 hi
+ * plane), so the fp32 g tensor never exists; dz may be NULL when only the bf16 planes are consumed (tcgen05 wgrad / dgrad) */
+extern "C" int pnp_bn_bwd_apply_direct(const float* dy, const float* y, const uint16_t* y_hi, int act, const float* z,
+                                       const float* mean, const float* invstd, const float* gamma, const double* sum_g,
+                                       const double* sum_gx, long long M, int C, int training, const pnp_dropout_cfg* drop,
+                                       float* dgamma, float* dbeta, float* dz, uint16_t* dz_hi, uint16_t* dz_lo, void* stream) {
+  if (!dy || !invstd || !gamma || (!dz && !dz_hi) || M <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
+  if (act != PNP_ACT_NONE && !y && !y_hi) return PNP_ERR_BAD_ARG;
+  if (training && (!z || !mean || !sum_g || !sum_gx)) return PNP_ERR_BAD_ARG;
+  if ((sum_g == nullptr) != (sum_gx == nullptr)) return PNP_ERR_BAD_ARG;
+  if ((dgamma || dbeta) && !sum_g) return PNP_ERR_BAD_ARG;
+  if (C % 4 != 0 || C > 1024) return PNP_ERR_UNSUPPORTED;
+  long long n4 = M * (C / 4);
+  bn_bwd_apply_fused_kernel<<<grid_for(n4, 256), 256, 5 * C * sizeof(float), S_>>>(dy, y, y_hi, act, z, mean, invstd, gamma, sum_g, sum_gx, M,
+                                                                                 C, training, make_drop(drop), dgamma, dbeta, dz, dz_hi,
+                                                                                 dz_lo, n4);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }

@@ -95,6 +95,7 @@ def _tc_mode():
 TC_WGRAD = os.environ.get("PNP_TC_WGRAD", "1") != "0"
 TC_PAD32 = os.environ.get("PNP_TC_PAD32", "0") == "1"
 _tc_declined = set()     # (kind, geometry) the tcgen05 launchers returned PNP_ERR_UNSUPPORTED for -> general SIMT kernel
+_tc_proven = set()       # (kind, geometry) that HAVE run on the tcgen05 path: only for those may a producer drop the fp32 copy
 
 
 def _gkey(kind, g):
@@ -140,6 +141,26 @@ def _new_planes(shape, dev, nterms):
     hi = torch.empty(shape, dtype=torch.bfloat16, device=dev)
     lo = torch.empty(shape, dtype=torch.bfloat16, device=dev) if nterms == 3 else None
     return hi, lo
+
+
+class _PlanesOnly:
+    """stand-in for a tensor whose fp32 copy was never written: it only carries the bf16 operand planes.  Any consumer that
+    asks for its address (a SIMT kernel) fails loudly instead of reading garbage."""
+
+    def __init__(self, shape, dev):
+        self.shape, self.device = tuple(shape), dev
+
+    def data_ptr(self):
+        raise RuntimeError("this gradient exists only as bf16 operand planes; its fp32 copy was elided")
+
+    def contiguous(self):
+        return self
+
+    def numel(self):
+        n = 1
+        for d in self.shape:
+            n *= d
+        return n
 
 
 def _planes_of(x, nterms):
@@ -205,10 +226,11 @@ def _conv_flops(g):
 class Epilogue:
     """what the tcgen05 forward convolution may apply to its accumulator before it leaves the SM (pnp_conv2d_tc_fwd_fused):
     y = act(z * scale + shift + skip), plus the bf16 operand planes of y"""
-    __slots__ = ("scale", "shift", "skip", "skip_c", "skip_off", "act", "planes")
+    __slots__ = ("scale", "shift", "skip", "skip_c", "skip_off", "act", "planes", "planes_only")
 
-    def __init__(self, scale=None, shift=None, skip=None, skip_off=0, act=ACT_NONE, planes=0):
+    def __init__(self, scale=None, shift=None, skip=None, skip_off=0, act=ACT_NONE, planes=0, planes_only=False):
         self.scale, self.shift, self.skip, self.skip_off, self.act, self.planes = scale, shift, skip, skip_off, act, planes
+        self.planes_only = planes_only
         self.skip_c = skip.shape[-1] if skip is not None else 0
 
 
@@ -229,11 +251,16 @@ def conv_fwd_raw(xp, W, geom, drop=None, stats=None, keep_planes=False, ep=None)
                 _tc_launch(tag, _conv_flops(geom), "pnp_conv2d_tc_fwd", ptr(planes[0]), ptr(planes[1]), ptr(whi), ptr(wlo), ptr(z),
                            ctypes.byref(g_tc), nt, _byref(drop), 0, ptr(stats[0]) if fuse else None, ptr(stats[1]) if fuse else None,
                            rt.stream())
+                _tc_proven.add(_gkey("fwd", geom))
                 return z, fuse, (planes if keep_planes else None), False
             yh, yl = _new_planes(z.shape, xp.device, ep.planes) if ep.planes else (None, None)
+            if ep.planes and ep.planes_only:
+                z = _PlanesOnly(z.shape, xp.device)
             cep = _C.TcEpilogue(ptr(ep.scale), ptr(ep.shift), ptr(ep.skip), ep.skip_c, ep.skip_off, ep.act, ptr(yh), ptr(yl))
-            _tc_launch(tag, _conv_flops(geom), "pnp_conv2d_tc_fwd_fused", ptr(planes[0]), ptr(planes[1]), ptr(whi), ptr(wlo), ptr(z),
+            _tc_launch(tag, _conv_flops(geom), "pnp_conv2d_tc_fwd_fused", ptr(planes[0]), ptr(planes[1]), ptr(whi), ptr(wlo),
+                       None if isinstance(z, _PlanesOnly) else ptr(z),
                        ctypes.byref(g_tc), nt, _byref(drop), 0, None, None, ctypes.byref(cep), rt.stream())
+            _tc_proven.add(_gkey("fwd", geom))
             if ep.planes:
                 z._pnp_planes = (ep.planes, yh, yl)
             return z, False, (planes if keep_planes else None), True
@@ -269,6 +296,7 @@ def conv_dgrad_raw(dz, W, geom, into=None, dz_planes=None):
         try:
             _tc_launch("dgr%dx%d.%d.%d" % (geom.Ho, geom.Cin, geom.Cout, geom.kh * geom.stride), _conv_flops(geom), "pnp_conv2d_tc_dgrad", ptr(hi), ptr(lo), ptr(whi), ptr(wlo), ptr(dx),
                        ctypes.byref(geom), nt, acc, rt.stream())
+            _tc_proven.add(_gkey("dgrad", geom))
             return dx
         except _C.Unsupported:
             _tc_declined.add(_gkey("dgrad", geom))
@@ -294,6 +322,7 @@ def conv_wgrad_raw(xp, dz, W, geom, x_planes=None, dz_planes=None):
             _tc_launch("wgr%dx%d.%d.%d" % (geom.Ho, geom.Cin, geom.Cout, geom.kh * geom.stride), _conv_flops(geom), "pnp_conv2d_tc_wgrad", ptr(xh), ptr(xl), ptr(dh), ptr(dl), ptr(W.grad),
                        ctypes.byref(geom), nt, cp if cp != geom.Cin else 0, rt.stream())
             _grad_written(W)
+            _tc_proven.add(_gkey("wgrad", geom))
             return
         except _C.Unsupported:
             _tc_declined.add(_gkey("wgrad", geom))
@@ -354,8 +383,11 @@ def _geometry(x_shape, w_shape, cfg):
 FUSE_EPILOGUE = os.environ.get("PNP_FUSE_EPILOGUE", "1") != "0"
 
 
-def layer_forward(x, W, cfg, skip=None, save=True):
-    """returns (y, saved) -- `saved` is None when save is False (inference / frozen sub-graph)"""
+def layer_forward(x, W, cfg, skip=None, save=True, planes_only=False):
+    """returns (y, saved) -- `saved` is None when save is False (inference / frozen sub-graph).
+    planes_only: the caller guarantees that y is consumed ONLY as bf16 operand planes (the hidden activation of a residual
+    block whose second convolution runs on the tcgen05 path): its fp32 copy is then never written, and the backward pass
+    takes the activation's sign from the hi plane."""
     x = x.contiguous()
     dev = x.device
     p, geom = _geometry(x.shape, W.shape, cfg)
@@ -378,7 +410,7 @@ def layer_forward(x, W, cfg, skip=None, save=True):
     if foldable:
         coef = _bn_infer_coef(bn) if bn is not None else None
         ep = Epilogue(coef[0] if bn is not None else None, coef[1] if bn is not None else None, skip, cfg.skip_off, cfg.act,
-                      _want_planes(C))
+                      _want_planes(C), planes_only and bool(_want_planes(C)))
         y, _, x_planes, applied = conv_fwd_raw(xp, W, geom, drop, None, keep_planes, ep)
         if applied:
             if not save:
@@ -386,6 +418,8 @@ def layer_forward(x, W, cfg, skip=None, save=True):
             saved = {"cfg": cfg, "geom": geom, "p": p, "x_shape": tuple(x.shape), "xp": xp, "xs": x_planes, "W": W, "drop": drop_info,
                      "z": None, "y": y if cfg.act != ACT_NONE else None, "mean": coef[2] if bn is not None else None,
                      "invstd": coef[3] if bn is not None else None, "skip_c": cs}
+            if isinstance(y, _PlanesOnly):
+                saved["y"], saved["y_hi"] = None, y._pnp_planes[1]
             return y, saved
         z, stats_done = y, False            # the launcher declined the tensor-core path: z is the plain convolution
         stats = None
@@ -404,12 +438,12 @@ def layer_forward(x, W, cfg, skip=None, save=True):
         if cfg.bn_training:
             bn.moving_mean.pnp_version = getattr(bn.moving_mean, "pnp_version", 0) + 1
             bn.moving_var.pnp_version = getattr(bn.moving_var, "pnp_version", 0) + 1
-        y = torch.empty_like(z)
         nt = _want_planes(C)
+        y = _PlanesOnly(z.shape, dev) if (planes_only and nt) else torch.empty_like(z)
         yh, yl = _new_planes(z.shape, dev, nt) if nt else (None, None)
         call("pnp_bn_apply_fused", ptr(z), ptr(stats[0]) if stats else None, ptr(stats[1]) if stats else None, M, C, ptr(bn.gamma),
              ptr(bn.beta), ptr(bn.moving_mean), ptr(bn.moving_var), 1 if cfg.bn_training else 0, ptr(skip), cs, cfg.skip_off, cfg.act,
-             ptr(y), ptr(yh), ptr(yl), ptr(mean), ptr(invstd), rt.stream())
+             None if isinstance(y, _PlanesOnly) else ptr(y), ptr(yh), ptr(yl), ptr(mean), ptr(invstd), rt.stream())
         if nt:
             y._pnp_planes = (nt, yh, yl)
     elif cfg.act != ACT_NONE or skip is not None:
@@ -424,7 +458,13 @@ def layer_forward(x, W, cfg, skip=None, save=True):
         "z": z if (bn is not None) else None, "y": y if cfg.act != ACT_NONE else None,
         "mean": mean, "invstd": invstd, "skip_c": cs,
     }
+    if isinstance(y, _PlanesOnly):
+        saved["y"], saved["y_hi"] = None, y._pnp_planes[1]
     return y, saved
+
+
+# PNP_BN_BWD_DIRECT=0: always materialise g = dy*act'(y) (the r1 data flow)
+BN_BWD_DIRECT = os.environ.get("PNP_BN_BWD_DIRECT", "1") != "0"
 
 
 def layer_backward(sv, dy, need_dx=True, dx_into=None, want_dskip=False):
@@ -437,39 +477,60 @@ def layer_backward(sv, dy, need_dx=True, dx_into=None, want_dskip=False):
     bn = cfg.bn
     drop = _drop_from(sv["drop"])
     y = sv["y"]
+    y_hi = sv.get("y_hi")             # the forward pass elided the fp32 activation: its sign lives in the bf16 hi plane
     g_owned = False
     if bn is not None:
         need_dparam = bn.gamma.requires_grad or bn.beta.requires_grad
         coef = None
         dgamma = dbeta = None
-        if cfg.bn_training or need_dparam:
-            g = torch.empty(dy.shape, dtype=torch.float32, device=dev)
-            g_owned = True
-            sums = _zeros_f64(2 * C, dev)
-            call("pnp_bn_bwd_reduce", ptr(dy), ptr(y), ptr(sv["z"]), ptr(sv["mean"]), ptr(sv["invstd"]), cfg.act, ptr(g),
-                 ptr(sums[:C]), ptr(sums[C:]), M, C, rt.stream())
-            coef = sums
-            if bn.gamma.requires_grad:
-                dgamma = _grad_slot(bn.gamma)
-            if bn.beta.requires_grad:
-                dbeta = _grad_slot(bn.beta)
-        elif cfg.act != ACT_NONE:
-            g = torch.empty(dy.shape, dtype=torch.float32, device=dev)
-            g_owned = True
-            call("pnp_act_bwd", ptr(dy), ptr(y), cfg.act, ptr(g), dy.numel(), rt.stream())
-        else:
-            g = dy
-        dz = torch.empty(dy.shape, dtype=torch.float32, device=dev)
         nt = _tc_mode()
-        want = nt and FUSE_SPLIT and ((W.requires_grad and _tc_will_run("wgrad", geom)) or (need_dx and _tc_will_run("dgrad", geom)))
+        use_w = W.requires_grad and _tc_will_run("wgrad", geom)
+        use_d = need_dx and _tc_will_run("dgrad", geom)
+        want = bool(nt and FUSE_SPLIT and (use_w or use_d))
+        # fp32 dz is only read by the SIMT kernels: drop it when every consumer has already run on the tensor-core path
+        consumers = [("wgrad", W.requires_grad), ("dgrad", need_dx)]
+        need_f32 = not want or any(on and _gkey(kind, geom) not in _tc_proven for kind, on in consumers)
+        need_g = bool(want_dskip and sv["skip_c"])          # the residual skip's gradient IS g: only then must it exist in HBM
+        if (cfg.bn_training or need_dparam) and bn.gamma.requires_grad:
+            dgamma = _grad_slot(bn.gamma)
+        if (cfg.bn_training or need_dparam) and bn.beta.requires_grad:
+            dbeta = _grad_slot(bn.beta)
+        dz = torch.empty(dy.shape, dtype=torch.float32, device=dev) if need_f32 else None
         dzh, dzl = _new_planes(dy.shape, dev, nt) if want else (None, None)
-        call("pnp_bn_bwd_apply_fused", ptr(g), ptr(sv["z"]), ptr(sv["mean"]), ptr(sv["invstd"]), ptr(bn.gamma),
-             ptr(coef[:C]) if coef is not None else None, ptr(coef[C:]) if coef is not None else None, M, C,
-             1 if cfg.bn_training else 0, _byref(drop), ptr(dgamma), ptr(dbeta), ptr(dz), ptr(dzh), ptr(dzl), rt.stream())
+        if y_hi is not None and not (BN_BWD_DIRECT and not need_g):
+            raise RuntimeError("planes-only activation reached a backward path that needs its fp32 copy")
+        if BN_BWD_DIRECT and not need_g:
+            # two passes over (dy, y, z), no g: 24-28 bytes per element instead of 32
+            if cfg.bn_training or need_dparam:
+                coef = _zeros_f64(2 * C, dev)
+                call("pnp_bn_bwd_reduce_sums", ptr(dy), ptr(y), ptr(y_hi), ptr(sv["z"]), ptr(sv["mean"]), ptr(sv["invstd"]), cfg.act,
+                     ptr(coef[:C]), ptr(coef[C:]), M, C, rt.stream())
+            call("pnp_bn_bwd_apply_direct", ptr(dy), ptr(y), ptr(y_hi), cfg.act, ptr(sv["z"]), ptr(sv["mean"]), ptr(sv["invstd"]),
+                 ptr(bn.gamma), ptr(coef[:C]) if coef is not None else None, ptr(coef[C:]) if coef is not None else None, M, C,
+                 1 if cfg.bn_training else 0, _byref(drop), ptr(dgamma), ptr(dbeta), ptr(dz), ptr(dzh), ptr(dzl), rt.stream())
+            g = None
+        else:
+            if cfg.bn_training or need_dparam:
+                g = torch.empty(dy.shape, dtype=torch.float32, device=dev)
+                g_owned = True
+                coef = _zeros_f64(2 * C, dev)
+                call("pnp_bn_bwd_reduce", ptr(dy), ptr(y), ptr(sv["z"]), ptr(sv["mean"]), ptr(sv["invstd"]), cfg.act, ptr(g),
+                     ptr(coef[:C]), ptr(coef[C:]), M, C, rt.stream())
+            elif cfg.act != ACT_NONE:
+                g = torch.empty(dy.shape, dtype=torch.float32, device=dev)
+                g_owned = True
+                call("pnp_act_bwd", ptr(dy), ptr(y), cfg.act, ptr(g), dy.numel(), rt.stream())
+            else:
+                g = dy
+            call("pnp_bn_bwd_apply_direct", ptr(g), None, None, ACT_NONE, ptr(sv["z"]), ptr(sv["mean"]), ptr(sv["invstd"]), ptr(bn.gamma),
+                 ptr(coef[:C]) if coef is not None else None, ptr(coef[C:]) if coef is not None else None, M, C,
+                 1 if cfg.bn_training else 0, _byref(drop), ptr(dgamma), ptr(dbeta), ptr(dz), ptr(dzh), ptr(dzl), rt.stream())
         if dgamma is not None:
             _grad_written(bn.gamma)
         if dbeta is not None:
             _grad_written(bn.beta)
+        if dz is None:
+            dz = _PlanesOnly(dy.shape, dev)
         if want:
             dz._pnp_planes = (nt, dzh, dzl)
     else:
@@ -566,7 +627,7 @@ class _ResBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, cfg1, cfg2, W1, W2, *bnp):
         save = any(ctx.needs_input_grad)
-        h, s1 = layer_forward(x, W1, cfg1, None, save)
+        h, s1 = layer_forward(x, W1, cfg1, None, save, planes_only=_hidden_planes_only(x, W1, W2, cfg1, cfg2, save))
         y, s2 = layer_forward(h, W2, cfg2, x, save)
         ctx.s1, ctx.s2 = s1, s2
         return y
@@ -578,6 +639,28 @@ class _ResBlockFn(torch.autograd.Function):
         dx, _ = layer_backward(ctx.s1, dh, need_dx, dskip if need_dx else None, False)
         ctx.s1 = ctx.s2 = None
         return (dx, None, None, None, None) + (None,) * (len(ctx.needs_input_grad) - 5)
+
+
+# PNP_PLANES_ONLY=0: always write the fp32 hidden activation of a residual block
+PLANES_ONLY = os.environ.get("PNP_PLANES_ONLY", "1") != "0"
+
+
+def _hidden_planes_only(x, W1, W2, cfg1, cfg2, save):
+    """may the hidden activation h = act(BN(conv1(x))) of a residual block exist as bf16 planes only?  Yes when its single
+    consumer, conv2 (forward, and the weight gradient if W2 trains), has already run on the tcgen05 path for this geometry, h
+    has a batch norm (whose apply pass / epilogue emits the planes) and the backward pass is the g-less one."""
+    if not (PLANES_ONLY and BN_BWD_DIRECT and FUSE_SPLIT and cfg1.bn is not None and cfg2.padding == "SAME" and _tc_mode()):
+        return False
+    try:
+        _, g1 = _geometry(tuple(x.shape), W1.shape, cfg1)
+        _, g2 = _geometry((g1.B, g1.Ho, g1.Wo, g1.Cout), W2.shape, cfg2)
+    except Exception:      # noqa: BLE001 -- shape errors surface in layer_forward with their proper message
+        return False
+    if not _want_planes(g1.Cout) or _gkey("fwd", g2) not in _tc_proven:
+        return False
+    if save and W2.requires_grad and _gkey("wgrad", g2) not in _tc_proven:
+        return False
+    return True
 
 
 def res_block(x, W1, W2, cfg1, cfg2):
