@@ -1015,7 +1015,13 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
     if (bk256_env < 0) { const char* e = getenv("PNP_TC_BK256"); bk256_env = e ? atoi(e) : 0; }
     const int bk256 = bk256_env ? bk256_env : (nterms == 1 ? 64 : 32);
     if (block_n == 256 && bk256 == 32) bk = 32;
-    if (block_n == 128 && bk == 32) block_n = 64;      // (no 128 x 32-wide instantiation)
+    // experiment knobs: 32-wide K blocks for the 128- and 64-column tiles of 64-multiple reductions (twice the pipeline stages of
+    // half the size: 64 KB x 3 -> 32 KB x 6 for N = 128, 48 KB x 4 -> 24 KB x 8 for N = 64)
+    static int bk128_env = -1, bk64_env = -1;
+    if (bk128_env < 0) { const char* e = getenv("PNP_TC_BK128"); bk128_env = e ? atoi(e) : 64; }
+    if (bk64_env < 0) { const char* e = getenv("PNP_TC_BK64"); bk64_env = e ? atoi(e) : 64; }
+    if (block_n == 128 && bk == 64 && bk128_env == 32) bk = 32;
+    if (block_n == 64 && bk == 64 && bk64_env == 32) bk = 32;
   }
   a.kchunks = a.Cin / bk;
   g_last_cfg[0] = block_n; g_last_cfg[1] = bk; g_last_cfg[2] = 1;
@@ -1087,6 +1093,7 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
   if (block_n == 256 && bk == 64) { PNP_TC_GO(256, 64); }
   else if (block_n == 256 && bk == 32) { PNP_TC_GO(256, 32); }
   else if (block_n == 128 && bk == 64) { PNP_TC_GO(128, 64); }
+  else if (block_n == 128 && bk == 32) { PNP_TC_GO(128, 32); }
   else if (block_n == 64 && bk == 64) { PNP_TC_GO(64, 64); }
   else if (block_n == 64 && bk == 32) { PNP_TC_GO(64, 32); }
   else if (block_n == 32 && bk == 64) { PNP_TC_GO(32, 64); }
