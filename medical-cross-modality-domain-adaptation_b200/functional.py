@@ -346,11 +346,12 @@ class BNVars:
 
 
 class LayerCfg:
-    __slots__ = ("stride", "dil", "padding", "keep_prob", "bn", "bn_training", "act", "skip_off")
+    __slots__ = ("stride", "dil", "padding", "keep_prob", "bn", "bn_training", "act", "skip_off", "grad_on")
 
     def __init__(self, stride=1, dil=1, padding="SAME", keep_prob=1.0, bn=None, bn_training=True, act=ACT_NONE, skip_off=0):
         self.stride, self.dil, self.padding, self.keep_prob = stride, dil, padding, keep_prob
         self.bn, self.bn_training, self.act, self.skip_off = bn, bool(bn_training), act, skip_off
+        self.grad_on = True
 
 
 def _geometry(x_shape, w_shape, cfg):
@@ -598,9 +599,10 @@ class _ConvLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, skip, cfg, W, *bnp):
-        # autograd.Function.forward always runs with grad mode off; needs_input_grad already folds in the caller's
-        # grad mode (all False under torch.no_grad()) and the inputs' requires_grad flags
-        save = any(ctx.needs_input_grad)
+        # autograd.Function.forward always runs with grad mode off, and needs_input_grad reflects the inputs' requires_grad flags
+        # whatever the caller's grad mode is (r2 ncu: a torch.no_grad() forward of a TRAINABLE network kept saving activations and
+        # never folded its batch norms) -- the wrapper records the caller's grad mode on the LayerCfg
+        save = any(ctx.needs_input_grad) and getattr(cfg, "grad_on", True)
         y, sv = layer_forward(x, W, cfg, skip, save)
         ctx.sv = sv
         ctx.has_skip = skip is not None
@@ -617,6 +619,7 @@ class _ConvLayerFn(torch.autograd.Function):
 
 
 def conv_layer(x, W, cfg, skip=None):
+    cfg.grad_on = torch.is_grad_enabled()
     return _ConvLayerFn.apply(x, skip, cfg, W, *_bn_params(cfg))
 
 
@@ -626,7 +629,7 @@ class _ResBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, cfg1, cfg2, W1, W2, *bnp):
-        save = any(ctx.needs_input_grad)
+        save = any(ctx.needs_input_grad) and getattr(cfg1, "grad_on", True)
         h, s1 = layer_forward(x, W1, cfg1, None, save, planes_only=_hidden_planes_only(x, W1, W2, cfg1, cfg2, save))
         y, s2 = layer_forward(h, W2, cfg2, x, save)
         ctx.s1, ctx.s2 = s1, s2
@@ -664,6 +667,7 @@ def _hidden_planes_only(x, W1, W2, cfg1, cfg2, save):
 
 
 def res_block(x, W1, W2, cfg1, cfg2):
+    cfg1.grad_on = cfg2.grad_on = torch.is_grad_enabled()
     return _ResBlockFn.apply(x, cfg1, cfg2, W1, W2, *(_bn_params(cfg1) + _bn_params(cfg2)))
 
 

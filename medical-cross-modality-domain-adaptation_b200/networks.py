@@ -127,8 +127,9 @@ class SegmenterTail:
     def run(self, c9, keep_prob, batch_size):
         from . import functional as F
         conv10 = L.conv2d(c9, self.w10, keep_prob_=keep_prob, padding='SYMMETRIC')
-        if F.FUSE_TAIL and not self.w11.requires_grad and self.w11.shape[3] in (5, 8):
-            # frozen output filter (adversarial steps, evaluation): PS + mirror pad + convolution in one kernel
+        import torch
+        if F.FUSE_TAIL and not (self.w11.requires_grad and torch.is_grad_enabled()) and self.w11.shape[3] in (5, 8):
+            # output filter takes no gradient (adversarial steps, any torch.no_grad() forward): PS + mirror pad + convolution in one kernel
             ops._check(conv10, batch_size)
             return F.tail_ps_conv(conv10, self.w11, 8, self.num_cls * 8, batch_size)
         flat = ops.PS(conv10, r=8, n_channel=self.num_cls * 8, batch_size=batch_size)
