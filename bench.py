@@ -386,7 +386,7 @@ def run_ours(a):
         reps = max(2, min(a.steps, 3))
         ms20 = timed(nd20_step, reps) / reps
         nd20 = {"n_D": 20, "slices_per_step": 41 * B, "ms_per_step": ms20, "value": 41 * B / (ms20 / 1e3), "unit": "slices/s",
-                "cuda_graph": bool(ok and a.graph), "conv_tflops_algorithmic": B * (20 * GF_D_STEP_PER_PAIR + GF_G_STEP_PER_SLICE) / ms20 / 1e3}
+                "cuda_graph": bool(ok and a.graph), "conv_tflops_algorithmic": B * (20 * GF_D_STEP_PER_PAIR + GF_G_STEP_PER_SLICE) / ms20}
         if a.graph:        # back to the joint graph for the roofline pass below (eager) -- nothing else replays after this
             tr.release_graphs()
             w.graphed = False
@@ -435,8 +435,8 @@ def run_ours(a):
             "data": "synthetic", "config": cfgobj,
             "detail": {"conv_backend": a.backend, "cuda_graph": bool(w.graphed or (a.graph and nd20 is not None)),
                        "gflop_per_step_algorithmic": w.gflop_per_step * world},
-            "conv_tflops_algorithmic": w.gflop_per_step * world / ms_step / 1e3,
-            "conv_roofline_frac_whole_step": w.gflop_per_step / ms_step / 1e3 / _peaks()["bf16_tflops"],
+            "conv_tflops_algorithmic": w.gflop_per_step * world / ms_step,                     # GFLOP / ms = TFLOP/s, all GPUs
+            "conv_roofline_frac_whole_step": w.gflop_per_step / ms_step / _peaks()["bf16_tflops"],   # per GPU, of the measured bf16 peak
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         if nd20 is not None:

@@ -209,6 +209,7 @@ struct TcArgs {
   int taps_inner;             // k-block order: 1 = channel chunk outer / taps inner (the shifted windows of one chunk hit L2)
   int ksplit;                 // > 1: each (m, n) tile's k-blocks are divided among ksplit CTAs that atomically add their partial
                               // sums into a zeroed output (few-tile, deep-K layers: 4x4 / 16x16 maps with 512 channels)
+  int b_resident;             // 1: all weight tiles live in shared memory (loaded once per CTA); stages carry activations only
   int nphases;                // 0: single phase described by the fields above
   struct Phase {
     short tap_begin, tap_count, py, px;
@@ -253,16 +254,31 @@ __device__ __forceinline__ TileCoord decode_tile(const TcArgs& a, int t, int n_t
   return c;
 }
 
+// k-block i of a tile -> (absolute tap, channel chunk); shared by the producer and (resident weights) the MMA issuer
+__device__ __forceinline__ void kblock_of(const TcArgs& a, const TileCoord& tc, int i, int kchunks, int& tap, int& kc) {
+  const int rot = (tc.kb_count >= 16) ? (int)(((long long)tc.mt * a.rot_mul) % tc.kb_count) : 0;
+  int kr = i + rot;
+  if (kr >= tc.kb_count) kr -= tc.kb_count;
+  const int kb = tc.kb_begin + kr;
+  int tl;
+  if (a.taps_inner) { kc = kb / tc.tap_count; tl = kb - kc * tc.tap_count; }
+  else { tl = kb / kchunks; kc = kb - tl * kchunks; }
+  tap = tc.tap_begin + tl;
+}
+
 template <int BLOCK_N, int NTERMS, int BK>
 struct TcCfg {
   static constexpr int A_TILE_BYTES = BLOCK_M * BK * 2;
   static constexpr int B_TILE_BYTES = BLOCK_N * BK * 2;
   static constexpr int NPLANES = (NTERMS == 1) ? 1 : 2;
   static constexpr int STAGE_BYTES = NPLANES * (A_TILE_BYTES + B_TILE_BYTES);
-  static constexpr int SMEM_BUDGET = 200 * 1024;
+  // narrow tiles (N <= 32: the 16- and 32-channel layers) may keep the weight tiles of ALL taps resident in shared memory for the
+  // life of the persistent CTA (TcArgs::b_resident): half of their TMA instructions were 0.5-2 KB weight fetches repeated per tile
+  static constexpr int WRES_BYTES = BLOCK_N <= 32 ? 40 * 1024 : 0;
+  static constexpr int SMEM_BUDGET = 200 * 1024 - WRES_BYTES;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + WRES_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   // epilogue: 4 warps cover the 128 accumulator rows (TMEM lane quarter = warp_id % 4); tiles >= 64 columns wide use a second
   // set of 4 warps on the other half of the columns -- a forward epilogue (dropout mask, BN partial statistics, stores) on ONE
@@ -287,11 +303,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty ; then the TMEM base holder
+  uint8_t* wres = smem + STAGES * Cfg::STAGE_BYTES;                      // resident weight tiles (1024-byte aligned: stage sizes are)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wres + Cfg::WRES_BYTES);
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, [2S+4] resident weights ; then the TMEM base holder
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* wres_full = bars + 2 * STAGES + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+  const bool bres = Cfg::WRES_BYTES > 0 && a.b_resident != 0;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -311,6 +330,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     mbar_init(smem_u32(&tmem_full[1]), 1);
     mbar_init(smem_u32(&tmem_empty[0]), 32 * Cfg::EPI_WARPS);      // every epilogue thread releases an accumulator
     mbar_init(smem_u32(&tmem_empty[1]), 32 * Cfg::EPI_WARPS);
+    mbar_init(smem_u32(wres_full), 1);
     fence_barrier_init();
   }
   if (warp == 1) tcgen05_alloc(smem_u32(tmem_holder), 2 * Cfg::TMEM_COLS);
@@ -323,7 +343,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ================= TMA producer =================
     if (lane == 0) {
       const uint32_t box_a_bytes = (uint32_t)(a.tw * a.th * a.tn) * BK * 2;
-      const uint32_t tx_bytes = Cfg::NPLANES * (box_a_bytes + Cfg::B_TILE_BYTES);
+      const uint32_t tx_bytes = Cfg::NPLANES * (box_a_bytes + (bres ? 0u : (uint32_t)Cfg::B_TILE_BYTES));
+      if (bres) {
+        // every (tap, chunk) weight tile of this layer, once: tile (tap, kc) at wres + (tap*kchunks + kc) * NPLANES * B_TILE_BYTES
+        const int nkb_all = a.ntaps * kchunks;
+        mbar_expect_tx(smem_u32(wres_full), (uint32_t)(nkb_all * Cfg::NPLANES * Cfg::B_TILE_BYTES));
+        for (int tap = 0; tap < a.ntaps; ++tap)
+          for (int kc = 0; kc < kchunks; ++kc) {
+            uint8_t* dst = wres + (size_t)(tap * kchunks + kc) * Cfg::NPLANES * Cfg::B_TILE_BYTES;
+            tma_load_2d(smem_u32(dst), &map_b_hi, smem_u32(wres_full), kc * BK, a.tap_wrow[tap]);
+            if (NTERMS > 1) tma_load_2d(smem_u32(dst + Cfg::B_TILE_BYTES), &map_b_lo, smem_u32(wres_full), kc * BK, a.tap_wrow[tap]);
+          }
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -331,15 +362,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int x0 = tc.x0, y0 = tc.y0, img0 = tc.img0, n0 = tc.n0;
         // CTAs that share a weight tile (same n0, different m-tile) would otherwise request the same L2 lines in lockstep;
         // rotating each m-tile's starting k-block spreads those requests over the whole weight slab (sum order is free)
-        const int rot = (tc.kb_count >= 16) ? (int)(((long long)tc.mt * a.rot_mul) % tc.kb_count) : 0;
         for (int i = 0; i < tc.kb_count; ++i) {
-          int kr = i + rot;
-          if (kr >= tc.kb_count) kr -= tc.kb_count;
-          const int kb = tc.kb_begin + kr;
-          int tl, kc;
-          if (a.taps_inner) { kc = kb / tc.tap_count; tl = kb - kc * tc.tap_count; }
-          else { tl = kb / kchunks; kc = kb - tl * kchunks; }
-          const int tap = tc.tap_begin + tl;
+          int tap, kc;
+          kblock_of(a, tc, i, kchunks, tap, kc);
           mbar_wait(smem_u32(&bars[STAGES + stage]), phase ^ 1);
           const uint32_t full = smem_u32(&bars[stage]);
           mbar_expect_tx(full, tx_bytes);
@@ -348,10 +373,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const int cy = y0 * a.in_mul + a.tap_oy[tap];
           const int wrow = a.tap_wrow[tap] + n0;
           tma_load_4d(smem_u32(st), &map_a_hi, full, kc * BK, cx, cy, img0);
-          tma_load_2d(smem_u32(st + Cfg::NPLANES * A_TILE_BYTES), &map_b_hi, full, kc * BK, wrow);
+          if (!bres) tma_load_2d(smem_u32(st + Cfg::NPLANES * A_TILE_BYTES), &map_b_hi, full, kc * BK, wrow);
           if (NTERMS > 1) {
             tma_load_4d(smem_u32(st + A_TILE_BYTES), &map_a_lo, full, kc * BK, cx, cy, img0);
-            tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES), &map_b_lo, full, kc * BK, wrow);
+            if (!bres) tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES), &map_b_lo, full, kc * BK, wrow);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -365,8 +390,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (bres) {
+        mbar_wait(smem_u32(wres_full), 0);
+        tcgen05_fence_after();
+      }
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int num_kb = decode_tile<BLOCK_N>(a, t, n_tiles).kb_count;
+        const TileCoord tcm = decode_tile<BLOCK_N>(a, t, n_tiles);
+        const int num_kb = tcm.kb_count;
         mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);     // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -376,7 +406,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const uint32_t st = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t a_hi = st;
           const uint32_t a_lo = st + A_TILE_BYTES;
-          const uint32_t b_hi = st + Cfg::NPLANES * A_TILE_BYTES;
+          uint32_t b_hi = st + Cfg::NPLANES * A_TILE_BYTES;
+          if (bres) {
+            int tap, kc;
+            kblock_of(a, tcm, kb, kchunks, tap, kc);
+            b_hi = smem_u32(wres) + (uint32_t)((tap * kchunks + kc) * Cfg::NPLANES * Cfg::B_TILE_BYTES);
+          }
           const uint32_t b_lo = b_hi + Cfg::B_TILE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -1072,6 +1107,12 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
         a.bn_sum = nullptr; a.bn_sumsq = nullptr;
       }
     }
+  }
+  {
+    static int bres_env = -1;
+    if (bres_env < 0) { const char* e = getenv("PNP_TC_BRES"); bres_env = e ? atoi(e) : 1; }
+    const long long wbytes = (long long)a.ntaps * a.kchunks * (nterms == 3 ? 2 : 1) * block_n * bk * 2;
+    a.b_resident = (bres_env && block_n <= 32 && a.Cout == block_n && a.ksplit == 1 && wbytes <= 40 * 1024) ? 1 : 0;
   }
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   rc = make_act_map(&ma_hi, a_hi, a.B, AH, AW, a.Cin, a.tw, a.th, a.tn, a_stride, bk);
