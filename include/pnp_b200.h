@@ -78,6 +78,10 @@ int pnp_weight_transpose(const float* w, float* wT, int taps, int Cin, int Cout,
  * odd kernels up to 5x5.  order_b1: the reference's batch_size == 1 sub-pixel order (ops.py:11-20). */
 int pnp_ps_mirror_conv_fwd(const float* X, const float* w, float* y, int B, int a, int b, int G, int r, int kh, int kw,
                            int Cout, int order_b1, void* stream);
+/* its gradient w.r.t. X in one launch: dX = PS_r^T(mirror_pad^T(conv^T(dy, w))) (transposed convolution, fold of the mirrored
+ * border, inverse phase shift), dy = [B, a*r, b*r, Cout] */
+int pnp_ps_mirror_conv_bwd(const float* dy, const float* w, float* dX, int B, int a, int b, int G, int r, int kh, int kw,
+                           int Cout, int order_b1, void* stream);
 
 /* ---- convolution, tcgen05 + TMA tensor-core path (conv_tc.cu) ----------------------------------
  * Same math as pnp_conv2d_fwd for convolutions whose Cin and Cout are each a multiple of 64, or exactly 32 or 16 (any stride /

@@ -48,6 +48,7 @@ SIGNATURES = {
     "pnp_conv2d_wgrad": [P, P, P, _GEOM, P],
     "pnp_weight_transpose": [P, P, c_int, c_int, c_int, P],
     "pnp_ps_mirror_conv_fwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "pnp_ps_mirror_conv_bwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "pnp_split_bf16": [P, P, P, c_ll, P],
     "pnp_split_weight_bf16": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "pnp_split_bf16_pad": [P, P, P, c_ll, c_int, c_int, P],

@@ -726,6 +726,100 @@ ps_mirror_conv_kernel(const float* __restrict__ X, const float* __restrict__ w, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward of the fused tail w.r.t. its feature-map input, in ONE kernel:
+//     dX = PS_r^T( mirror_pad^T( conv^T(dy, w) ) )        (the G step's path from d logits to d conv10)
+// Output-stationary over the unpadded 256x256 map: dflat[Y, X, g] = sum over the padded positions (py, px) that mirror onto
+// (Y, X) -- (Y+p, X+p) itself, plus the reflected rows / columns for the p border pixels -- of
+//     dpadded[py, px, g] = sum_{ky,kx,o} dy[py-ky, px-kx, o] * w[ky, kx, g, o]      (dy outside the image = 0)
+// and dX[n, Y/r, X/r, g*r*r + (X%r)*r + (Y%r)] = dflat[Y, X, g] (batch >= 2 order; transposed for B == 1).
+// r1/r2a: transposed conv 477 us + mirror fold 108 us + inverse phase shift ~100 us per G step.
+// ------------------------------------------------------------------------------------------------
+template <int NO>
+__global__ void __launch_bounds__(256)
+ps_mirror_conv_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dX, int B, int a, int b, int G,
+                          int r, int kh, int kw, int order_b1) {
+  constexpr int T = 32, CC = 8, HALO = T + 4;
+  __shared__ float s_d[NO][HALO][HALO + 1];       // dy tile with halo, channel-major
+  __shared__ __align__(16) float s_w[25][NO][CC];  // [tap][out channel of the forward conv][group]: 8 groups = two 128-bit broadcasts
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * T, y0 = blockIdx.y * T, n = blockIdx.z;
+  const int H = a * r, W = b * r, rr = r * r;
+  const int ph = kh / 2, pw = kw / 2;
+  const int hh = T + kh - 1, hw = T + kw - 1;
+  const long long Ctot = (long long)G * rr;
+  // dy halo tile: rows y0-ph .. y0+T-1+ph of the image (zero outside): dpadded[py] with py = Y+ph reads dy rows Y+ph-ky
+  const float* dyn = dy + (long long)n * H * W * NO;
+  for (int p = threadIdx.x; p < hh * hw; p += 256) {
+    const int py = p / hw, px = p - py * hw;
+    const int iy = y0 + py - ph, ix = x0 + px - pw;
+    const bool in = iy >= 0 && iy < H && ix >= 0 && ix < W;
+#pragma unroll
+    for (int o = 0; o < NO; ++o) s_d[o][py][px] = in ? __ldg(dyn + ((long long)iy * W + ix) * NO + o) : 0.f;
+  }
+  // this thread's 4 output pixels (column tx, rows ty + 8j) and their mirror images: padded positions that fold onto (Y, X)
+  const int X = x0 + tx;
+  int xs[3], nx = 0;                           // padded columns, relative to the dy halo tile: px_rel = Xp - x0 (Xp = padded col)
+  if (X < W) {
+    xs[nx++] = X + pw;
+    if (X < pw) xs[nx++] = pw - 1 - X;
+    if (X >= W - pw) xs[nx++] = 2 * W - 1 - X + pw;
+  }
+  float* dXn = dX + (long long)n * a * b * Ctot;
+  for (int c0 = 0; c0 < G; c0 += CC) {
+    __syncthreads();
+    for (int p = threadIdx.x; p < kh * kw * CC * NO; p += 256) {
+      const int o = p % NO, c = (p / NO) % CC, t = p / (NO * CC);
+      s_w[t][o][c] = (c0 + c < G) ? __ldg(w + ((long long)t * G + c0 + c) * NO + o) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int Y = y0 + ty + 8 * j;
+      if (Y >= H || X >= W) continue;
+      int ys[3], ny = 0;
+      ys[ny++] = Y + ph;
+      if (Y < ph) ys[ny++] = ph - 1 - Y;
+      if (Y >= H - ph) ys[ny++] = 2 * H - 1 - Y + ph;
+      float acc[CC];
+#pragma unroll
+      for (int c = 0; c < CC; ++c) acc[c] = 0.f;
+      for (int iyp = 0; iyp < ny; ++iyp)
+        for (int ixp = 0; ixp < nx; ++ixp) {
+          // dpadded[Yp, Xp] = sum_taps dy[Yp-ky, Xp-kx] * w[ky,kx]; tile-relative dy row of image row q is q - (y0 - ph)
+          const int Yp = ys[iyp], Xp = xs[ixp];
+          for (int ky = 0; ky < kh; ++ky) {
+            const int ry = Yp - ky - (y0 - ph);          // image row Yp-ky, in halo coordinates
+            if (ry < 0 || ry >= hh) continue;            // outside the halo == outside the image (see below)
+            for (int kx = 0; kx < kw; ++kx) {
+              const int rx = Xp - kx - (x0 - pw);
+              if (rx < 0 || rx >= hw) continue;
+              const int t = ky * kw + kx;
+              float d[NO];
+#pragma unroll
+              for (int o = 0; o < NO; ++o) d[o] = s_d[o][ry][rx];
+#pragma unroll
+              for (int o = 0; o < NO; ++o) {
+                const float4 w0 = *reinterpret_cast<const float4*>(&s_w[t][o][0]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&s_w[t][o][4]);
+                acc[0] = fmaf(d[o], w0.x, acc[0]); acc[1] = fmaf(d[o], w0.y, acc[1]);
+                acc[2] = fmaf(d[o], w0.z, acc[2]); acc[3] = fmaf(d[o], w0.w, acc[3]);
+                acc[4] = fmaf(d[o], w1.x, acc[4]); acc[5] = fmaf(d[o], w1.y, acc[5]);
+                acc[6] = fmaf(d[o], w1.z, acc[6]); acc[7] = fmaf(d[o], w1.w, acc[7]);
+              }
+            }
+          }
+        }
+      const int iy = Y / r, qy = Y - iy * r, ix = X / r, qx = X - ix * r;
+      const int sub = order_b1 ? (qy * r + qx) : (qx * r + qy);
+      float* dst = dXn + ((long long)iy * b + ix) * Ctot + sub;
+#pragma unroll
+      for (int c = 0; c < CC; ++c)
+        if (c0 + c < G) dst[(long long)(c0 + c) * rr] = acc[c];
+    }
+  }
+}
+
 bool geom_ok(const pnp_conv_geom* g) {
   return g && g->B > 0 && g->H > 0 && g->W > 0 && g->Cin > 0 && g->Ho > 0 && g->Wo > 0 && g->Cout > 0 && g->kh > 0 &&
          g->kw > 0 && g->stride > 0 && g->dil > 0 && g->pad_t >= 0 && g->pad_l >= 0;
@@ -769,6 +863,19 @@ extern "C" int pnp_ps_mirror_conv_fwd(const float* X, const float* w, float* y, 
   dim3 grid(pnp_cdiv(b * r, 32), pnp_cdiv(a * r, 32), B);
   if (Cout == 5) ps_mirror_conv_kernel<5><<<grid, 256, 0, (cudaStream_t)stream>>>(X, w, y, B, a, b, G, r, kh, kw, order_b1);
   else if (Cout == 8) ps_mirror_conv_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(X, w, y, B, a, b, G, r, kh, kw, order_b1);
+  else return PNP_ERR_UNSUPPORTED;
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_ps_mirror_conv_bwd(const float* dy, const float* w, float* dX, int B, int a, int b, int G, int r, int kh, int kw,
+                                      int Cout, int order_b1, void* stream) {
+  if (!dy || !w || !dX || B <= 0 || a <= 0 || b <= 0 || G <= 0 || r <= 0) return PNP_ERR_BAD_ARG;
+  if (kh > 5 || kw > 5 || kh < 1 || kw < 1 || (kh & 1) == 0 || (kw & 1) == 0 || B > 65535) return PNP_ERR_UNSUPPORTED;
+  if (kh / 2 > a * r || kw / 2 > b * r) return PNP_ERR_UNSUPPORTED;
+  dim3 grid(pnp_cdiv(b * r, 32), pnp_cdiv(a * r, 32), B);
+  if (Cout == 5) ps_mirror_conv_bwd_kernel<5><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, w, dX, B, a, b, G, r, kh, kw, order_b1);
+  else if (Cout == 8) ps_mirror_conv_bwd_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, w, dX, B, a, b, G, r, kh, kw, order_b1);
   else return PNP_ERR_UNSUPPORTED;
   PNP_LAUNCH_CHECK();
   return PNP_OK;

@@ -1110,7 +1110,7 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
   }
   {
     static int bres_env = -1;
-    if (bres_env < 0) { const char* e = getenv("PNP_TC_BRES"); bres_env = e ? atoi(e) : 1; }
+    if (bres_env < 0) { const char* e = getenv("PNP_TC_BRES"); bres_env = e ? atoi(e) : 0; }   // measured r2j: resident weights are SLOWER (16-channel kernel 4.85 vs 4.63 ms per 3 steps): off
     const long long wbytes = (long long)a.ntaps * a.kchunks * (nterms == 3 ? 2 : 1) * block_n * bk * 2;
     a.b_resident = (bres_env && block_n <= 32 && a.Cout == block_n && a.ksplit == 1 && wbytes <= 40 * 1024) ? 1 : 0;
   }

@@ -771,6 +771,12 @@ class _TailFn(torch.autograd.Function):
         kh, kw, cin, cout = w.shape
         p = kh // 2
         H, W = a * r, b * r
+        if FUSE_TAIL_BWD:
+            dX = torch.empty(B, a, b, G * r * r, dtype=dy.dtype, device=dy.device)
+            flops = 2.0 * B * H * W * cout * kh * kw * cin
+            _tc_launch("simt:tailbwd%dx%d.%d.%d" % (H, cin, cout, kh), flops, "pnp_ps_mirror_conv_bwd", ptr(dy.contiguous()), ptr(w), ptr(dX),
+                       B, a, b, G, r, kh, kw, cout, o, rt.stream())
+            return dX, None, None, None, None
         geom = ConvGeom(B, H + 2 * p, W + 2 * p, cin, H, W, cout, kh, kw, 1, 1, 0, 0)
         dxp = conv_dgrad_raw(dy.contiguous(), w, geom)
         dflat = torch.empty(B, H, W, cin, dtype=dy.dtype, device=dy.device)
@@ -782,6 +788,8 @@ class _TailFn(torch.autograd.Function):
 
 # PNP_FUSE_TAIL=0: phase shift, mirror pad and output convolution as three kernels
 FUSE_TAIL = os.environ.get("PNP_FUSE_TAIL", "1") != "0"
+# PNP_FUSE_TAIL_BWD=0: its input gradient as transposed conv -> mirror-pad fold -> inverse phase shift (three kernels)
+FUSE_TAIL_BWD = os.environ.get("PNP_FUSE_TAIL_BWD", "1") != "0"
 
 
 def tail_ps_conv(X, w, r, n_channel, batch_size):

@@ -578,7 +578,12 @@ def test_tail_ps_mirror_conv_equals_three_kernels(B):
     y = F.tail_ps_conv(Xg, wg, r, G, B)
     check("fused tail vs oracle", y, yo, 1e-5)
     y.backward(rr.to(DEV))
-    check("dX", Xg.grad, Xo.grad, 1e-5)
+    check("dX (one-kernel backward)", Xg.grad, Xo.grad, 1e-5)
+    F.FUSE_TAIL_BWD = False
+    Xg2 = _var(X)
+    F.tail_ps_conv(Xg2, wg, r, G, B).backward(rr.to(DEV))
+    F.FUSE_TAIL_BWD = True
+    check("dX (three-kernel backward)", Xg2.grad, Xo.grad, 1e-5)
     Xs = _var(X, False)
     ys = L.conv2d(ops.PS(Xs, r, n_channel=G, batch_size=B), wg, 1.0, padding="SYMMETRIC")
     check("fused tail vs separate kernels", y, ys, 1e-6)
