@@ -248,6 +248,10 @@ int pnp_adam_step(float* theta, const float* grad, float* m, float* v, long long
 int pnp_rmsprop_step(float* theta, const float* grad, float* ms, float* mom, long long n, const int* chunk_seg,
                      const float* seg_wd, const float* seg_clip, const float* lr_ptr /* device scalar */, float decay,
                      float momentum, float eps, float grad_scale, void* stream);
+/* tf.train.MomentumOptimizer (the source segmenter's other optimizer branch, source_segmenter.py:360-372): accum = momentum*accum +
+ * (grad*grad_scale + wd*theta); theta -= lr*accum; lr is a device scalar (the staircase exponential decay is host logic) */
+int pnp_momentum_step(float* theta, const float* grad, float* accum, long long n, const int* chunk_seg, const float* seg_wd,
+                      const float* lr_ptr, float momentum, float grad_scale, void* stream);
 int pnp_fill(float* p, float v, long long n, void* stream);
 
 #ifdef __cplusplus

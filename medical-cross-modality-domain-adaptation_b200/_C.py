@@ -92,6 +92,7 @@ SIGNATURES = {
     "pnp_adam_advance": [P, c_float, c_float, P],
     "pnp_adam_step": [P, P, P, P, c_ll, P, P, P, c_float, c_float, c_float, c_float, P],
     "pnp_rmsprop_step": [P, P, P, P, c_ll, P, P, P, P, c_float, c_float, c_float, c_float, P],
+    "pnp_momentum_step": [P, P, P, c_ll, P, P, P, c_float, c_float, P],
     "pnp_fill": [P, c_float, c_ll, P],
 }
 

@@ -445,6 +445,41 @@ class Trainer(object):
             cm = F.confusion_counts(out["logits"], ct_labels_onehot)
         return {"dice_eval": float(dice), "dice_arr": [float(a) for a in arr], "confusion_matrix": cm.cpu().numpy()}
 
+    def test_eval_volume(self, raw, raw_y, flip_correction=True, shuffle_seed=None):
+        """adversarial.py:993-1052 for ONE subject without the NIfTI reader: `raw` [256,256,D] intensity volume, `raw_y` [256,256,D]
+        integer labels (what read_nii_image returns).  Like the reference: optional flip of both in-plane axes, frames 1..D-2 (each
+        fed with its two neighbours as channels) in shuffled order, floor(D / batch) full batches -- the remaining frames are
+        dropped as the reference drops them --, inference-mode forward (keep_prob 1, BN switches off), confusion matrix summed
+        over the subject.  Returns (per-class Dice, per-class Jaccard, confusion matrix, predicted label volume)."""
+        from .lib import _dice, _jaccard, _label_decomp
+        raw = np.asarray(raw, np.float32)
+        raw_y = np.asarray(raw_y)
+        if flip_correction:
+            raw, raw_y = np.flip(np.flip(raw, 0), 1), np.flip(np.flip(raw_y, 0), 1)
+        B, nc = self.net.batch_size, self.num_cls or self.net.n_class
+        frames = list(range(1, raw.shape[2] - 1))
+        (np.random if shuffle_seed is None else np.random.RandomState(shuffle_seed)).shuffle(frames)
+        dev = rt.device()
+        cm = torch.zeros(nc, nc, dtype=torch.int64, device=dev)
+        pred_vol = np.zeros(raw_y.shape, np.int64)
+        for ii in range(raw.shape[2] // B):
+            idx = frames[ii * B:(ii + 1) * B]
+            vol = np.zeros((B,) + raw.shape[:2] + (3,), np.float32)
+            sl = np.zeros((B,) + raw.shape[:2], np.int64)
+            for k, jj in enumerate(idx):
+                vol[k] = raw[..., jj - 1:jj + 2]
+                sl[k] = raw_y[..., jj]
+            x = torch.from_numpy(vol).to(dev)
+            y = _label_decomp(nc, torch.from_numpy(sl).to(dev))
+            with torch.no_grad():
+                logits = self.net.segment(x, "ct", 1.0, front_bn=False, joint_bn=False)["logits"]
+                cm += F.confusion_counts(logits, y)
+                pred = logits.argmax(3).cpu().numpy()
+            for k, jj in enumerate(idx):
+                pred_vol[..., jj] = pred[k]
+        cmh = cm.cpu().numpy()
+        return _dice(cmh), _jaccard(cmh), cmh, pred_vol
+
     # ---- steps as CUDA graphs -----------------------------------------------------------------------------------------
     def _capture(self, fn, warmup):
         """Capture `fn()` (forward, backward, all-reduce, optimizer, clip: ~1 k kernel launches) into one CUDA graph.

@@ -994,6 +994,25 @@ rmsprop_kernel(float* __restrict__ theta, const float* __restrict__ grad, float*
   reinterpret_cast<float4*>(mom)[i] = mo;
 }
 
+// tf.train.MomentumOptimizer (source_segmenter.py:371): accum = momentum*accum + g ; theta -= lr*accum   (g includes wd*theta)
+__global__ void __launch_bounds__(256)
+momentum_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ accum, const int* __restrict__ chunk_seg,
+                const float* __restrict__ seg_wd, const float* __restrict__ lr_ptr, float momentum, float gscale) {
+  const int seg = chunk_seg[blockIdx.x];
+  const float lr = *lr_ptr;
+  const float wd = seg_wd[seg];
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  float4 t = reinterpret_cast<float4*>(theta)[i];
+  const float4 g = __ldg(reinterpret_cast<const float4*>(grad) + i);
+  float4 ac = reinterpret_cast<float4*>(accum)[i];
+  ac.x = momentum * ac.x + fmaf(wd, t.x, g.x * gscale); t.x -= lr * ac.x;
+  ac.y = momentum * ac.y + fmaf(wd, t.y, g.y * gscale); t.y -= lr * ac.y;
+  ac.z = momentum * ac.z + fmaf(wd, t.z, g.z * gscale); t.z -= lr * ac.z;
+  ac.w = momentum * ac.w + fmaf(wd, t.w, g.w * gscale); t.w -= lr * ac.w;
+  reinterpret_cast<float4*>(theta)[i] = t;
+  reinterpret_cast<float4*>(accum)[i] = ac;
+}
+
 // state = [beta1^t, beta2^t, lr, lr_t]: advance t and refresh lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t) (TF Adam)
 __global__ void adam_advance_kernel(double* state, double b1, double b2) {
   double p1 = state[0] * b1, p2 = state[1] * b2;
@@ -1413,6 +1432,14 @@ extern "C" int pnp_rmsprop_step(float* theta, const float* grad, float* ms, floa
   if (!theta || !grad || !ms || !mom || !chunk_seg || !seg_wd || !lr_ptr || n <= 0 || (n % 1024) != 0) return PNP_ERR_BAD_ARG;
   rmsprop_kernel<<<(unsigned)(n / 1024), 256, 0, S_>>>(theta, grad, ms, mom, chunk_seg, seg_wd, seg_clip, lr_ptr, decay, momentum, eps,
                                                       grad_scale);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+extern "C" int pnp_momentum_step(float* theta, const float* grad, float* accum, long long n, const int* chunk_seg, const float* seg_wd,
+                                 const float* lr_ptr, float momentum, float grad_scale, void* stream) {
+  if (!theta || !grad || !accum || !chunk_seg || !seg_wd || !lr_ptr || n <= 0 || (n % 1024) != 0) return PNP_ERR_BAD_ARG;
+  momentum_kernel<<<(unsigned)(n / 1024), 256, 0, S_>>>(theta, grad, accum, chunk_seg, seg_wd, lr_ptr, momentum, grad_scale);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }

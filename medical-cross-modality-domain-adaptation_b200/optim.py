@@ -158,3 +158,41 @@ class RMSProp:
         call("pnp_rmsprop_step", ptr(a.theta), ptr(a.grad), ptr(self.ms), ptr(self.mom), a.total, ptr(a.chunk_seg), ptr(self.seg_wd),
              ptr(self.seg_clip), ptr(self.lr_t), self.decay, self.momentum, self.eps, float(grad_scale), rt.stream())
         a.bump_versions()
+
+
+class Momentum:
+    """tf.train.MomentumOptimizer(learning_rate=exponential_decay(lr, global_step, decay_steps, decay_rate, staircase=True),
+    momentum) over an Arena -- the source segmenter's `optimizer="momentum"` branch (source_segmenter.py:360-372; defaults
+    learning_rate 0.2, decay_rate 0.95, momentum 0.2)."""
+
+    def __init__(self, arena, lr=0.2, decay_rate=0.95, momentum=0.2, decay_steps=100, weight_decay=None):
+        self.arena = arena
+        self.lr0, self.decay_rate, self.momentum, self.decay_steps = float(lr), float(decay_rate), float(momentum), int(decay_steps)
+        dev = arena.theta.device
+        self.accum = torch.zeros_like(arena.theta)
+        self.lr_t = torch.tensor([float(lr)], dtype=torch.float32, device=dev)
+        self.seg_wd = arena.seg_table(weight_decay if weight_decay is not None else [0.0] * len(arena.vars))
+        self.global_step = 0
+
+    def current_lr(self):
+        return self.lr0 * self.decay_rate ** (self.global_step // max(1, self.decay_steps))
+
+    def set_lr(self, lr):
+        self.lr0 = float(lr)
+
+    def get_lr(self):
+        return self.current_lr()
+
+    def slot_state(self):
+        return _export_slots(self.arena, {"Momentum": self.accum})
+
+    def load_slot_state(self, d):
+        return _import_slots(self.arena, {"Momentum": self.accum}, d)
+
+    def step(self, grad_scale=1.0):
+        a = self.arena
+        self.lr_t[0] = self.current_lr()                 # staircase decay is evaluated at the step's global_step, as TF does
+        call("pnp_momentum_step", ptr(a.theta), ptr(a.grad), ptr(self.accum), a.total, ptr(a.chunk_seg), ptr(self.seg_wd),
+             ptr(self.lr_t), self.momentum, float(grad_scale), rt.stream())
+        self.global_step += 1
+        a.bump_versions()

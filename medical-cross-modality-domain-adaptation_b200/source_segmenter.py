@@ -146,8 +146,9 @@ class Trainer(object):
         self.opt_kwargs = dict(opt_kwargs)
         self.lr_update_flag = lr_update_flag
         self.train_list, self.val_list = train_list, val_list
-        if optimizer != "adam":
-            raise NotImplementedError("only the reference's configured optimizer (adam, train_segmenter.py:38) is on the hot path")
+        if optimizer not in ("adam", "momentum"):
+            raise ValueError("optimizer must be 'adam' or 'momentum' (source_segmenter.py:359-381)")
+        self.optimizer_name = optimizer
         self.source = source
         self.global_step = 0
         self.dp = parallel.DataParallel()
@@ -159,9 +160,15 @@ class Trainer(object):
         self.trainables = tv
         self.arena = optim.Arena(tv)
         self.dp.attach(self.arena)
-        lr = self.opt_kwargs.pop("learning_rate", 1e-3)
-        self._new_LR = lr
-        self.optimizer = optim.Adam(self.arena, lr=lr, weight_decay=self.net.weight_decay_table(tv), **self.opt_kwargs)
+        if self.optimizer_name == "momentum":
+            # source_segmenter.py:360-372; decay_steps = training_iters is bound when train() is called
+            self._new_LR = lr = self.opt_kwargs.pop("learning_rate", 0.2)
+            self.optimizer = optim.Momentum(self.arena, lr=lr, decay_rate=self.opt_kwargs.pop("decay_rate", 0.95),
+                                            momentum=self.opt_kwargs.pop("momentum", 0.2), weight_decay=self.net.weight_decay_table(tv))
+        else:
+            lr = self.opt_kwargs.pop("learning_rate", 1e-3)
+            self._new_LR = lr
+            self.optimizer = optim.Adam(self.arena, lr=lr, weight_decay=self.net.weight_decay_table(tv), **self.opt_kwargs)
         dev = self.arena.theta.device
         self._g_cross = torch.tensor(float(self.net.miu_cross or 0.0) if self.net.cross_flag else 0.0, device=dev)
         self._g_dice = torch.tensor(float(self.net.miu_dice or 0.0) if self.net.dice_flag else 0.0, device=dev)
@@ -255,8 +262,12 @@ class Trainer(object):
         elif restore:
             print("Unable to restore, start from beginning")
         self.dp.broadcast_variables(rt.global_variables())
-        self.dp.broadcast_params(self.optimizer.m)
-        self.dp.broadcast_params(self.optimizer.v)
+        if self.optimizer_name == "momentum":
+            self.optimizer.decay_steps = training_iters
+            self.dp.broadcast_params(self.optimizer.accum)
+        else:
+            self.dp.broadcast_params(self.optimizer.m)
+            self.dp.broadcast_params(self.optimizer.v)
         if self.source is not None:
             src = self.source
         elif self.train_list:      # the reference's lists/*_train_list of single-example TFRecord files

@@ -148,3 +148,49 @@ def test_evaluation_path_matches_oracle():
     cm = st["confusion_matrix"]
     assert cm.sum() == B * 256 * 256 and np.abs(cm - cm_ref).sum() <= 2e-3 * cm.sum(), (cm, cm_ref)
     rt.set_conv_backend("auto")
+
+
+def test_per_volume_evaluation_matches_oracle():
+    """Trainer.test_eval_volume (adversarial.py:993-1052 without the NIfTI reader): a synthetic [256,256,D] subject, frames fed with
+    their neighbours as channels, confusion matrix over the subject -> per-class Dice / Jaccard (lib.py:121-152) == the same
+    protocol run on the oracle"""
+    import pnp_b200  # noqa: F401
+    from pnp_b200 import runtime as rt, adversarial as adv
+    from pnp_b200.data import label_maps
+    from pnp_b200.lib import _dice, _jaccard
+    from pnp_b200.train_gan import configure
+    from oracle.pnp_graphs import OracleAdversarial, init_numpy_params
+    rt.set_conv_backend("auto")
+    ws, bns = OracleAdversarial.layout()
+    P = init_numpy_params(ws, bns, 0, 0.05)
+    _bn_noise(P, bns, 6)
+    ck, nc, tc = configure("train-gan")
+    net = adv.Full_DRN(channels=3, n_class=5, batch_size=B, cost_kwargs=ck, network_config=nc)
+    rt.load_state_dict(P)
+    trainer = adv.Trainer(net, num_cls=5, batch_size=B, opt_kwargs={"learning_rate": 3e-4}, train_config=tc)
+    D = 7                                   # 5 usable frames -> floor(7 / 2) = 3 batches of 2, as the reference counts them
+    rng = np.random.RandomState(3)
+    raw = rng.randn(256, 256, D).astype(np.float32)
+    raw_y = np.transpose(label_maps(D, 55), (1, 2, 0)).copy()
+    dice, jac, cm, pred = trainer.test_eval_volume(raw, raw_y, flip_correction=True, shuffle_seed=9)
+    # the same protocol on the oracle
+    oracle = OracleAdversarial(P, B, lambda_mask_loss=0.3, dis_sub_iter=1, gen_sub_iter=1)
+    r2, y2 = np.flip(np.flip(raw, 0), 1), np.flip(np.flip(raw_y, 0), 1)
+    frames = list(range(1, D - 1))
+    np.random.RandomState(9).shuffle(frames)
+    cm_ref = np.zeros((5, 5), np.int64)
+    for ii in range(D // B):
+        idx = frames[ii * B:(ii + 1) * B]
+        vol = np.zeros((B, 256, 256, 3), np.float32)
+        sl = np.zeros((B, 256, 256), np.int64)
+        for k, jj in enumerate(idx):
+            vol[k] = r2[..., jj - 1:jj + 2]
+            sl[k] = y2[..., jj]
+        with torch.no_grad():
+            p_ref = oracle.segment(torch.from_numpy(vol), "ct", 1.0, False)["logits"].argmax(3).numpy()
+        np.add.at(cm_ref, (sl.reshape(-1), p_ref.reshape(-1)), 1)
+    print("  per-class Dice   ours", np.round(dice, 5), "oracle", np.round(_dice(cm_ref), 5))
+    print("  per-class Jaccard ours", np.round(jac, 5), "oracle", np.round(_jaccard(cm_ref), 5))
+    assert cm.sum() == cm_ref.sum() == (D // B) * B * 256 * 256
+    assert np.abs(cm - cm_ref).sum() <= 2e-3 * cm.sum()
+    assert np.abs(dice - _dice(cm_ref)).max() <= 1e-3 and np.abs(jac - _jaccard(cm_ref)).max() <= 1e-3

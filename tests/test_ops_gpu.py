@@ -434,6 +434,35 @@ def test_optimizers_match_tf_semantics():
             check("%s theta[%d]" % (kind, i), p.detach(), q, 1e-5)
 
 
+def test_momentum_optimizer_matches_tf_semantics():
+    """the source segmenter's `optimizer="momentum"` branch (source_segmenter.py:360-372): tf.train.MomentumOptimizer
+    (accum = momentum*accum + g; theta -= lr*accum) under exponential_decay(lr, step, decay_steps, decay_rate, staircase=True),
+    against a numpy statement of those two published formulas; 5 steps across a staircase boundary"""
+    L, ops, F, rt = _prod()
+    from pnp_b200 import optim
+    shapes = [(3, 3, 8, 16), (16,), (2048, 1)]
+    ps = [randn(s, 300 + i, 0.05) for i, s in enumerate(shapes)]
+    po = [p.double().numpy().copy() for p in ps]
+    acc = [np.zeros_like(p) for p in po]
+    pg = [_var(p) for p in ps]
+    arena = optim.Arena(pg)
+    wd = [1e-4, 0.0, 2e-4]
+    opt = optim.Momentum(arena, lr=0.2, decay_rate=0.95, momentum=0.2, decay_steps=2, weight_decay=wd)
+    for step in range(5):
+        gs = [randn(s, 400 + 10 * step + i, 0.1) for i, s in enumerate(shapes)]
+        arena.zero_grad()
+        for p, g in zip(pg, gs):
+            p.grad.copy_(g.to(DEV) * 4.0)              # 4 ranks summed
+        opt.step(grad_scale=0.25)
+        lr = 0.2 * 0.95 ** (step // 2)
+        for i, g in enumerate(gs):
+            acc[i] = 0.2 * acc[i] + (g.double().numpy() + wd[i] * po[i])
+            po[i] = po[i] - lr * acc[i]
+    assert abs(opt.get_lr() - 0.2 * 0.95 ** 2) < 1e-12
+    for i, (p, q) in enumerate(zip(pg, po)):
+        check("momentum theta[%d]" % i, p.detach(), torch.from_numpy(q), 1e-5)
+
+
 def test_dropout_statistics_and_backward_consistency():
     """tf.nn.dropout semantics: keep fraction ~ keep_prob, kept values scaled by 1/keep, the backward pass
     regenerates the same mask; distinct call sites / steps draw distinct masks."""
