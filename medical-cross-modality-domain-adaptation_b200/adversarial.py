@@ -445,6 +445,47 @@ class Trainer(object):
             cm = F.confusion_counts(out["logits"], ct_labels_onehot)
         return {"dice_eval": float(dice), "dice_arr": [float(a) for a in arr], "confusion_matrix": cm.cpu().numpy()}
 
+    # the reference's TensorBoard scalar tags (adversarial.py:664-683), written as JSON lines because TensorBoard is not a dependency
+    SCALAR_TAGS = ("fixed_coeff_reg", "discriminator_loss", "generator_loss", "ct_dice_eval_c1_lv_myo", "ct_dice_eval_c2_la_blood",
+                   "ct_dice_eval_c3_lv_blood", "ct_dice_eval_c4_aa", "mri_dice", "learning_rate")
+
+    def output_minibatch_stats(self, step, ct_batch, ct_batch_y, mr_batch, mr_batch_y, log_dir=None, detail=False):
+        """adversarial.py:948-990, scalar part: one monitoring pass with the segmenter in inference mode and keep_prob 1 (the feed
+        also sets cls_bn False, but create_classifier / create_mask_critic never read that placeholder: the critics run with
+        their hard-wired batch-statistics BN -- moving averages move -- and keep_prob 0.75, reproduced).  Returns the scalars under
+        the reference's tags and appends them to <log_dir>/scalars.jsonl; detail=True also prints per-organ Dice / Jaccard."""
+        import json
+        from .lib import _indicator_eval
+        net = self.net
+        rt.scratch.begin_step()
+        nc = self.num_cls or net.n_class
+        if ct_batch_y.dim() == 3:            # integer label maps: the host-side _label_decomp of the reference, on the device
+            ct_batch_y = F.one_hot(ct_batch_y, nc)
+        if mr_batch_y.dim() == 3:
+            mr_batch_y = F.one_hot(mr_batch_y, nc)
+        with torch.no_grad():
+            fc_ = net.segment(ct_batch, "ct", 1.0, front_bn=False, joint_bn=False)
+            fm = net.segment(mr_batch, "mr", 1.0, front_bn=False, joint_bn=False)
+            ct_cls, mr_cls = net.classify(fc_), net.classify(fm)
+            ct_m = mr_m = None
+            if net.lambda_mask_loss != 0:
+                ct_m, mr_m = net.create_mask_critic(fc_["logits"]), net.create_mask_critic(fm["logits"])
+            dis = self.loss_value(net.dis_loss_terms(ct_cls, mr_cls, ct_m, mr_m))
+            gen = self.loss_value(net.gen_loss_terms(ct_cls, ct_m))
+            ct_d, ct_arr = net.dice_eval(fc_["logits"], ct_batch_y)
+            mr_d, _ = net.dice_eval(fm["logits"], mr_batch_y)
+            cm = F.confusion_counts(fc_["logits"], ct_batch_y) if detail else None
+        vals = [net.fixed_coeff_reg(), dis, gen, float(ct_arr[1]), float(ct_arr[2]), float(ct_arr[3]), float(ct_arr[4]), float(mr_d),
+                self.dis_optimizer.get_lr()]
+        scalars = dict(zip(self.SCALAR_TAGS, vals))
+        if detail:
+            _indicator_eval(cm.cpu().numpy())
+        if log_dir is not None and self.dp.rank == 0:
+            os.makedirs(log_dir, exist_ok=True)
+            with open(os.path.join(log_dir, "scalars.jsonl"), "a") as f:
+                f.write(json.dumps(dict(step=int(step), **scalars)) + "\n")
+        return scalars
+
     def test_eval_volume(self, raw, raw_y, flip_correction=True, shuffle_seed=None):
         """adversarial.py:993-1052 for ONE subject without the NIfTI reader: `raw` [256,256,D] intensity volume, `raw_y` [256,256,D]
         integer labels (what read_nii_image returns).  Like the reference: optional flip of both in-plane axes, frames 1..D-2 (each
@@ -667,8 +708,18 @@ class Trainer(object):
                     self.gen_sub_iter += gen_inc
                 if step % display_step == 0:
                     logging.info("Training step %s epoch %s finished, %.3f s" % (step, epoch, time.time() - start))
+                    # the monitoring passes of adversarial.py:894-922: a training batch, then a "validation" batch with the
+                    # per-organ table (the synthetic / list sources stand in for the separate validation queues)
+                    for sub, detail in (("train_log", False), ("val_log", True)):
+                        (ct, cty), (mr, mry) = ct_src.next(), mr_src.next()
+                        self.output_minibatch_stats(step, to_device(ct, dev), to_device(cty, dev), to_device(mr, dev), to_device(mry, dev),
+                                                    os.path.join(output_path, sub), detail)
                 if step % ckpt_space == 0 and step != 0:
                     self.save(save_path, output_path)
+                    # "Model has been restored for re-allocation" (adversarial.py:929-935): the reference re-reads the checkpoint it
+                    # has just written -- numerically a no-op, kept so that a corrupt write surfaces immediately on every rank
+                    self.net.restore(os.path.join(output_path, "latest.npz"))
+                    self.load_optimizer_state(self.net.last_restored)
                     lr = self.dis_optimizer.get_lr() * decay
                     self.dis_optimizer.set_lr(lr)
                     self.gen_optimizer.set_lr(lr)

@@ -424,7 +424,11 @@ def test_training_schedule_and_step_feeds_match_the_reference(tmp_path):
     tr.d_step = lambda mr, ct, keep_prob=0.75, apply=True: got.append(("D+clip", keep_prob, tuple(mr.shape), tuple(ct.shape)))
     tr.g_step = lambda ct, keep_prob=0.75, apply=True: got.append(("G", keep_prob, tuple(ct.shape)))
     wd_before = tr.dis_optimizer.seg_wd.clone()
+    mon = []
+    tr.output_minibatch_stats = lambda step, ct, cty, mr, mry, log_dir=None, detail=False: mon.append((step, os.path.basename(log_dir), detail))
     tr.train(output_path=str(tmp_path), restore=True, restored_path=str(tmp_path), **sched["train_args"])
+    # the monitoring passes (adversarial.py:894-922): every display_step a training batch, then a validation batch with the table
+    assert mon and all(a[1:] == ("train_log", False) and b[1:] == ("val_log", True) and a[0] == b[0] for a, b in zip(mon[0::2], mon[1::2]))
     assert [g[0] for g in got] == ref_ops
     assert all(g[1] == 0.75 for g in got) and all(g[2] == (B, 256, 256, 3) for g in got)
     assert tr.dis_sub_iter == 4 and tr.gen_sub_iter == 1
