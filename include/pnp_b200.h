@@ -95,16 +95,6 @@ int pnp_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long long n, void
  * for_dgrad != 0: [tap][Cin][Cout] (K-major B operand of the data gradient) */
 int pnp_split_weight_bf16(const float* w, uint16_t* hi, uint16_t* lo, int kh, int kw, int Cin, int Cout,
                           int for_dgrad, int cin_pad /* forward layout only: zero-pad Cin up to this (0 = none) */, void* stream);
-/* The same for MANY (variable, layout) pairs in one launch: jobs_dev[njobs] and tile_start_dev[njobs] (prefix of 32x32 tile counts:
- * taps * ceil(CinP/32) * ceil(Cout/32) per job) live in device memory; total_tiles = sum.  The trainers refresh every stale weight
- * plane of a step with one call instead of one launch per variable and layout. */
-typedef struct {
-  const float* w;
-  uint16_t* hi;
-  uint16_t* lo;          /* NULL for the one-term path */
-  int taps, Cin, Cout, CinP, for_dgrad, pad_;
-} pnp_split_job;
-int pnp_split_weight_bf16_batched(const pnp_split_job* jobs_dev, const int* tile_start_dev, int njobs, int total_tiles, void* stream);
 /* [rows, C] fp32 -> [rows, Cpad] bf16 planes with zero channels >= C: Cin = 32 layers ride the 64-channel K chunk */
 int pnp_split_bf16_pad(const float* x, uint16_t* hi, uint16_t* lo, long long rows, int C, int Cpad, void* stream);
 int pnp_conv2d_tc_fwd(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo,

@@ -27,12 +27,6 @@ class TcEpilogue(ctypes.Structure):
                 ("y_hi", c_void_p), ("y_lo", c_void_p)]
 
 
-class SplitJob(ctypes.Structure):
-    """pnp_split_job"""
-    _fields_ = [("w", c_void_p), ("hi", c_void_p), ("lo", c_void_p), ("taps", c_int), ("Cin", c_int), ("Cout", c_int), ("CinP", c_int),
-                ("for_dgrad", c_int), ("pad_", c_int)]
-
-
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -58,7 +52,6 @@ SIGNATURES = {
     "pnp_split_bf16": [P, P, P, c_ll, P],
     "pnp_split_weight_bf16": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "pnp_split_bf16_pad": [P, P, P, c_ll, c_int, c_int, P],
-    "pnp_split_weight_bf16_batched": [P, P, c_int, c_int, P],
     "pnp_conv2d_tc_fwd": [P, P, P, P, P, _GEOM, c_int, _DROP, c_int, P, P, P],
     "pnp_conv2d_tc_fwd_fused": [P, P, P, P, P, _GEOM, c_int, _DROP, c_int, P, P, ctypes.POINTER(TcEpilogue), P],
     "pnp_conv2d_tc_dgrad": [P, P, P, P, P, _GEOM, c_int, c_int, P],

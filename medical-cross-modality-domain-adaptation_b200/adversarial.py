@@ -595,8 +595,7 @@ class Trainer(object):
 
     def _invalidate_operand_caches(self):
         for v in self.d_vars + self.g_vars:
-            for k_, ent in list(v.__dict__.get("_pnp_planes", {}).items()):
-                v.__dict__["_pnp_planes"][k_] = (-1, ent[1], ent[2])        # stale, same buffers (functional.PlaneRegistry)
+            v.__dict__.pop("_pnp_planes", None)
             v.__dict__.pop("_pnp_wT", None)
             v.__dict__.pop("_pnp_bncoef", None)      # inference-mode BN coefficients of the DAM (its statistics move in the G step)
 

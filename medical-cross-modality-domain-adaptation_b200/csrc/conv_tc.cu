@@ -662,14 +662,16 @@ split_bf16_pad_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, ui
 
 // w HWIO [taps][Cin][Cout] -> fwd : out[tap][co][ci]          (B operand rows = co, K = ci)
 //                             dgrad: out[tap][ci][co]          (B operand rows = ci, K = co)
-__device__ __forceinline__ void split_weight_tile(const float* __restrict__ w, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
-                                                  int Cin, int Cout, int for_dgrad, int CinP, int tap, int by, int bx,
-                                                  float (&tile)[32][33]) {
+__global__ void __launch_bounds__(256)
+split_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int taps, int Cin,
+                    int Cout, int for_dgrad, int CinP) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z;
   const float* src = w + (long long)tap * Cin * Cout;
   if (for_dgrad) {
     long long obase = (long long)tap * Cin * Cout;
-    int ci = by * 32 + threadIdx.y * 4;
-    int co = bx * 32 + threadIdx.x;
+    int ci = blockIdx.y * 32 + threadIdx.y * 4;
+    int co = blockIdx.x * 32 + threadIdx.x;
     for (int r = 0; r < 4; ++r) {
       if (ci + r < Cin && co < Cout) {
         uint16_t h, l;
@@ -680,7 +682,7 @@ __device__ __forceinline__ void split_weight_tile(const float* __restrict__ w, u
     }
     return;
   }
-  int ci0 = by * 32, co0 = bx * 32;
+  int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
   for (int r = threadIdx.y; r < 32; r += 8) {
     int ci = ci0 + r, co = co0 + threadIdx.x;
     tile[r][threadIdx.x] = (ci < Cin && co < Cout) ? src[(long long)ci * Cout + co] : 0.f;
@@ -696,34 +698,6 @@ __device__ __forceinline__ void split_weight_tile(const float* __restrict__ w, u
       if (lo) lo[obase + (long long)co * CinP + ci] = l;
     }
   }
-}
-
-__global__ void __launch_bounds__(256)
-split_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int taps, int Cin,
-                    int Cout, int for_dgrad, int CinP) {
-  __shared__ float tile[32][33];
-  split_weight_tile(w, hi, lo, Cin, Cout, for_dgrad, CinP, blockIdx.z, blockIdx.y, blockIdx.x, tile);
-}
-
-// every stale (variable, layout) pair of a step in ONE launch (r2: 86 split launches of ~5 us per step): block -> job by binary
-// search in the tile prefix, then the same 32x32 tile body
-__global__ void __launch_bounds__(256)
-split_weight_batched_kernel(const pnp_split_job* __restrict__ jobs, const int* __restrict__ tile_start, int njobs) {
-  __shared__ float tile[32][33];
-  const int t = blockIdx.x;
-  int lo_ = 0, hi_ = njobs - 1;
-  while (lo_ < hi_) {
-    const int mid = (lo_ + hi_ + 1) >> 1;
-    if (tile_start[mid] <= t) lo_ = mid; else hi_ = mid - 1;
-  }
-  const pnp_split_job j = jobs[lo_];
-  int r = t - tile_start[lo_];
-  const int tiles_x = (j.Cout + 31) >> 5, tiles_y = (j.CinP + 31) >> 5;
-  const int bx = r % tiles_x;
-  r /= tiles_x;
-  const int by = r % tiles_y;
-  const int tap = r / tiles_y;
-  split_weight_tile(j.w, j.hi, j.lo, j.Cin, j.Cout, j.for_dgrad, j.CinP, tap, by, bx, tile);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1224,14 +1198,6 @@ extern "C" int pnp_split_weight_bf16(const float* w, uint16_t* hi, uint16_t* lo,
   if (for_dgrad && CinP != Cin) return PNP_ERR_UNSUPPORTED;
   dim3 grid(pnp_cdiv(Cout, 32), pnp_cdiv(CinP, 32), kh * kw);
   split_weight_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(w, hi, lo, kh * kw, Cin, Cout, for_dgrad, CinP);
-  PNP_LAUNCH_CHECK();
-  return PNP_OK;
-}
-
-extern "C" int pnp_split_weight_bf16_batched(const pnp_split_job* jobs_dev, const int* tile_start_dev, int njobs, int total_tiles,
-                                             void* stream) {
-  if (!jobs_dev || !tile_start_dev || njobs <= 0 || total_tiles <= 0) return PNP_ERR_BAD_ARG;
-  split_weight_batched_kernel<<<(unsigned)total_tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(jobs_dev, tile_start_dev, njobs);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }

@@ -192,80 +192,11 @@ def _weight_planes(W, for_dgrad, nterms, cin_pad=0):
     if hit is not None and ver is not None and hit[0] == ver:
         return hit[1], hit[2]
     kh, kw, cin, cout = W.shape
-    if hit is not None:
-        hi, lo = hit[1], hit[2]          # stale values, same buffers: the addresses of a variable's planes never change
-    else:
-        hi = torch.empty(kh * kw * max(cin, cin_pad) * cout, dtype=torch.bfloat16, device=W.device)
-        lo = torch.empty_like(hi) if nterms == 3 else None
+    hi = torch.empty(kh * kw * max(cin, cin_pad) * cout, dtype=torch.bfloat16, device=W.device)
+    lo = torch.empty_like(hi) if nterms == 3 else None
     call("pnp_split_weight_bf16", ptr(W), ptr(hi), ptr(lo), kh, kw, cin, cout, 1 if for_dgrad else 0, cin_pad, rt.stream())
     cache[key] = (ver, hi, lo)
-    if getattr(W, "_pnp_arena", None) is not None:
-        plane_registry.add(W, key)
     return hi, lo
-
-
-class PlaneRegistry:
-    """Which (trainable variable, plane layout) pairs the steps use -- learned from the lazy path above -- so that a step can
-    refresh every STALE pair with one batched launch at its start (`refresh()`, called from runtime.begin_step) instead of one
-    split launch per variable and layout at first use (r2: 86 launches of ~5 us per joint step).  Buffers are persistent, so
-    the refresh is CUDA-graph friendly: a captured step begins with the batched split of the live arenas."""
-
-    def __init__(self):
-        self.items = {}            # (id(W), key) -> (W, key)
-        self.tables = {}           # frozenset of stale items -> (jobs tensor, tile_start tensor, njobs, total_tiles)
-
-    def add(self, W, key):
-        k = (id(W), key)
-        if k not in self.items:
-            self.items[k] = (W, key)
-            self.tables.clear()
-
-    def clear(self):
-        self.items.clear()
-        self.tables.clear()
-
-    def refresh(self):
-        if not BATCHED_SPLIT or not self.items:
-            return
-        stale = []
-        for k, (W, key) in self.items.items():
-            ent = W.__dict__.get("_pnp_planes", {}).get(key)
-            if ent is not None and ent[0] != getattr(W, "pnp_version", None):
-                stale.append(k)
-        if len(stale) < 2:
-            return                  # nothing (or a single pair): the lazy path handles it
-        sig = frozenset(stale)
-        tab = self.tables.get(sig)
-        if tab is None:
-            import numpy as np
-            jobs = (_C.SplitJob * len(stale))()
-            starts, total = [], 0
-            for i, k in enumerate(stale):
-                W, key = self.items[k]
-                for_dgrad, nterms, cin_pad = key
-                _, hi, lo = W.__dict__["_pnp_planes"][key]
-                kh, kw, cin, cout = W.shape
-                cinp = max(cin, cin_pad)
-                jobs[i] = _C.SplitJob(W.data_ptr(), hi.data_ptr(), lo.data_ptr() if lo is not None else None, kh * kw, cin, cout, cinp,
-                                      1 if for_dgrad else 0, 0)
-                starts.append(total)
-                total += kh * kw * (-(-cinp // 32)) * (-(-cout // 32))
-            dev = self.items[stale[0]][0].device
-            jt = torch.from_numpy(np.frombuffer(bytes(jobs), dtype=np.uint8).copy()).to(dev)
-            st = torch.tensor(starts, dtype=torch.int32, device=dev)
-            tab = (jt, st, len(stale), total)
-            self.tables[sig] = tab
-        jt, st, n, total = tab
-        call("pnp_split_weight_bf16_batched", ptr(jt), ptr(st), n, total, rt.stream())
-        for k in stale:
-            W, key = self.items[k]
-            _, hi, lo = W.__dict__["_pnp_planes"][key]
-            W.__dict__["_pnp_planes"][key] = (getattr(W, "pnp_version", None), hi, lo)
-
-
-# PNP_BATCHED_SPLIT=0: split weight planes lazily, one launch per variable and layout
-BATCHED_SPLIT = os.environ.get("PNP_BATCHED_SPLIT", "1") != "0"
-plane_registry = PlaneRegistry()
 
 
 def _padded_planes(x, nterms, cpad):

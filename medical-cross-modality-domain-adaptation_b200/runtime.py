@@ -111,8 +111,6 @@ class Scratch:
         if self.buf is not None and self.high > 0:
             _C.call("pnp_fill", self.buf.data_ptr(), 0.0, 2 * self.high, stream())
         self.off = self.high = 0
-        from . import functional as F          # every stale weight plane of the trainable arenas, one launch
-        F.plane_registry.refresh()
 
 
 scratch = Scratch()
@@ -139,10 +137,6 @@ graph = _Graph()
 
 def reset_default_graph():
     graph.reset()
-    import sys
-    F = sys.modules.get(__name__.rsplit(".", 1)[0] + ".functional")
-    if F is not None:
-        F.plane_registry.clear()
 
 
 @contextlib.contextmanager

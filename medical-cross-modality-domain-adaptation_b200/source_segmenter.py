@@ -201,8 +201,7 @@ class Trainer(object):
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             for v in self.trainables:          # see adversarial.Trainer._capture: no stale operand caches inside the graph
-                for k_, ent in list(v.__dict__.get("_pnp_planes", {}).items()):
-                    v.__dict__["_pnp_planes"][k_] = (-1, ent[1], ent[2])    # stale, same buffers (functional.PlaneRegistry)
+                v.__dict__.pop("_pnp_planes", None)
                 v.__dict__.pop("_pnp_wT", None)
                 v.__dict__.pop("_pnp_bncoef", None)
             g = torch.cuda.CUDAGraph()
