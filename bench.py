@@ -514,7 +514,9 @@ def _roofline(recs_all, nprof, ms_step, a):
     if tj:
         with open(tj) as f:
             nj = json.load(f)
-        mine = [l_ for l_ in nj.get("launches", []) if l_["kernel"].endswith(dom)]
+        # captures taken before the CTA-pair variant existed name the single-CTA kernel without its 4th template argument
+        norm = lambda k_: k_.replace(", 1>", ">") if k_.count(",") == 3 else k_
+        mine = [l_ for l_ in nj.get("launches", []) if norm(l_["kernel"]).endswith(norm(dom))]
         if mine:
             traffic = sum(l_["dram_bytes"] for l_ in mine) / len(mine)
             traffic_note = ("dram__bytes_read+write per launch, mean over the %d %s launches of the committed ncu --set full capture "

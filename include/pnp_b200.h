@@ -59,6 +59,9 @@ int pnp_tc_available(void);
 /* tile configuration chosen by the most recent pnp_conv2d_tc_fwd / _dgrad call (N tile, K block, split-K factor); lets the
    benchmark attribute each timed launch to a kernel instantiation.  Host-side bookkeeping only. */
 int pnp_tc_last_config(int* block_n, int* block_k, int* ksplit);
+/* 1 if that launch ran as CTA pairs (clusters of 2, tcgen05 cta_group::2: one 256-row MMA per pair of 128-pixel tiles, each CTA
+   staging half of the weight tile); PNP_TC_PAIR selects the tile shapes that may (bit 0: N 256, bit 1: N 128, bit 2: N 64) */
+int pnp_tc_last_pair(void);
 
 /* ---- convolution, general SIMT fp32 path (conv_simt.cu) --------------------------------------
  * replaces tf.nn.conv2d (layers.py:18,24,67,73) and tf.nn.atrous_conv2d (layers.py:86,92) plus

@@ -90,6 +90,33 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// CTA pair (cta_group::2): both CTAs of the pair issue their own loads; the transaction bytes are credited to the barrier of
+// the pair's even CTA (shared::cluster address with the peer bit cleared), whose MMA thread is the only consumer
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {      // arrive on the even CTA's copy of this barrier
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -100,6 +127,26 @@ __device__ __forceinline__ void tcgen05_alloc(uint32_t dst_smem, uint32_t ncols)
 }
 __device__ __forceinline__ void tcgen05_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tcgen05_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// completion of the pair's MMAs -> one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -266,10 +313,13 @@ __device__ __forceinline__ void kblock_of(const TcArgs& a, const TileCoord& tc, 
   tap = tc.tap_begin + tl;
 }
 
-template <int BLOCK_N, int NTERMS, int BK>
+// CG = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) works on two M-tiles of the same N-tile as ONE 256 x BLOCK_N MMA; each
+// CTA stages its own 128 activation rows and HALF of the weight tile, so the L2 -> SM fill per MMA drops from A + B to A + B/2
+// (the 3-term 128x256 tile needs 48 KB per 768 tensor cycles = the whole 64 B/clk SM ingest port; the pair needs 32 KB)
+template <int BLOCK_N, int NTERMS, int BK, int CG = 1>
 struct TcCfg {
   static constexpr int A_TILE_BYTES = BLOCK_M * BK * 2;
-  static constexpr int B_TILE_BYTES = BLOCK_N * BK * 2;
+  static constexpr int B_TILE_BYTES = (BLOCK_N / CG) * BK * 2;        // this CTA's share of the weight tile
   static constexpr int NPLANES = (NTERMS == 1) ? 1 : 2;
   static constexpr int STAGE_BYTES = NPLANES * (A_TILE_BYTES + B_TILE_BYTES);
   // narrow tiles (N <= 32: the 16- and 32-channel layers) may keep the weight tiles of ALL taps resident in shared memory for the
@@ -290,15 +340,15 @@ struct TcCfg {
   static constexpr int NCH = CW / EW;                               // chunks per epilogue warp and tile
 };
 
-template <int BLOCK_N, int NTERMS, int BK>
-__global__ void __launch_bounds__((TcCfg<BLOCK_N, NTERMS, BK>::THREADS), 1)
+template <int BLOCK_N, int NTERMS, int BK, int CG = 1>
+__global__ void __launch_bounds__((TcCfg<BLOCK_N, NTERMS, BK, CG>::THREADS), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                float* __restrict__ out, TcArgs a) {
   // PERSISTENT: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the smem ring and its phases run
   // across tile boundaries (the producer prefetches the next tile while the last MMAs of the current one retire) and the
   // accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the main loop of tile i+1.
-  using Cfg = TcCfg<BLOCK_N, NTERMS, BK>;
+  using Cfg = TcCfg<BLOCK_N, NTERMS, BK, CG>;
   constexpr int A_TILE_BYTES = Cfg::A_TILE_BYTES;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -310,13 +360,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint64_t* wres_full = bars + 2 * STAGES + 4;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
-  const bool bres = Cfg::WRES_BYTES > 0 && a.b_resident != 0;
+  const bool bres = CG == 1 && Cfg::WRES_BYTES > 0 && a.b_resident != 0;
+  // pair mode: cluster c = blockIdx.x / 2 walks PAIRS of m-tiles (2*mp, 2*mp + 1) of one n-tile; rank = which of the two is ours
+  const int cta_rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int walk_first = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int walk_step = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int walk_count = (CG == 2) ? a.total_tiles / 2 : a.total_tiles;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = a.Cout / BLOCK_N;
-  const int num_tiles = a.total_tiles;
   const int kchunks = a.kchunks;
+  // walk index -> this CTA's tile; both CTAs of a pair must run the same k-block order, so the rotation key is the pair index
+  auto tile_of = [&](int w) -> TileCoord {
+    if (CG == 1) return decode_tile<BLOCK_N>(a, w, n_tiles);
+    const int mp = w / n_tiles, nt = w - mp * n_tiles;
+    TileCoord c = decode_tile<BLOCK_N>(a, (2 * mp + cta_rank) * n_tiles + nt, n_tiles);
+    c.mt = mp;
+    return c;
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a_hi);
@@ -328,14 +391,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     mbar_init(smem_u32(&tmem_full[0]), 1);
     mbar_init(smem_u32(&tmem_full[1]), 1);
-    mbar_init(smem_u32(&tmem_empty[0]), 32 * Cfg::EPI_WARPS);      // every epilogue thread releases an accumulator
-    mbar_init(smem_u32(&tmem_empty[1]), 32 * Cfg::EPI_WARPS);
+    mbar_init(smem_u32(&tmem_empty[0]), 32 * Cfg::EPI_WARPS * CG);  // every epilogue thread (of both CTAs of a pair) releases an accumulator
+    mbar_init(smem_u32(&tmem_empty[1]), 32 * Cfg::EPI_WARPS * CG);
     mbar_init(smem_u32(wres_full), 1);
     fence_barrier_init();
   }
-  if (warp == 1) tcgen05_alloc(smem_u32(tmem_holder), 2 * Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if (CG == 2) tcgen05_alloc_pair(smem_u32(tmem_holder), 2 * Cfg::TMEM_COLS);
+    else tcgen05_alloc(smem_u32(tmem_holder), 2 * Cfg::TMEM_COLS);
+  }
   tcgen05_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();            // the peer's barriers exist before anything signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
@@ -343,7 +410,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ================= TMA producer =================
     if (lane == 0) {
       const uint32_t box_a_bytes = (uint32_t)(a.tw * a.th * a.tn) * BK * 2;
-      const uint32_t tx_bytes = Cfg::NPLANES * (box_a_bytes + (bres ? 0u : (uint32_t)Cfg::B_TILE_BYTES));
+      const uint32_t tx_bytes = CG * Cfg::NPLANES * (box_a_bytes + (bres ? 0u : (uint32_t)Cfg::B_TILE_BYTES));
       if (bres) {
         // every (tap, chunk) weight tile of this layer, once: tile (tap, kc) at wres + (tap*kchunks + kc) * NPLANES * B_TILE_BYTES
         const int nkb_all = a.ntaps * kchunks;
@@ -357,8 +424,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile<BLOCK_N>(a, t, n_tiles);
+      for (int t = walk_first; t < walk_count; t += walk_step) {
+        const TileCoord tc = tile_of(t);
         const int x0 = tc.x0, y0 = tc.y0, img0 = tc.img0, n0 = tc.n0;
         // CTAs that share a weight tile (same n0, different m-tile) would otherwise request the same L2 lines in lockstep;
         // rotating each m-tile's starting k-block spreads those requests over the whole weight slab (sum order is free)
@@ -367,16 +434,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           kblock_of(a, tc, i, kchunks, tap, kc);
           mbar_wait(smem_u32(&bars[STAGES + stage]), phase ^ 1);
           const uint32_t full = smem_u32(&bars[stage]);
-          mbar_expect_tx(full, tx_bytes);
+          if (leader) mbar_expect_tx(full, tx_bytes);             // pair: the even CTA's barrier counts both CTAs' bytes
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
           const int cx = x0 * a.in_mul + a.tap_ox[tap];
           const int cy = y0 * a.in_mul + a.tap_oy[tap];
-          const int wrow = a.tap_wrow[tap] + n0;
-          tma_load_4d(smem_u32(st), &map_a_hi, full, kc * BK, cx, cy, img0);
-          if (!bres) tma_load_2d(smem_u32(st + Cfg::NPLANES * A_TILE_BYTES), &map_b_hi, full, kc * BK, wrow);
-          if (NTERMS > 1) {
-            tma_load_4d(smem_u32(st + A_TILE_BYTES), &map_a_lo, full, kc * BK, cx, cy, img0);
-            if (!bres) tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES), &map_b_lo, full, kc * BK, wrow);
+          const int wrow = a.tap_wrow[tap] + n0 + cta_rank * (BLOCK_N / CG);
+          if (CG == 2) {
+            tma_load_4d_pair(smem_u32(st), &map_a_hi, full, kc * BK, cx, cy, img0);
+            tma_load_2d_pair(smem_u32(st + Cfg::NPLANES * A_TILE_BYTES), &map_b_hi, full, kc * BK, wrow);
+            if (NTERMS > 1) {
+              tma_load_4d_pair(smem_u32(st + A_TILE_BYTES), &map_a_lo, full, kc * BK, cx, cy, img0);
+              tma_load_2d_pair(smem_u32(st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES), &map_b_lo, full, kc * BK, wrow);
+            }
+          } else {
+            tma_load_4d(smem_u32(st), &map_a_hi, full, kc * BK, cx, cy, img0);
+            if (!bres) tma_load_2d(smem_u32(st + Cfg::NPLANES * A_TILE_BYTES), &map_b_hi, full, kc * BK, wrow);
+            if (NTERMS > 1) {
+              tma_load_4d(smem_u32(st + A_TILE_BYTES), &map_a_lo, full, kc * BK, cx, cy, img0);
+              if (!bres) tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES), &map_b_lo, full, kc * BK, wrow);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -384,8 +460,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -394,8 +470,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         mbar_wait(smem_u32(wres_full), 0);
         tcgen05_fence_after();
       }
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const TileCoord tcm = decode_tile<BLOCK_N>(a, t, n_tiles);
+      for (int t = walk_first; t < walk_count; t += walk_step) {
+        const TileCoord tcm = tile_of(t);
         const int num_kb = tcm.kb_count;
         mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);     // epilogue has drained this accumulator
         tcgen05_fence_after();
@@ -422,15 +498,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               const uint64_t da_lo = make_kmajor_desc<BK>(a_lo + koff);
               const uint64_t db_lo = make_kmajor_desc<BK>(b_lo + koff);
               // small cross terms first, then the dominant hi*hi term
-              tcgen05_mma_bf16(tmem_d, da_lo, db_hi, idesc, (kb | k) != 0);
-              tcgen05_mma_bf16(tmem_d, da_hi, db_lo, idesc, 1);
-              tcgen05_mma_bf16(tmem_d, da_hi, db_hi, idesc, 1);
+              if (CG == 2) {
+                tcgen05_mma_bf16_pair(tmem_d, da_lo, db_hi, idesc, (kb | k) != 0);
+                tcgen05_mma_bf16_pair(tmem_d, da_hi, db_lo, idesc, 1);
+                tcgen05_mma_bf16_pair(tmem_d, da_hi, db_hi, idesc, 1);
+              } else {
+                tcgen05_mma_bf16(tmem_d, da_lo, db_hi, idesc, (kb | k) != 0);
+                tcgen05_mma_bf16(tmem_d, da_hi, db_lo, idesc, 1);
+                tcgen05_mma_bf16(tmem_d, da_hi, db_hi, idesc, 1);
+              }
+            } else if (CG == 2) {
+              tcgen05_mma_bf16_pair(tmem_d, da_hi, db_hi, idesc, (kb | k) != 0);
             } else {
               tcgen05_mma_bf16(tmem_d, da_hi, db_hi, idesc, (kb | k) != 0);
             }
           }
-          tcgen05_commit(smem_u32(&bars[STAGES + stage]));   // frees the smem slot when these MMAs retire
-          if (kb == num_kb - 1) tcgen05_commit(smem_u32(&tmem_full[acc]));
+          if (CG == 2) {
+            tcgen05_commit_pair(smem_u32(&bars[STAGES + stage]));   // frees the slot in BOTH CTAs when these MMAs retire
+            if (kb == num_kb - 1) tcgen05_commit_pair(smem_u32(&tmem_full[acc]));
+          } else {
+            tcgen05_commit(smem_u32(&bars[STAGES + stage]));   // frees the smem slot when these MMAs retire
+            if (kb == num_kb - 1) tcgen05_commit(smem_u32(&tmem_full[acc]));
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         acc ^= 1;
@@ -461,8 +550,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     int stat_n0 = -1;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile<BLOCK_N>(a, t, n_tiles);
+    for (int t = walk_first; t < walk_count; t += walk_step) {
+      const TileCoord tc = tile_of(t);
       const int n0 = tc.n0;
       const int img = tc.img0 + ni, u = tc.y0 + yy, v_ = tc.x0 + xx;
       const bool valid = (ni < a.tn) && (img < a.B) && (u < tc.U) && (v_ < tc.V);
@@ -598,7 +687,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
       }
       tcgen05_fence_before();
-      mbar_arrive(smem_u32(&tmem_empty[acc]));       // this thread is done reading accumulator `acc`
+      if (CG == 2) mbar_arrive_leader(smem_u32(&tmem_empty[acc]));   // the pair's MMA thread lives in the even CTA
+      else mbar_arrive(smem_u32(&tmem_empty[acc]));  // this thread is done reading accumulator `acc`
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -610,11 +700,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
     }
   }
+  tcgen05_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();            // neither CTA may retire while the other can still signal its barriers / use its TMEM
   if (warp == 1) {
     __syncwarp();
     tcgen05_fence_after();
-    tcgen05_dealloc(tmem_base, 2 * Cfg::TMEM_COLS);
+    if (CG == 2) tcgen05_dealloc_pair(tmem_base, 2 * Cfg::TMEM_COLS);
+    else tcgen05_dealloc(tmem_base, 2 * Cfg::TMEM_COLS);
   }
 }
 
@@ -977,7 +1070,7 @@ int choose_tile(int U, int V, int B, int rows, int exact, int* tw, int* th, int*
   return PNP_OK;
 }
 
-int g_last_cfg[3] = {0, 0, 0};      // {N tile, K block, split-K factor} of the most recent conv launch (profiling aid)
+int g_last_cfg[4] = {0, 0, 0, 0};   // {N tile, K block, split-K factor, CTA pair} of the most recent conv launch (profiling aid)
 
 int sm_count() {
   static int num_sms = 0;
@@ -1002,6 +1095,52 @@ int launch_tc(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensor
   const long long tiles = a.total_tiles;
   dim3 grid((unsigned)(tiles < num_sms ? tiles : num_sms));     // persistent: one CTA per SM walks the tile list
   conv_tc_kernel<BLOCK_N, NTERMS, BK><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, y, a);
+  PNP_LAUNCH_CHECK();
+  return PNP_OK;
+}
+
+// CTA-pair launch: clusters of 2 (the pair shares one TPC), persistent over PAIRS of m-tiles; how many pairs can be co-resident
+// is asked of the driver once per instantiation (74 on a full B200: 148 SMs)
+template <int BLOCK_N, int NTERMS, int BK>
+int pair_capacity() {
+  using Cfg = TcCfg<BLOCK_N, NTERMS, BK, 2>;
+  static int cap = -1;
+  if (cap < 0) {
+    auto kern = conv_tc_kernel<BLOCK_N, NTERMS, BK, 2>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); cap = 0; return cap; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (unsigned)(sm_count() / 2));
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    cap = n;
+  }
+  return cap;
+}
+
+template <int BLOCK_N, int NTERMS, int BK>
+int launch_tc_pair(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi, const CUtensorMap& mb_lo,
+                   float* y, const TcArgs& a, cudaStream_t s) {
+  using Cfg = TcCfg<BLOCK_N, NTERMS, BK, 2>;
+  const int cap = pair_capacity<BLOCK_N, NTERMS, BK>();
+  if (cap <= 0) return PNP_ERR_UNSUPPORTED;
+  const int pairs = a.total_tiles / 2;
+  const int clusters = pairs < cap ? pairs : cap;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (unsigned)clusters);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  PNP_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, NTERMS, BK, 2>, ma_hi, ma_lo, mb_hi, mb_lo, y, a));
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1114,15 +1253,28 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
     const long long wbytes = (long long)a.ntaps * a.kchunks * (nterms == 3 ? 2 : 1) * block_n * bk * 2;
     a.b_resident = (bres_env && block_n <= 32 && a.Cout == block_n && a.ksplit == 1 && wbytes <= 40 * 1024) ? 1 : 0;
   }
+  // CTA pairs (cta_group::2): single-phase, unsplit layers with an even number of m-tiles on the tile shapes that carry the step
+  // (PNP_TC_PAIR: bit 0 = 128x256 tiles, bit 1 = 128x128, bit 2 = 128x64; default 1)
+  int pair = 0;
+  {
+    static int pair_env = -1;
+    if (pair_env < 0) { const char* e = getenv("PNP_TC_PAIR"); pair_env = e ? atoi(e) : 1; }
+    const long long mtiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n;
+    const bool shape_ok = (block_n == 256 && (pair_env & 1) && ((nterms == 3 && bk == 32) || (nterms == 1 && bk == 64))) ||
+                          (block_n == 128 && (pair_env & 2) && nterms == 3 && bk == 64) ||
+                          (block_n == 64 && (pair_env & 4) && nterms == 3 && bk == 64);
+    if (shape_ok && a.nphases == 0 && a.ksplit == 1 && !a.b_resident && mtiles % 2 == 0 && mtiles >= 2) pair = 1;
+  }
+  g_last_cfg[3] = pair;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   rc = make_act_map(&ma_hi, a_hi, a.B, AH, AW, a.Cin, a.tw, a.th, a.tn, a_stride, bk);
   if (rc) return rc;
-  rc = make_w_map(&mb_hi, w_hi, w_rows, a.Cin, block_n, bk);
+  rc = make_w_map(&mb_hi, w_hi, w_rows, a.Cin, pair ? block_n / 2 : block_n, bk);
   if (rc) return rc;
   if (nterms == 3) {
     rc = make_act_map(&ma_lo, a_lo, a.B, AH, AW, a.Cin, a.tw, a.th, a.tn, a_stride, bk);
     if (rc) return rc;
-    rc = make_w_map(&mb_lo, w_lo, w_rows, a.Cin, block_n, bk);
+    rc = make_w_map(&mb_lo, w_lo, w_rows, a.Cin, pair ? block_n / 2 : block_n, bk);
     if (rc) return rc;
   } else {
     ma_lo = ma_hi;
@@ -1131,7 +1283,13 @@ int run_tc(const uint16_t* a_hi, const uint16_t* a_lo, int AH, int AW, int a_str
 #define PNP_TC_GO(N_, K_)                                                                                  \
   rc = (nterms == 3) ? launch_tc<N_, 3, K_>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s)                         \
                      : launch_tc<N_, 1, K_>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s)
-  if (block_n == 256 && bk == 64) { PNP_TC_GO(256, 64); }
+  if (pair) {
+    if (block_n == 256 && nterms == 3) rc = launch_tc_pair<256, 3, 32>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
+    else if (block_n == 256) rc = launch_tc_pair<256, 1, 64>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
+    else if (block_n == 128) rc = launch_tc_pair<128, 3, 64>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
+    else rc = launch_tc_pair<64, 3, 64>(ma_hi, ma_lo, mb_hi, mb_lo, out, a, s);
+  }
+  else if (block_n == 256 && bk == 64) { PNP_TC_GO(256, 64); }
   else if (block_n == 256 && bk == 32) { PNP_TC_GO(256, 32); }
   else if (block_n == 128 && bk == 64) { PNP_TC_GO(128, 64); }
   else if (block_n == 128 && bk == 32) { PNP_TC_GO(128, 32); }
@@ -1163,6 +1321,8 @@ extern "C" int pnp_tc_last_config(int* block_n, int* block_k, int* ksplit) {
   if (ksplit) *ksplit = g_last_cfg[2];
   return PNP_OK;
 }
+
+extern "C" int pnp_tc_last_pair(void) { return g_last_cfg[3]; }
 
 extern "C" int pnp_tc_available(void) {
   int dev = 0;

@@ -39,7 +39,7 @@ def _tc_launch(tag, flops, name, *args):
     if name in ("pnp_conv2d_tc_fwd", "pnp_conv2d_tc_fwd_fused", "pnp_conv2d_tc_dgrad"):
         n_, k_, s_ = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
         _C.lib.pnp_tc_last_config(ctypes.byref(n_), ctypes.byref(k_), ctypes.byref(s_))
-        kern = "conv_tc_kernel<%d, %d, %d>" % (n_.value, 1 if _tc_mode() == 1 else 3, k_.value)
+        kern = "conv_tc_kernel<%d, %d, %d, %d>" % (n_.value, 1 if _tc_mode() == 1 else 3, k_.value, 2 if _C.lib.pnp_tc_last_pair() else 1)
     elif name == "pnp_conv2d_tc_wgrad":
         kern = "conv_wgrad_tc_kernel"
     PROFILE.append((e0, e1, flops, tag, kern))

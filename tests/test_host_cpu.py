@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in declared if not hasattr(lib, n)]
     assert not missing, missing
     # the ctypes table mirrors the header one to one
-    bound = set(_C.SIGNATURES) | {"pnp_error_string", "pnp_version", "pnp_tc_available", "pnp_tc_last_config"}
+    bound = set(_C.SIGNATURES) | {"pnp_error_string", "pnp_version", "pnp_tc_available", "pnp_tc_last_config", "pnp_tc_last_pair"}
     assert set(declared) == bound, (set(declared) ^ bound)
     assert _C.lib.pnp_version() >= 100
     assert _C.lib.pnp_error_string(100002).decode().startswith("pnp: unsupported")

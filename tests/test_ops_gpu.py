@@ -2,6 +2,7 @@
 C-ABI) vs the CPU oracle (oracle/tf14_torch.py, fp64) on identical seeded inputs.  fp32 kernels: tolerance
 1e-4 relative to the largest reference magnitude; the 3-term bf16-split tensor-core path: 2e-4; stated per test.
 """
+import ctypes
 import math
 
 import numpy as np
@@ -115,6 +116,10 @@ TC_CASES = [
     (2, 32, 32, 16, 32, 3, 1, 1, "SAME"),       # g2 inc: forward N 32 / K 16, dgrad N 16 / K 32
     (1, 256, 256, 16, 16, 3, 1, 1, "SAME"),     # g1 at full width
     (8, 32, 32, 16, 32, 5, 4, 1, "SAME"),       # m_cls_2_3: 5x5 stride 4, phase dgrad with N = 16
+    # CTA pairs (cta_group::2): more tile pairs than the 74 clusters of a B200, so every pair walks several tiles
+    (16, 32, 32, 512, 512, 3, 1, 2, "SAME"),    # g8 at config 1's batch: 128 m-tiles x 2 n-tiles of 128x256, dilated
+    (4, 64, 64, 128, 128, 3, 1, 1, "SAME"),     # 128x128 tiles (PNP_TC_PAIR bit 1)
+    (2, 128, 128, 64, 64, 3, 1, 1, "SAME"),     # 128x64 tiles (PNP_TC_PAIR bit 2)
 ]
 
 
@@ -143,6 +148,26 @@ def test_conv_tensor_core(case, backend, tol):
     check("dw", wg.grad, wo.grad, tol)
     F.TC_PAD32 = False
     assert not F._tc_declined, "these shapes must run on tcgen05: %s" % (F._tc_declined,)
+    rt.set_conv_backend("auto")
+
+
+def test_cta_pair_kernel_is_selected_for_the_wide_layers():
+    """the 512-channel 32x32 layers of the segmenter (the step's dominant launches) run as CTA pairs unless PNP_TC_PAIR=0"""
+    import os
+    L, ops, F, rt = _prod()
+    from pnp_b200 import _C
+    if not (int(os.environ.get("PNP_TC_PAIR", "1")) & 1):
+        pytest.skip("PNP_TC_PAIR disables the 128x256 pair kernel")
+    rt.set_conv_backend("tc3")
+    x, w = randn((8, 32, 32, 512), 3).to(DEV), randn((3, 3, 512, 512), 4, 0.05).to(DEV)
+    with torch.no_grad():
+        y = L.conv2d(x, w, 1.0)
+    torch.cuda.synchronize()
+    n_, k_, s_ = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    _C.lib.pnp_tc_last_config(ctypes.byref(n_), ctypes.byref(k_), ctypes.byref(s_))
+    assert (n_.value, k_.value, s_.value) == (256, 32, 1) and _C.lib.pnp_tc_last_pair() == 1
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.permute(3, 2, 0, 1).double(), padding=1).permute(0, 2, 3, 1)
+    assert float((y.double() - ref).abs().max() / ref.abs().max()) < 2e-5
     rt.set_conv_backend("auto")
 
 

@@ -18,7 +18,10 @@
     relative to fp32, as in the gradient checks) for steps 0-3 -- afterwards two fp32 runs are decorrelated and a ratio of their
     deviations is noise -- and the run must reach the loss level the reference reaches (wce / 5, dice-loss < -0.85 by step 11).
   * held-out Dice gate (north_star): train the segmenter on label-correlated synthetic slices on the GPU, hand the trained
-    variables to the oracle, evaluate both on 64 held-out slices (seed 7777): hard Dice (lib.py:96-110) within 1e-3.
+    variables to the oracle, evaluate both on 64 held-out slices (seed 7777): hard Dice (lib.py:96-110) within 1e-3 per
+    class, per batch and in the mean.  The checkpoint evaluated is the first one on which hard Dice is insensitive to fp32
+    rounding (measured oracle-free, between the product's tcgen05 and SIMT convolution paths): a model with thousands of
+    pixels within rounding of a tie separates no two fp32 implementations to 1e-3 (see the comment in the test).
 """
 import json
 import os
@@ -142,13 +145,35 @@ def test_held_out_dice_gate_seed_7777():
     from pnp_b200.data import SyntheticSource
     from oracle.pnp_graphs import OracleSegmenter
     from oracle.tf14_numpy import label_decomp
+    from oracle import tf14_torch as T
     B = 8
     net, trainer, _, P = seg_pair("auto", B)
     # label-correlated slices so that a briefly trained model predicts something non-trivial
     train_src = SyntheticSource(B, seed=1234, num_cls=5, pool=4, contrast=1.0, scale=0.25)
     held = SyntheticSource(B, seed=7777, num_cls=5, pool=8, contrast=1.0, scale=0.25)     # 8 x 8 = 64 held-out slices
-    probe = trainer.feed(*held.pool[0])
-    steps = 0
+    held_dev = [trainer.feed(*held.pool[i]) for i in range(8)]
+
+    def rounding_sensitivity():
+        """How far does fp32-level rounding move the hard Dice of THIS model?  Measured without the oracle: the same forward on
+        the two independent convolution implementations of the product (tcgen05 bf16-split tiles vs the fp32 SIMT direct
+        convolution; they differ from each other by what the tcgen05 path differs from the oracle, tests/test_ops_gpu.py).
+        -> (worst |dDice| over batches and classes between the two, re-labelled pixels, mean held-out Dice)"""
+        worst, flips, dices = 0.0, 0, []
+        with torch.no_grad():
+            for xg, yg in held_dev:
+                rt.set_conv_backend("auto")
+                lg = net.forward(xg, 1.0, False, False)
+                d_a, arr_a = net.dice_eval(lg, yg)
+                rt.set_conv_backend("simt")
+                ls = net.forward(xg, 1.0, False, False)
+                d_s, arr_s = net.dice_eval(ls, yg)
+                flips += int((lg.argmax(3) != ls.argmax(3)).sum())
+                worst = max(worst, abs(float(d_a) - float(d_s)), max(abs(float(p_) - float(q_)) for p_, q_ in zip(arr_a, arr_s)))
+                dices.append(float(d_a))
+        rt.set_conv_backend("auto")
+        return worst, flips, float(np.mean(dices))
+
+    steps, best = 0, None
     while True:
         # 30 Adam steps, then 30 steps at lr 0 that only let the BN moving averages (decay 0.9) settle on the current weights:
         # the validation feed runs inference-mode BN, and moving statistics that lag fast-moving weights give a degenerate model
@@ -159,11 +184,27 @@ def test_held_out_dice_gate_seed_7777():
         for _ in range(30):
             trainer.train_step(*trainer.feed(*train_src.next()), keep_prob=1.0)
         steps += 30
-        dv = trainer.val_stats(*probe)["dice_eval"]
-        print("  after %d Adam steps on the GPU: wce %.4f dice-loss %.4f ; held-out Dice (batch 0) %.4f" % (steps, float(wce), float(dice), dv))
-        if dv > 0.5 or steps >= 240:
+        # A hard-Dice gate of 1e-3 measures the implementation only on a model that is DECISIVE.  GPU training is run-to-run
+        # nondeterministic (split-K / weight-gradient atomics) and chaotic (test above), so every run yields a different model.
+        # Most are fine (36 of 36 checkpoints of three 360-step runs: 1 .. 4 re-labelled pixels per batch of 524 288, |dDice|
+        # <= 1e-4, gpurun_out/r2r_diag_*.log), but now and then one puts hundreds or thousands of pixels within fp32 rounding of
+        # a tie -- 26, 300 and 3 600 re-labelled pixels per batch in three of ~15 runs, all in one class pair, moving the 2 %-of-
+        # the-image class by 3e-3 .. 1.6e-1 (gpurun_out/r2n_gpu_suite.log, r2o_dice_*.log) at the SAME logits deviation (1e-4 of
+        # the largest logit).  Any two fp32 implementations disagree by about as much on such a model; it says nothing about this
+        # one.  So: evaluate the first checkpoint whose Dice does not move by more than a quarter of the gate between the
+        # product's own two convolution implementations (else the least sensitive one of 12).
+        sens, flips, dv = rounding_sensitivity()
+        print("  after %3d Adam steps on the GPU: wce %.4f dice-loss %.4f ; held-out Dice %.4f ; tcgen05 vs SIMT forward: %d re-labelled pixels, worst |dDice| %.2e"
+              % (steps, float(wce), float(dice), dv, flips, sens))
+        if dv > 0.5 and (best is None or sens < best[0]):
+            best = (sens, steps, rt.state_dict())
+        if (best is not None and best[0] <= 2.5e-4) or steps >= 360:
             break
-    trained = rt.state_dict()
+    assert best is not None, "the segmenter did not train (held-out Dice %.3f after %d steps)" % (dv, steps)
+    print("  evaluating the checkpoint after %d Adam steps (rounding sensitivity %.2e)" % (best[1], best[0]))
+    if best[1] != steps:
+        rt.load_state_dict(best[2])
+    trained = best[2]
     oracle = OracleSegmenter(trained, B)
     worst, ours, theirs, agree, lerr = 0.0, [], [], [], []
     cm_tot = torch.zeros(5, 5, dtype=torch.int64)
@@ -172,10 +213,12 @@ def test_held_out_dice_gate_seed_7777():
         xg, yg = trainer.feed(xs, ys)
         st = trainer.val_stats(xg, yg)
         y_host = torch.from_numpy(label_decomp(5, ys.numpy()))
-        d_ref, arr_ref, compact_ref = oracle.evaluate(xs.clone(), y_host)
         with torch.no_grad():
             lg = net.forward(xg, 1.0, False, False)
             lr_ = oracle.forward(xs.clone(), 1.0, False)["logits"]
+            compact_ref = T.pixel_wise_softmax_2(lr_).argmax(3)              # OracleSegmenter.evaluate, sharing the forward
+            d_ref, arr_ref = T.dice_eval(compact_ref, y_host, 5)
+            d_ref, arr_ref = float(d_ref), [float(a) for a in arr_ref]
         agree.append(float((lg.argmax(3).cpu() == compact_ref).float().mean()))
         lerr.append(float((lg.cpu() - lr_).abs().max() / lr_.abs().max()))
         ours.append(st["dice_eval"])
