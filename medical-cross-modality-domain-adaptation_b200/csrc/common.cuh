@@ -23,6 +23,49 @@
 static inline int pnp_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (opt-in: PNP_PDL=1).  A step is ~860 short kernels in stream order (inside one CUDA graph).
+// Every kernel of this library starts with pnp_pdl_enter(): `griddepcontrol.launch_dependents` lets the NEXT kernel of the
+// stream become resident as soon as all CTAs of this one have started (its CTAs take whatever SM resources are free),
+// `griddepcontrol.wait` then blocks until the PREVIOUS kernel has completed and its writes are visible -- no kernel touches
+// global memory before that, so stream-order semantics are kept and only launch latency, CTA scheduling and the per-kernel
+// prologue (the tcgen05 kernels wait after their barrier / TMEM set-up) overlap the predecessor's tail.  With PNP_PDL=1 launches
+// carry cudaLaunchAttributeProgrammaticStreamSerialization (stream capture turns it into a programmatic graph edge); without
+// it both instructions are no-ops.  Measured on one B200 (r2t, 20 graph-replayed steps, two repeats): config 4 28.44 ms
+// without vs 28.59 ms with it, config 2 20.22 vs 19.81 ms, config 1 4.39 vs 4.40 ms, config 3 52.17 vs 52.46 ms -- the graph
+// already hides most launch latency and the early-resident dependents cost about what they save: default OFF.  All GPU tests
+// (eager and graph replay) pass in both modes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pnp_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pnp_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pnp_pdl_enter() {
+  pnp_pdl_trigger();
+  pnp_pdl_wait();
+}
+
+#ifdef __CUDACC__
+#include <stdlib.h>
+static inline int pnp_pdl_on() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PNP_PDL"); v = e ? atoi(e) : 0; }
+  return v;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pnp_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pnp_pdl_on() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based RNG.  One call yields the 4 uniforms for the 4 consecutive elements
 // [4*idx4, 4*idx4+3] of a tensor; `stream` separates dropout call sites, the seed lives in device
 // memory so that a captured CUDA graph sees a fresh seed on every replay.

@@ -37,6 +37,7 @@ __device__ __forceinline__ int row_index(int i, int t, int T, int BT) {
 template <int BM, int BN, int BK, int TM, int TN, int VEC, bool TRANSPOSED>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_gather_kernel(const float* __restrict__ in, const float* __restrict__ wmat, float* __restrict__ out, GatherArgs a) {
+  pnp_pdl_enter();
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int KCH = BK / VEC;                                   // k-chunks per row
   constexpr int ROWS_PT = (BM >= NT) ? (BM / NT) : 1;             // rows per thread (A loader)
@@ -298,7 +299,7 @@ int launch_gather(const float* in, const float* wmat, float* out, const GatherAr
   }
   dim3 grid(pnp_cdiv(a.M, BM), pnp_cdiv(a.OC, BN));
   dim3 block((BM / TM) * (BN / TN));
-  conv_gather_kernel<BM, BN, BK, TM, TN, VEC, TR><<<grid, block, 0, s>>>(in, wmat, out, a);
+  pnp_launch(conv_gather_kernel<BM, BN, BK, TM, TN, VEC, TR>, grid, block, 0, s, in, wmat, out, a);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -341,6 +342,7 @@ template <int NO>
 __global__ void __launch_bounds__(256)
 conv_few_out_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int B, int H, int W, int Cin,
                     int Ho, int Wo, int kh, int kw, int pad_t, int pad_l) {
+  pnp_pdl_enter();
   constexpr int T = 32, CC = 8, HALO = T + 4;            // kernels up to 5x5
   __shared__ float s_x[CC][HALO][HALO + 1];
   __shared__ float s_w[25][CC][NO];
@@ -414,6 +416,7 @@ struct WgradArgs {
 template <int BKK, int BN, int BR, int TK, int TN, int VEC>
 __global__ void __launch_bounds__((BKK / TK) * (BN / TN))
 conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, WgradArgs a) {
+  pnp_pdl_enter();
   constexpr int NT = (BKK / TK) * (BN / TN);
   constexpr int KCH = BKK / VEC;                 // kk chunks per pixel row
   constexpr int A_TOTAL = BR * KCH;
@@ -584,12 +587,13 @@ int launch_wgrad(const float* x, const float* dy, float* dw, WgradArgs a, cudaSt
   splits = pnp_cdiv(a.M, mps);
   a.m_per_split = mps;
   dim3 grid(pnp_cdiv(a.KK, BKK), pnp_cdiv(a.Cout, BN), splits);
-  conv_wgrad_kernel<BKK, BN, BR, TK, TN, VEC><<<grid, (BKK / TK) * (BN / TN), 0, s>>>(x, dy, dw, a);
+  pnp_launch(conv_wgrad_kernel<BKK, BN, BR, TK, TN, VEC>, grid, (BKK / TK) * (BN / TN), 0, s, x, dy, dw, a);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
 
 __global__ void weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ wT, int Cin, int Cout) {
+  pnp_pdl_enter();
   // per tap: [Cin][Cout] -> [Cout][Cin]
   __shared__ float tile[32][33];
   const float* src = w + (long long)blockIdx.z * Cin * Cout;
@@ -621,6 +625,7 @@ template <int NO>
 __global__ void __launch_bounds__(256)
 ps_mirror_conv_kernel(const float* __restrict__ X, const float* __restrict__ w, float* __restrict__ y, int B, int a, int b, int G,
                       int r, int kh, int kw, int order_b1) {
+  pnp_pdl_enter();
   constexpr int T = 32, CC = 8, HALO = T + 4;            // kernels up to 5x5
   __shared__ float s_x[CC][HALO][HALO + 1];
   __shared__ float s_w[25][CC][NO];
@@ -739,6 +744,7 @@ template <int NO>
 __global__ void __launch_bounds__(256)
 ps_mirror_conv_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dX, int B, int a, int b, int G,
                           int r, int kh, int kw, int order_b1) {
+  pnp_pdl_enter();
   constexpr int T = 32, CC = 8, HALO = T + 4;
   __shared__ float s_d[NO][HALO][HALO + 1];       // dy tile with halo, channel-major
   __shared__ __align__(16) float s_w[25][NO][CC];  // [tap][out channel of the forward conv][group]: 8 groups = two 128-bit broadcasts
@@ -844,10 +850,10 @@ extern "C" int pnp_conv2d_fwd(const float* x, const float* w, float* y, const pn
       a.drop.seed_ptr == nullptr && g->B <= 65535) {
     dim3 grid(pnp_cdiv(g->Wo, 32), pnp_cdiv(g->Ho, 32), g->B);
     if (g->Cout == 5)
-      conv_few_out_kernel<5><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, y, g->B, g->H, g->W, g->Cin, g->Ho, g->Wo, g->kh, g->kw,
+      pnp_launch(conv_few_out_kernel<5>, grid, 256, 0, (cudaStream_t)stream, x, w, y, g->B, g->H, g->W, g->Cin, g->Ho, g->Wo, g->kh, g->kw,
                                                                      g->pad_t, g->pad_l);
     else
-      conv_few_out_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, y, g->B, g->H, g->W, g->Cin, g->Ho, g->Wo, g->kh, g->kw,
+      pnp_launch(conv_few_out_kernel<8>, grid, 256, 0, (cudaStream_t)stream, x, w, y, g->B, g->H, g->W, g->Cin, g->Ho, g->Wo, g->kh, g->kw,
                                                                      g->pad_t, g->pad_l);
     PNP_LAUNCH_CHECK();
     return PNP_OK;
@@ -861,8 +867,8 @@ extern "C" int pnp_ps_mirror_conv_fwd(const float* X, const float* w, float* y, 
   if (kh > 5 || kw > 5 || kh < 1 || kw < 1 || (kh & 1) == 0 || (kw & 1) == 0 || B > 65535) return PNP_ERR_UNSUPPORTED;
   if (kh / 2 > a * r || kw / 2 > b * r) return PNP_ERR_UNSUPPORTED;
   dim3 grid(pnp_cdiv(b * r, 32), pnp_cdiv(a * r, 32), B);
-  if (Cout == 5) ps_mirror_conv_kernel<5><<<grid, 256, 0, (cudaStream_t)stream>>>(X, w, y, B, a, b, G, r, kh, kw, order_b1);
-  else if (Cout == 8) ps_mirror_conv_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(X, w, y, B, a, b, G, r, kh, kw, order_b1);
+  if (Cout == 5) pnp_launch(ps_mirror_conv_kernel<5>, grid, 256, 0, (cudaStream_t)stream, X, w, y, B, a, b, G, r, kh, kw, order_b1);
+  else if (Cout == 8) pnp_launch(ps_mirror_conv_kernel<8>, grid, 256, 0, (cudaStream_t)stream, X, w, y, B, a, b, G, r, kh, kw, order_b1);
   else return PNP_ERR_UNSUPPORTED;
   PNP_LAUNCH_CHECK();
   return PNP_OK;
@@ -874,8 +880,8 @@ extern "C" int pnp_ps_mirror_conv_bwd(const float* dy, const float* w, float* dX
   if (kh > 5 || kw > 5 || kh < 1 || kw < 1 || (kh & 1) == 0 || (kw & 1) == 0 || B > 65535) return PNP_ERR_UNSUPPORTED;
   if (kh / 2 > a * r || kw / 2 > b * r) return PNP_ERR_UNSUPPORTED;
   dim3 grid(pnp_cdiv(b * r, 32), pnp_cdiv(a * r, 32), B);
-  if (Cout == 5) ps_mirror_conv_bwd_kernel<5><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, w, dX, B, a, b, G, r, kh, kw, order_b1);
-  else if (Cout == 8) ps_mirror_conv_bwd_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, w, dX, B, a, b, G, r, kh, kw, order_b1);
+  if (Cout == 5) pnp_launch(ps_mirror_conv_bwd_kernel<5>, grid, 256, 0, (cudaStream_t)stream, dy, w, dX, B, a, b, G, r, kh, kw, order_b1);
+  else if (Cout == 8) pnp_launch(ps_mirror_conv_bwd_kernel<8>, grid, 256, 0, (cudaStream_t)stream, dy, w, dX, B, a, b, G, r, kh, kw, order_b1);
   else return PNP_ERR_UNSUPPORTED;
   PNP_LAUNCH_CHECK();
   return PNP_OK;
@@ -919,7 +925,7 @@ extern "C" int pnp_conv2d_wgrad(const float* x, const float* dy, float* dw, cons
 extern "C" int pnp_weight_transpose(const float* w, float* wT, int taps, int Cin, int Cout, void* stream) {
   if (!w || !wT || taps <= 0 || Cin <= 0 || Cout <= 0) return PNP_ERR_BAD_ARG;
   dim3 grid(pnp_cdiv(Cout, 32), pnp_cdiv(Cin, 32), taps);
-  weight_transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(w, wT, Cin, Cout);
+  pnp_launch(weight_transpose_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, w, wT, Cin, Cout);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }

@@ -345,6 +345,7 @@ __global__ void __launch_bounds__((TcCfg<BLOCK_N, NTERMS, BK, CG>::THREADS), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                float* __restrict__ out, TcArgs a) {
+  pnp_pdl_trigger();      // the wait comes after the prologue (barriers, TMEM, tensor-map prefetch touch no predecessor data)
   // PERSISTENT: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the smem ring and its phases run
   // across tile boundaries (the producer prefetches the next tile while the last MMAs of the current one retire) and the
   // accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the main loop of tile i+1.
@@ -404,6 +405,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   __syncthreads();
   if (CG == 2) cluster_sync_all();            // the peer's barriers exist before anything signals them
   tcgen05_fence_after();
+  pnp_pdl_wait();                             // from here on the predecessor kernel's results are read / its buffers written
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
@@ -717,6 +719,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, long long n) {
+  pnp_pdl_enter();
   long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
@@ -738,6 +741,7 @@ split_bf16_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16
 __global__ void __launch_bounds__(256)
 split_bf16_pad_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, long long rows, int C,
                       int Cpad) {
+  pnp_pdl_enter();
   const int q4 = Cpad >> 2;
   long long total = rows * q4;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -758,6 +762,7 @@ split_bf16_pad_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, ui
 __global__ void __launch_bounds__(256)
 split_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int taps, int Cin,
                     int Cout, int for_dgrad, int CinP) {
+  pnp_pdl_enter();
   __shared__ float tile[32][33];
   const int tap = blockIdx.z;
   const float* src = w + (long long)tap * Cin * Cout;
@@ -874,6 +879,7 @@ template <int BLOCK_N, int NTERMS>
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                      const __grid_constant__ CUtensorMap map_dy_hi, const __grid_constant__ CUtensorMap map_dy_lo, WgArgs a) {
+  pnp_pdl_trigger();
   using Cfg = WgCfg<BLOCK_N, NTERMS>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -909,6 +915,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pnp_pdl_wait();
 
   if (num_kb > 0) {
     if (warp == 0) {
@@ -1094,7 +1101,7 @@ int launch_tc(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensor
   const int num_sms = sm_count();
   const long long tiles = a.total_tiles;
   dim3 grid((unsigned)(tiles < num_sms ? tiles : num_sms));     // persistent: one CTA per SM walks the tile list
-  conv_tc_kernel<BLOCK_N, NTERMS, BK><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, y, a);
+  pnp_launch(conv_tc_kernel<BLOCK_N, NTERMS, BK>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, s, ma_hi, ma_lo, mb_hi, mb_lo, y, a);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1136,10 +1143,12 @@ int launch_tc_pair(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUt
   cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pnp_pdl_on() ? 2 : 1;
   PNP_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, NTERMS, BK, 2>, ma_hi, ma_lo, mb_hi, mb_lo, y, a));
   PNP_LAUNCH_CHECK();
   return PNP_OK;
@@ -1155,7 +1164,7 @@ int launch_wg(const CUtensorMap& mx_hi, const CUtensorMap& mx_lo, const CUtensor
     attr_set = true;
   }
   dim3 grid(a.ngroups * a.mt * a.nt, splits);
-  conv_wgrad_tc_kernel<BLOCK_N, NTERMS><<<grid, 192, Cfg::SMEM_BYTES, s>>>(mx_hi, mx_lo, md_hi, md_lo, a);
+  pnp_launch(conv_wgrad_tc_kernel<BLOCK_N, NTERMS>, grid, 192, Cfg::SMEM_BYTES, s, mx_hi, mx_lo, md_hi, md_lo, a);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1337,7 +1346,7 @@ extern "C" int pnp_split_bf16(const float* x, uint16_t* hi, uint16_t* lo, long l
   long long blocks = (n / 4 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
-  split_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, hi, lo, n);
+  pnp_launch(split_bf16_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, x, hi, lo, n);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1346,7 +1355,7 @@ extern "C" int pnp_split_bf16_pad(const float* x, uint16_t* hi, uint16_t* lo, lo
   if (!x || !hi || rows <= 0 || C <= 0 || Cpad < C || (C % 4) != 0 || (Cpad % 4) != 0) return PNP_ERR_BAD_ARG;
   long long blocks = (rows * (Cpad / 4) + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
-  split_bf16_pad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, hi, lo, rows, C, Cpad);
+  pnp_launch(split_bf16_pad_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, x, hi, lo, rows, C, Cpad);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1357,7 +1366,7 @@ extern "C" int pnp_split_weight_bf16(const float* w, uint16_t* hi, uint16_t* lo,
   const int CinP = (cin_pad > Cin) ? cin_pad : Cin;
   if (for_dgrad && CinP != Cin) return PNP_ERR_UNSUPPORTED;
   dim3 grid(pnp_cdiv(Cout, 32), pnp_cdiv(CinP, 32), kh * kw);
-  split_weight_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(w, hi, lo, kh * kw, Cin, Cout, for_dgrad, CinP);
+  pnp_launch(split_weight_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, w, hi, lo, kh * kw, Cin, Cout, for_dgrad, CinP);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }

@@ -62,6 +62,7 @@ bn_reduce_kernel(const float* __restrict__ z, const float* __restrict__ dy, cons
                  const unsigned short* __restrict__ yact_hi, const float* __restrict__ mean, const float* __restrict__ invstd, int act,
                  float* __restrict__ gout,
                  long long M, int C, int tpr, long long rows_per_block, double* __restrict__ out_a, double* __restrict__ out_b) {
+  pnp_pdl_enter();
   // WITH_G == false: out_a += sum z, out_b += sum z^2
   // WITH_G == true : g = dy*act'(y) (written to gout); out_a += sum g ; out_b += sum g*xhat
   // thread (q, rlane) owns channel quad q and every rstep-th row; block partials are combined through shared memory
@@ -166,6 +167,7 @@ int reduce_launch_cfg(long long M, int C, int* tpr, long long* rpb, int* grid) {
 __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, long long M, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float* moving_mean,
                                    float* moving_var, int training, float* scale, float* shift, float* mean, float* invstd) {
+  pnp_pdl_enter();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mu, var;
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(256)
 bn_act_apply_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ skip, int Cs, int skip_off, int act, float* __restrict__ y,
                     unsigned short* __restrict__ p_hi, unsigned short* __restrict__ p_lo, long long n4, int C4) {
+  pnp_pdl_enter();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     int q = (int)(i % C4);
     float4 v = __ldg(reinterpret_cast<const float4*>(z) + i);
@@ -231,6 +234,7 @@ bn_apply_fused_kernel(const float* __restrict__ z, const double* __restrict__ su
                       int training, const float* __restrict__ skip, int Cs, int skip_off, int act, float* __restrict__ y,
                       unsigned short* __restrict__ p_hi, unsigned short* __restrict__ p_lo, float* mean_out, float* invstd_out,
                       long long n4) {
+  pnp_pdl_enter();
   extern __shared__ float s_coef[];        // scale[C], shift[C]
   for (int c = threadIdx.x; c < C; c += 256) {
     float mu, var;
@@ -290,6 +294,7 @@ bn_bwd_apply_fused_kernel(const float* __restrict__ g, const float* __restrict__
                           const double* __restrict__ sum_gx, long long M, int C, int training, PnpDropout drop, float* dgamma,
                           float* dbeta, float* __restrict__ dz, unsigned short* __restrict__ p_hi, unsigned short* __restrict__ p_lo,
                           long long n4) {
+  pnp_pdl_enter();
   extern __shared__ float s_coef[];        // k[C] = gamma*invstd, c1[C] = sum_g/M, d[C] = invstd * sum_gx/M, mu[C]
   for (int c = threadIdx.x; c < C; c += 256) {
     const float is = invstd[c];
@@ -351,6 +356,7 @@ bn_bwd_apply_fused_kernel(const float* __restrict__ g, const float* __restrict__
 
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sum_g, const double* __restrict__ sum_gx, long long M,
                                        int C, float* dgamma, float* dbeta, float* coef) {
+  pnp_pdl_enter();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double sg = sum_g[c], sgx = sum_gx[c];
@@ -365,6 +371,7 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, co
                     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ coef,
                     int training, PnpDropout drop, float* __restrict__ dz, unsigned short* __restrict__ p_hi,
                     unsigned short* __restrict__ p_lo, long long n4, int C4) {
+  pnp_pdl_enter();
   unsigned long long seed = 0ull;
   const bool drop_on = drop.seed_ptr != nullptr;
   if (drop_on) seed = *drop.seed_ptr;
@@ -397,12 +404,14 @@ bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ z, co
 
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int act, float* __restrict__ g, long long n) {
+  pnp_pdl_enter();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
     g[i] = dy[i] * act_slope(y[i], act);
 }
 
 __global__ void __launch_bounds__(256)
 channel_slice_kernel(const float* __restrict__ g, int C, int off, int Cs, float* __restrict__ out, long long total, int accumulate) {
+  pnp_pdl_enter();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     long long m = i / Cs;
     int c = (int)(i - m * Cs);
@@ -413,6 +422,7 @@ channel_slice_kernel(const float* __restrict__ g, int C, int off, int Cs, float*
 
 __global__ void __launch_bounds__(256)
 dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, PnpDropout drop) {
+  pnp_pdl_enter();
   unsigned long long seed = *drop.seed_ptr;
   long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
@@ -427,7 +437,8 @@ dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, 
   }
 }
 
-__global__ void seed_advance_kernel(unsigned long long* s) { *s = *s * 6364136223846793005ull + 1442695040888963407ull; }
+__global__ void seed_advance_kernel(unsigned long long* s) {
+  pnp_pdl_enter(); *s = *s * 6364136223846793005ull + 1442695040888963407ull; }
 
 // ------------------------------------------------------------------------------------------------
 // pooling / padding / phase shift
@@ -435,6 +446,7 @@ __global__ void seed_advance_kernel(unsigned long long* s) { *s = *s * 636413622
 template <int V>
 __global__ void __launch_bounds__(256)
 maxpool2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  pnp_pdl_enter();
   const int Ho = H / 2, Wo = W / 2, CV = C / V;
   long long total = (long long)B * Ho * Wo * CV;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -462,6 +474,7 @@ maxpool2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, i
 template <int V>
 __global__ void __launch_bounds__(256)
 maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C) {
+  pnp_pdl_enter();
   const int Ho = H / 2, Wo = W / 2, CV = C / V;
   long long total = (long long)B * Ho * Wo * CV;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -492,6 +505,7 @@ maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, f
 // tf.nn.avg_pool 2x2/2 (layers.py:105-106); with_grad: dx = dy/4 broadcast to the window
 __global__ void __launch_bounds__(256)
 avgpool2_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C, int backward) {
+  pnp_pdl_enter();
   const int Ho = H / 2, Wo = W / 2;
   long long total = (long long)B * Ho * Wo * C;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -515,6 +529,7 @@ __device__ __forceinline__ int mirror_idx(int i, int n) { return i < 0 ? (-i - 1
 
 __global__ void __launch_bounds__(256)
 mirror_pad_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C, int p) {
+  pnp_pdl_enter();
   const int Hp = H + 2 * p, Wp = W + 2 * p;
   long long total = (long long)B * Hp * Wp * C;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -531,6 +546,7 @@ mirror_pad_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
 
 __global__ void __launch_bounds__(256)
 mirror_pad_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C, int p) {
+  pnp_pdl_enter();
   const int Hp = H + 2 * p, Wp = W + 2 * p;
   long long total = (long long)B * H * W * C;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -557,6 +573,7 @@ mirror_pad_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int 
 __global__ void __launch_bounds__(256)
 phase_shift_fwd_kernel(const float* __restrict__ X, float* __restrict__ out, int B, int a, int b, int G, int r, int Ctot,
                        int coff, int ntile, int order_b1) {
+  pnp_pdl_enter();
   const int OH = a * r, OW = b * r;
   long long total = (long long)B * OH * OW * G;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -577,6 +594,7 @@ phase_shift_fwd_kernel(const float* __restrict__ X, float* __restrict__ out, int
 __global__ void __launch_bounds__(256)
 phase_shift_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dX, int B, int a, int b, int G, int r, int Ctot,
                        int coff, int ntile, int order_b1) {
+  pnp_pdl_enter();
   const int OH = a * r, OW = b * r, rr = r * r;
   const long long Cx = (long long)G * rr;
   long long total = (long long)B * a * b * Cx;
@@ -613,6 +631,7 @@ struct DiscPlan {
 __global__ void __launch_bounds__(256)
 disc_input_kernel(DiscPlan plan, const float* __restrict__ logits, int NC, float* __restrict__ out, int B, int H, int W, int Ctot,
                   int r, int order_b1) {
+  pnp_pdl_enter();
   const int Q = Ctot >> 2;
   const unsigned total = (unsigned)B * H * W * Q;          // < 2^31 (checked by the launcher): 32-bit index arithmetic throughout
   const int rr = r * r;
@@ -663,6 +682,7 @@ struct DiscLines {
 __global__ void __launch_bounds__(256)
 disc_input_r8_kernel(DiscPlan plan, DiscLines ln, const float* __restrict__ logits, int NC, float* __restrict__ out, int B, int a, int b,
                      int Ctot) {
+  pnp_pdl_enter();
   extern __shared__ float s_tile[];      // [4 source pixels][nlines][65]
   const int nl = ln.nlines;
   const int bx4 = (b + 3) >> 2;
@@ -721,6 +741,7 @@ disc_input_r8_kernel(DiscPlan plan, DiscLines ln, const float* __restrict__ logi
 
 __global__ void __launch_bounds__(256)
 logits_argmax_concat_kernel(const float* __restrict__ logits, float* __restrict__ out, long long P, int C, int Ctot, int coff) {
+  pnp_pdl_enter();
   for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += (long long)gridDim.x * 256) {
     const float* l = logits + p * C;
     float* o = out + p * Ctot + coff;
@@ -743,6 +764,7 @@ constexpr int kMaxC = 8;
 
 __global__ void __launch_bounds__(256)
 pixel_softmax2_kernel(const float* __restrict__ logits, float* __restrict__ out, long long P, int C) {
+  pnp_pdl_enter();
   for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += (long long)gridDim.x * 256) {
     float e[kMaxC], s = 0.f;
     for (int c = 0; c < C; ++c) { e[c] = expf(logits[p * C + c]); s += e[c]; }   // no max subtraction (layers.py:135)
@@ -761,6 +783,7 @@ __device__ __forceinline__ void stable_softmax(const float* l, int C, float* p) 
 
 __global__ void __launch_bounds__(256)
 segloss_reduce_kernel(const float* __restrict__ logits, const float* __restrict__ y, long long P, int C, double* __restrict__ acc) {
+  pnp_pdl_enter();
   __shared__ double s_acc[4 * kMaxC];
   if (threadIdx.x < 4 * kMaxC) s_acc[threadIdx.x] = 0.0;
   __syncthreads();
@@ -804,6 +827,7 @@ segloss_reduce_kernel(const float* __restrict__ logits, const float* __restrict_
 }
 
 __global__ void segloss_finalize_kernel(const double* __restrict__ acc, long long P, int C, float* out, float* coef) {
+  pnp_pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double tot = 0.0;
   for (int c = 0; c < C; ++c) tot += acc[c];
@@ -826,6 +850,7 @@ __global__ void __launch_bounds__(256)
 segloss_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ y, const float* __restrict__ coef,
                    const float* __restrict__ g_wce, const float* __restrict__ g_dice, float* __restrict__ dlogits,
                    long long P, int C) {
+  pnp_pdl_enter();
   const float gw = g_wce ? *g_wce : 0.f;
   const float gd = g_dice ? *g_dice : 0.f;
   for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += (long long)gridDim.x * 256) {
@@ -846,6 +871,7 @@ segloss_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ y
 
 __global__ void __launch_bounds__(256)
 confusion_kernel(const float* __restrict__ logits, const float* __restrict__ y, long long P, int C, unsigned long long* counts) {
+  pnp_pdl_enter();
   __shared__ unsigned int s_cnt[kMaxC * kMaxC];
   if (threadIdx.x < kMaxC * kMaxC) s_cnt[threadIdx.x] = 0u;
   __syncthreads();
@@ -865,6 +891,7 @@ confusion_kernel(const float* __restrict__ logits, const float* __restrict__ y, 
 
 __global__ void __launch_bounds__(256)
 one_hot_kernel(const long long* __restrict__ labels, float* __restrict__ out, long long P, int C) {
+  pnp_pdl_enter();
   for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < P; p += (long long)gridDim.x * 256) {
     long long l = labels[p];
     for (int c = 0; c < C; ++c) out[p * C + c] = (l == c) ? 1.f : 0.f;
@@ -873,6 +900,7 @@ one_hot_kernel(const long long* __restrict__ labels, float* __restrict__ out, lo
 
 __global__ void __launch_bounds__(256)
 fc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out, int F) {
+  pnp_pdl_enter();
   __shared__ float s[8];
   const float* row = x + (long long)blockIdx.x * F;
   float acc = 0.f;
@@ -890,6 +918,7 @@ fc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* _
 __global__ void __launch_bounds__(256)
 fc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ dout, float* __restrict__ dx,
               float* __restrict__ dw, int B, int F) {
+  pnp_pdl_enter();
   int f = blockIdx.x * 256 + threadIdx.x;
   if (f >= F) return;
   float wf = w[f], acc = 0.f;
@@ -903,6 +932,7 @@ fc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
 
 __global__ void __launch_bounds__(256)
 mean_combo_kernel(const float* __restrict__ a, float ca, const float* __restrict__ b, float cb, int n, float* out) {
+  pnp_pdl_enter();
   __shared__ float s[8];
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) acc += ca * a[i] + (b ? cb * b[i] : 0.f);
@@ -918,6 +948,7 @@ mean_combo_kernel(const float* __restrict__ a, float ca, const float* __restrict
 
 __global__ void __launch_bounds__(256)
 l2_loss_kernel(const float* __restrict__ w, long long n, double* out) {
+  pnp_pdl_enter();
   __shared__ double s[8];
   double acc = 0.0;
   float part = 0.f;
@@ -945,6 +976,7 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
             const int* __restrict__ chunk_seg, const float* __restrict__ seg_wd, const double* __restrict__ state, float b1,
             float b2, float eps, float gscale) {
+  pnp_pdl_enter();
   const float wd = seg_wd[chunk_seg[blockIdx.x]];
   const float lr_t = (float)state[3];
   long long i = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -970,6 +1002,7 @@ __global__ void __launch_bounds__(256)
 rmsprop_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ ms, float* __restrict__ mom,
                const int* __restrict__ chunk_seg, const float* __restrict__ seg_wd, const float* __restrict__ seg_clip,
                const float* __restrict__ lr_ptr, float decay, float momentum, float eps, float gscale) {
+  pnp_pdl_enter();
   const int seg = chunk_seg[blockIdx.x];
   const float lr = *lr_ptr;
   const float wd = seg_wd[seg];
@@ -998,6 +1031,7 @@ rmsprop_kernel(float* __restrict__ theta, const float* __restrict__ grad, float*
 __global__ void __launch_bounds__(256)
 momentum_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ accum, const int* __restrict__ chunk_seg,
                 const float* __restrict__ seg_wd, const float* __restrict__ lr_ptr, float momentum, float gscale) {
+  pnp_pdl_enter();
   const int seg = chunk_seg[blockIdx.x];
   const float lr = *lr_ptr;
   const float wd = seg_wd[seg];
@@ -1015,6 +1049,7 @@ momentum_kernel(float* __restrict__ theta, const float* __restrict__ grad, float
 
 // state = [beta1^t, beta2^t, lr, lr_t]: advance t and refresh lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t) (TF Adam)
 __global__ void adam_advance_kernel(double* state, double b1, double b2) {
+  pnp_pdl_enter();
   double p1 = state[0] * b1, p2 = state[1] * b2;
   state[0] = p1;
   state[1] = p2;
@@ -1022,6 +1057,7 @@ __global__ void adam_advance_kernel(double* state, double b1, double b2) {
 }
 
 __global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ p, float v, long long n) {
+  pnp_pdl_enter();
   long long n4 = n >> 2;
   float4 vv = make_float4(v, v, v, v);
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256)
@@ -1038,7 +1074,7 @@ extern "C" int pnp_bn_stats(const float* z, long long M, int C, double* sum, dou
   int tpr, grid; long long rpb;
   int rc = reduce_launch_cfg(M, C, &tpr, &rpb, &grid);
   if (rc) return rc;
-  bn_reduce_kernel<false><<<grid, 256, 0, S_>>>(z, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, M, C, tpr, rpb, sum, sumsq);
+  pnp_launch(bn_reduce_kernel<false>, grid, 256, 0, S_, z, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, M, C, tpr, rpb, sum, sumsq);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1048,7 +1084,7 @@ extern "C" int pnp_bn_finalize(const double* sum, const double* sumsq, long long
                                float* shift, float* mean, float* invstd, void* stream) {
   if (!gamma || !beta || !moving_mean || !moving_var || !scale || !shift || !mean || !invstd || C <= 0) return PNP_ERR_BAD_ARG;
   if (training && (!sum || !sumsq || M <= 0)) return PNP_ERR_BAD_ARG;
-  bn_finalize_kernel<<<pnp_cdiv(C, 128), 128, 0, S_>>>(sum, sumsq, M, C, gamma, beta, moving_mean, moving_var, training, scale,
+  pnp_launch(bn_finalize_kernel, pnp_cdiv(C, 128), 128, 0, S_, sum, sumsq, M, C, gamma, beta, moving_mean, moving_var, training, scale,
                                                        shift, mean, invstd);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
@@ -1061,7 +1097,7 @@ extern "C" int pnp_bn_act_apply(const float* z, const float* scale, const float*
   if (skip && (Cs % 4 != 0 || skip_off % 4 != 0 || skip_off < 0 || skip_off + Cs > C)) return PNP_ERR_UNSUPPORTED;
   if ((scale == nullptr) != (shift == nullptr)) return PNP_ERR_BAD_ARG;
   long long n4 = M * (C / 4);
-  bn_act_apply_kernel<<<grid_for(n4, 256), 256, 0, S_>>>(z, scale, shift, skip, Cs, skip_off, act, y, y_hi, y_lo, n4, C / 4);
+  pnp_launch(bn_act_apply_kernel, grid_for(n4, 256), 256, 0, S_, z, scale, shift, skip, Cs, skip_off, act, y, y_hi, y_lo, n4, C / 4);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1073,7 +1109,7 @@ extern "C" int pnp_bn_bwd_reduce(const float* dy, const float* y, const float* z
   int tpr, grid; long long rpb;
   int rc = reduce_launch_cfg(M, C, &tpr, &rpb, &grid);
   if (rc) return rc;
-  bn_reduce_kernel<true><<<grid, 256, 0, S_>>>(z, dy, y, nullptr, mean, invstd, act, g, M, C, tpr, rpb, sum_g, sum_gx);
+  pnp_launch(bn_reduce_kernel<true>, grid, 256, 0, S_, z, dy, y, nullptr, mean, invstd, act, g, M, C, tpr, rpb, sum_g, sum_gx);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1087,7 +1123,7 @@ extern "C" int pnp_bn_bwd_reduce_sums(const float* dy, const float* y, const uin
   int tpr, grid; long long rpb;
   int rc = reduce_launch_cfg(M, C, &tpr, &rpb, &grid);
   if (rc) return rc;
-  bn_reduce_kernel<true><<<grid, 256, 0, S_>>>(z, dy, y, y_hi, mean, invstd, act, nullptr, M, C, tpr, rpb, sum_g, sum_gx);
+  pnp_launch(bn_reduce_kernel<true>, grid, 256, 0, S_, z, dy, y, y_hi, mean, invstd, act, nullptr, M, C, tpr, rpb, sum_g, sum_gx);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1095,7 +1131,7 @@ extern "C" int pnp_bn_bwd_reduce_sums(const float* dy, const float* y, const uin
 extern "C" int pnp_bn_bwd_finalize(const double* sum_g, const double* sum_gx, long long M, int C, float* dgamma,
                                    float* dbeta, float* coef, void* stream) {
   if (!sum_g || !sum_gx || !coef || C <= 0 || M <= 0) return PNP_ERR_BAD_ARG;
-  bn_bwd_finalize_kernel<<<pnp_cdiv(C, 128), 128, 0, S_>>>(sum_g, sum_gx, M, C, dgamma, dbeta, coef);
+  pnp_launch(bn_bwd_finalize_kernel, pnp_cdiv(C, 128), 128, 0, S_, sum_g, sum_gx, M, C, dgamma, dbeta, coef);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1107,7 +1143,7 @@ extern "C" int pnp_bn_bwd_apply(const float* g, const float* z, const float* mea
   if (training && (!z || !mean || !coef)) return PNP_ERR_BAD_ARG;
   if (C % 4 != 0) return PNP_ERR_UNSUPPORTED;
   long long n4 = M * (C / 4);
-  bn_bwd_apply_kernel<<<grid_for(n4, 256), 256, 0, S_>>>(g, z, mean, invstd, gamma, coef, training, make_drop(drop), dz, dz_hi, dz_lo,
+  pnp_launch(bn_bwd_apply_kernel, grid_for(n4, 256), 256, 0, S_, g, z, mean, invstd, gamma, coef, training, make_drop(drop), dz, dz_hi, dz_lo,
                                                             n4, C / 4);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
@@ -1123,7 +1159,7 @@ extern "C" int pnp_bn_apply_fused(const float* z, const double* sum, const doubl
   if (C % 4 != 0 || C > 1024) return PNP_ERR_UNSUPPORTED;
   if (skip && (Cs % 4 != 0 || skip_off % 4 != 0 || skip_off < 0 || skip_off + Cs > C)) return PNP_ERR_UNSUPPORTED;
   long long n4 = M * (C / 4);
-  bn_apply_fused_kernel<<<grid_for(n4, 256), 256, 2 * C * sizeof(float), S_>>>(z, sum, sumsq, M, C, gamma, beta, moving_mean, moving_var,
+  pnp_launch(bn_apply_fused_kernel, grid_for(n4, 256), 256, 2 * C * sizeof(float), S_, z, sum, sumsq, M, C, gamma, beta, moving_mean, moving_var,
                                                                              training, skip, Cs, skip_off, act, y, y_hi, y_lo,
                                                                              mean_out, invstd_out, n4);
   PNP_LAUNCH_CHECK();
@@ -1140,7 +1176,7 @@ extern "C" int pnp_bn_bwd_apply_fused(const float* g, const float* z, const floa
   if ((dgamma || dbeta) && !sum_g) return PNP_ERR_BAD_ARG;
   if (C % 4 != 0 || C > 1024) return PNP_ERR_UNSUPPORTED;
   long long n4 = M * (C / 4);
-  bn_bwd_apply_fused_kernel<<<grid_for(n4, 256), 256, 5 * C * sizeof(float), S_>>>(g, nullptr, nullptr, PNP_ACT_NONE, z, mean, invstd, gamma,
+  pnp_launch(bn_bwd_apply_fused_kernel, grid_for(n4, 256), 256, 5 * C * sizeof(float), S_, g, nullptr, nullptr, PNP_ACT_NONE, z, mean, invstd, gamma,
                                                                                  sum_g, sum_gx, M, C, training, make_drop(drop), dgamma,
                                                                                  dbeta, dz, dz_hi, dz_lo, n4);
   PNP_LAUNCH_CHECK();
@@ -1160,7 +1196,7 @@ extern "C" int pnp_bn_bwd_apply_direct(const float* dy, const float* y, const ui
   if ((dgamma || dbeta) && !sum_g) return PNP_ERR_BAD_ARG;
   if (C % 4 != 0 || C > 1024) return PNP_ERR_UNSUPPORTED;
   long long n4 = M * (C / 4);
-  bn_bwd_apply_fused_kernel<<<grid_for(n4, 256), 256, 5 * C * sizeof(float), S_>>>(dy, y, y_hi, act, z, mean, invstd, gamma, sum_g, sum_gx, M,
+  pnp_launch(bn_bwd_apply_fused_kernel, grid_for(n4, 256), 256, 5 * C * sizeof(float), S_, dy, y, y_hi, act, z, mean, invstd, gamma, sum_g, sum_gx, M,
                                                                                  C, training, make_drop(drop), dgamma, dbeta, dz, dz_hi,
                                                                                  dz_lo, n4);
   PNP_LAUNCH_CHECK();
@@ -1169,7 +1205,7 @@ extern "C" int pnp_bn_bwd_apply_direct(const float* dy, const float* y, const ui
 
 extern "C" int pnp_act_bwd(const float* dy, const float* y, int act, float* g, long long n, void* stream) {
   if (!dy || !y || !g || n <= 0) return PNP_ERR_BAD_ARG;
-  act_bwd_kernel<<<grid_for(n, 256 * 8), 256, 0, S_>>>(dy, y, act, g, n);
+  pnp_launch(act_bwd_kernel, grid_for(n, 256 * 8), 256, 0, S_, dy, y, act, g, n);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1177,7 +1213,7 @@ extern "C" int pnp_act_bwd(const float* dy, const float* y, int act, float* g, l
 extern "C" int pnp_channel_slice(const float* g, int C, int off, int Cs, float* out, long long M, int accumulate, void* stream) {
   if (!g || !out || M <= 0 || Cs <= 0 || off < 0 || off + Cs > C) return PNP_ERR_BAD_ARG;
   long long total = M * Cs;
-  channel_slice_kernel<<<grid_for(total, 256 * 8), 256, 0, S_>>>(g, C, off, Cs, out, total, accumulate);
+  pnp_launch(channel_slice_kernel, grid_for(total, 256 * 8), 256, 0, S_, g, C, off, Cs, out, total, accumulate);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1189,14 +1225,14 @@ extern "C" int pnp_dropout_apply(const float* x, float* y, long long n, const pn
     if (x != y) PNP_CUDA(cudaMemcpyAsync(y, x, n * sizeof(float), cudaMemcpyDeviceToDevice, S_));
     return PNP_OK;
   }
-  dropout_kernel<<<grid_for(n / 4 + 1, 256 * 4), 256, 0, S_>>>(x, y, n, d);
+  pnp_launch(dropout_kernel, grid_for(n / 4 + 1, 256 * 4), 256, 0, S_, x, y, n, d);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
 
 extern "C" int pnp_seed_advance(unsigned long long* seed_ptr, void* stream) {
   if (!seed_ptr) return PNP_ERR_BAD_ARG;
-  seed_advance_kernel<<<1, 1, 0, S_>>>(seed_ptr);
+  pnp_launch(seed_advance_kernel, 1, 1, 0, S_, seed_ptr);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1205,8 +1241,8 @@ extern "C" int pnp_maxpool2_fwd(const float* x, float* y, int B, int H, int W, i
   if (!x || !y || B <= 0 || H <= 0 || W <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
   if ((H | W) & 1) return PNP_ERR_UNSUPPORTED;
   long long total = (long long)B * (H / 2) * (W / 2) * C;
-  if (C % 4 == 0) maxpool2_fwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S_>>>(x, y, B, H, W, C);
-  else maxpool2_fwd_kernel<1><<<grid_for(total, 256 * 4), 256, 0, S_>>>(x, y, B, H, W, C);
+  if (C % 4 == 0) pnp_launch(maxpool2_fwd_kernel<4>, grid_for(total / 4, 256 * 2), 256, 0, S_, x, y, B, H, W, C);
+  else pnp_launch(maxpool2_fwd_kernel<1>, grid_for(total, 256 * 4), 256, 0, S_, x, y, B, H, W, C);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1215,8 +1251,8 @@ extern "C" int pnp_maxpool2_bwd(const float* x, const float* dy, float* dx, int 
   if (!x || !dy || !dx || B <= 0 || H <= 0 || W <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
   if ((H | W) & 1) return PNP_ERR_UNSUPPORTED;
   long long total = (long long)B * (H / 2) * (W / 2) * C;
-  if (C % 4 == 0) maxpool2_bwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S_>>>(x, dy, dx, B, H, W, C);
-  else maxpool2_bwd_kernel<1><<<grid_for(total, 256 * 4), 256, 0, S_>>>(x, dy, dx, B, H, W, C);
+  if (C % 4 == 0) pnp_launch(maxpool2_bwd_kernel<4>, grid_for(total / 4, 256 * 2), 256, 0, S_, x, dy, dx, B, H, W, C);
+  else pnp_launch(maxpool2_bwd_kernel<1>, grid_for(total, 256 * 4), 256, 0, S_, x, dy, dx, B, H, W, C);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1225,7 +1261,7 @@ extern "C" int pnp_avgpool2(const float* in, float* out, int B, int H, int W, in
   if (!in || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
   if ((H | W) & 1) return PNP_ERR_UNSUPPORTED;
   long long total = (long long)B * (H / 2) * (W / 2) * C;
-  avgpool2_kernel<<<grid_for(total, 256 * 4), 256, 0, S_>>>(in, out, B, H, W, C, backward);
+  pnp_launch(avgpool2_kernel, grid_for(total, 256 * 4), 256, 0, S_, in, out, B, H, W, C, backward);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1234,7 +1270,7 @@ extern "C" int pnp_mirror_pad_fwd(const float* x, float* y, int B, int H, int W,
   if (!x || !y || B <= 0 || H <= 0 || W <= 0 || C <= 0 || p < 0) return PNP_ERR_BAD_ARG;
   if (p > H || p > W) return PNP_ERR_UNSUPPORTED;
   long long total = (long long)B * (H + 2 * p) * (W + 2 * p) * C;
-  mirror_pad_fwd_kernel<<<grid_for(total, 256 * 8), 256, 0, S_>>>(x, y, B, H, W, C, p);
+  pnp_launch(mirror_pad_fwd_kernel, grid_for(total, 256 * 8), 256, 0, S_, x, y, B, H, W, C, p);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1243,7 +1279,7 @@ extern "C" int pnp_mirror_pad_bwd(const float* dy, float* dx, int B, int H, int 
   if (!dy || !dx || B <= 0 || H <= 0 || W <= 0 || C <= 0 || p < 0) return PNP_ERR_BAD_ARG;
   if (2 * p > H || 2 * p > W) return PNP_ERR_UNSUPPORTED;
   long long total = (long long)B * H * W * C;
-  mirror_pad_bwd_kernel<<<grid_for(total, 256 * 8), 256, 0, S_>>>(dy, dx, B, H, W, C, p);
+  pnp_launch(mirror_pad_bwd_kernel, grid_for(total, 256 * 8), 256, 0, S_, dy, dx, B, H, W, C, p);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1253,7 +1289,7 @@ extern "C" int pnp_phase_shift_fwd(const float* X, float* out, int B, int a, int
   if (!X || !out || B <= 0 || a <= 0 || b <= 0 || G <= 0 || r <= 0 || ntile <= 0 || coff < 0 || coff + ntile * G > Ctot)
     return PNP_ERR_BAD_ARG;
   long long total = (long long)B * a * r * b * r * G;
-  phase_shift_fwd_kernel<<<grid_for(total, 256 * 8), 256, 0, S_>>>(X, out, B, a, b, G, r, Ctot, coff, ntile, order_b1);
+  pnp_launch(phase_shift_fwd_kernel, grid_for(total, 256 * 8), 256, 0, S_, X, out, B, a, b, G, r, Ctot, coff, ntile, order_b1);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1263,7 +1299,7 @@ extern "C" int pnp_phase_shift_bwd(const float* dout, float* dX, int B, int a, i
   if (!dout || !dX || B <= 0 || a <= 0 || b <= 0 || G <= 0 || r <= 0 || ntile <= 0 || coff < 0 || coff + ntile * G > Ctot)
     return PNP_ERR_BAD_ARG;
   long long total = (long long)B * a * b * G * r * r;
-  phase_shift_bwd_kernel<<<grid_for(total, 256 * 8), 256, 0, S_>>>(dout, dX, B, a, b, G, r, Ctot, coff, ntile, order_b1);
+  pnp_launch(phase_shift_bwd_kernel, grid_for(total, 256 * 8), 256, 0, S_, dout, dX, B, a, b, G, r, Ctot, coff, ntile, order_b1);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1318,19 +1354,19 @@ extern "C" int pnp_disc_input_fwd(const float* const* srcs, const int* a, const 
     const size_t smem = (size_t)4 * ln.nlines * 65 * sizeof(float);
     if (fits && ln.nlines > 0 && smem <= 48 * 1024) {
       const long long blocks = (long long)B * a[0] * ((b[0] + 3) / 4);
-      disc_input_r8_kernel<<<(unsigned)blocks, 256, smem, S_>>>(plan, ln, logits, NC, out, B, a[0], b[0], Ctot);
+      pnp_launch(disc_input_r8_kernel, (unsigned)blocks, 256, smem, S_, plan, ln, logits, NC, out, B, a[0], b[0], Ctot);
       PNP_LAUNCH_CHECK();
       return PNP_OK;
     }
   }
-  disc_input_kernel<<<grid_for(total, 256), 256, 0, S_>>>(plan, logits, NC, out, B, H, W, Ctot, r, order_b1);
+  pnp_launch(disc_input_kernel, grid_for(total, 256), 256, 0, S_, plan, logits, NC, out, B, H, W, Ctot, r, order_b1);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
 
 extern "C" int pnp_logits_argmax_concat(const float* logits, float* out, long long P, int C, int Ctot, int coff, void* stream) {
   if (!logits || !out || P <= 0 || C <= 0 || coff < 0 || coff + C + 1 > Ctot) return PNP_ERR_BAD_ARG;
-  logits_argmax_concat_kernel<<<grid_for(P, 256 * 2), 256, 0, S_>>>(logits, out, P, C, Ctot, coff);
+  pnp_launch(logits_argmax_concat_kernel, grid_for(P, 256 * 2), 256, 0, S_, logits, out, P, C, Ctot, coff);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1338,7 +1374,7 @@ extern "C" int pnp_logits_argmax_concat(const float* logits, float* out, long lo
 extern "C" int pnp_pixel_softmax2(const float* logits, float* out, long long P, int C, void* stream) {
   if (!logits || !out || P <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
   if (C > kMaxC) return PNP_ERR_UNSUPPORTED;
-  pixel_softmax2_kernel<<<grid_for(P, 256 * 2), 256, 0, S_>>>(logits, out, P, C);
+  pnp_launch(pixel_softmax2_kernel, grid_for(P, 256 * 2), 256, 0, S_, logits, out, P, C);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1346,14 +1382,14 @@ extern "C" int pnp_pixel_softmax2(const float* logits, float* out, long long P, 
 extern "C" int pnp_segloss_reduce(const float* logits, const float* y, long long P, int C, double* acc, void* stream) {
   if (!logits || !y || !acc || P <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
   if (C > kMaxC) return PNP_ERR_UNSUPPORTED;
-  segloss_reduce_kernel<<<grid_for(P, 256 * 8), 256, 0, S_>>>(logits, y, P, C, acc);
+  pnp_launch(segloss_reduce_kernel, grid_for(P, 256 * 8), 256, 0, S_, logits, y, P, C, acc);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
 
 extern "C" int pnp_segloss_finalize(const double* acc, long long P, int C, float* out, float* coef, void* stream) {
   if (!acc || !out || !coef || P <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
-  segloss_finalize_kernel<<<1, 32, 0, S_>>>(acc, P, C, out, coef);
+  pnp_launch(segloss_finalize_kernel, 1, 32, 0, S_, acc, P, C, out, coef);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1362,7 +1398,7 @@ extern "C" int pnp_segloss_bwd(const float* logits, const float* y, const float*
                                float* dlogits, long long P, int C, void* stream) {
   if (!logits || !y || !coef || !dlogits || P <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
   if (C > kMaxC) return PNP_ERR_UNSUPPORTED;
-  segloss_bwd_kernel<<<grid_for(P, 256 * 2), 256, 0, S_>>>(logits, y, coef, g_wce, g_dice, dlogits, P, C);
+  pnp_launch(segloss_bwd_kernel, grid_for(P, 256 * 2), 256, 0, S_, logits, y, coef, g_wce, g_dice, dlogits, P, C);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1370,49 +1406,49 @@ extern "C" int pnp_segloss_bwd(const float* logits, const float* y, const float*
 extern "C" int pnp_confusion(const float* logits, const float* y, long long P, int C, unsigned long long* counts, void* stream) {
   if (!logits || !y || !counts || P <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
   if (C > kMaxC) return PNP_ERR_UNSUPPORTED;
-  confusion_kernel<<<grid_for(P, 256 * 16), 256, 0, S_>>>(logits, y, P, C, counts);
+  pnp_launch(confusion_kernel, grid_for(P, 256 * 16), 256, 0, S_, logits, y, P, C, counts);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
 
 extern "C" int pnp_one_hot(const long long* labels, float* out, long long P, int C, void* stream) {
   if (!labels || !out || P <= 0 || C <= 0) return PNP_ERR_BAD_ARG;
-  one_hot_kernel<<<grid_for(P, 256 * 2), 256, 0, S_>>>(labels, out, P, C);
+  pnp_launch(one_hot_kernel, grid_for(P, 256 * 2), 256, 0, S_, labels, out, P, C);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
 
 extern "C" int pnp_fc_fwd(const float* x, const float* w, float* out, int B, int F, void* stream) {
   if (!x || !w || !out || B <= 0 || F <= 0) return PNP_ERR_BAD_ARG;
-  fc_fwd_kernel<<<B, 256, 0, S_>>>(x, w, out, F);
+  pnp_launch(fc_fwd_kernel, B, 256, 0, S_, x, w, out, F);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
 
 extern "C" int pnp_fc_bwd(const float* x, const float* w, const float* dout, float* dx, float* dw, int B, int F, void* stream) {
   if (!x || !w || !dout || B <= 0 || F <= 0) return PNP_ERR_BAD_ARG;
-  fc_bwd_kernel<<<pnp_cdiv(F, 256), 256, 0, S_>>>(x, w, dout, dx, dw, B, F);
+  pnp_launch(fc_bwd_kernel, pnp_cdiv(F, 256), 256, 0, S_, x, w, dout, dx, dw, B, F);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
 
 extern "C" int pnp_mean_combo(const float* a, float ca, const float* b, float cb, int n, float* out, void* stream) {
   if (!a || !out || n <= 0) return PNP_ERR_BAD_ARG;
-  mean_combo_kernel<<<1, 256, 0, S_>>>(a, ca, b, cb, n, out);
+  pnp_launch(mean_combo_kernel, 1, 256, 0, S_, a, ca, b, cb, n, out);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
 
 extern "C" int pnp_l2_loss_acc(const float* w, long long n, double* out, void* stream) {
   if (!w || !out || n <= 0) return PNP_ERR_BAD_ARG;
-  l2_loss_kernel<<<grid_for(n, 256 * 16), 256, 0, S_>>>(w, n, out);
+  pnp_launch(l2_loss_kernel, grid_for(n, 256 * 16), 256, 0, S_, w, n, out);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
 
 extern "C" int pnp_adam_advance(double* state, float beta1, float beta2, void* stream) {
   if (!state) return PNP_ERR_BAD_ARG;
-  adam_advance_kernel<<<1, 1, 0, S_>>>(state, (double)beta1, (double)beta2);
+  pnp_launch(adam_advance_kernel, 1, 1, 0, S_, state, (double)beta1, (double)beta2);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1421,7 +1457,7 @@ extern "C" int pnp_adam_step(float* theta, const float* grad, float* m, float* v
                              const float* seg_wd, const double* state, float beta1, float beta2, float eps, float grad_scale,
                              void* stream) {
   if (!theta || !grad || !m || !v || !chunk_seg || !seg_wd || !state || n <= 0 || (n % 1024) != 0) return PNP_ERR_BAD_ARG;
-  adam_kernel<<<(unsigned)(n / 1024), 256, 0, S_>>>(theta, grad, m, v, chunk_seg, seg_wd, state, beta1, beta2, eps, grad_scale);
+  pnp_launch(adam_kernel, (unsigned)(n / 1024), 256, 0, S_, theta, grad, m, v, chunk_seg, seg_wd, state, beta1, beta2, eps, grad_scale);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
@@ -1430,7 +1466,7 @@ extern "C" int pnp_rmsprop_step(float* theta, const float* grad, float* ms, floa
                                 const float* seg_wd, const float* seg_clip, const float* lr_ptr, float decay, float momentum,
                                 float eps, float grad_scale, void* stream) {
   if (!theta || !grad || !ms || !mom || !chunk_seg || !seg_wd || !lr_ptr || n <= 0 || (n % 1024) != 0) return PNP_ERR_BAD_ARG;
-  rmsprop_kernel<<<(unsigned)(n / 1024), 256, 0, S_>>>(theta, grad, ms, mom, chunk_seg, seg_wd, seg_clip, lr_ptr, decay, momentum, eps,
+  pnp_launch(rmsprop_kernel, (unsigned)(n / 1024), 256, 0, S_, theta, grad, ms, mom, chunk_seg, seg_wd, seg_clip, lr_ptr, decay, momentum, eps,
                                                       grad_scale);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
@@ -1439,14 +1475,14 @@ extern "C" int pnp_rmsprop_step(float* theta, const float* grad, float* ms, floa
 extern "C" int pnp_momentum_step(float* theta, const float* grad, float* accum, long long n, const int* chunk_seg, const float* seg_wd,
                                  const float* lr_ptr, float momentum, float grad_scale, void* stream) {
   if (!theta || !grad || !accum || !chunk_seg || !seg_wd || !lr_ptr || n <= 0 || (n % 1024) != 0) return PNP_ERR_BAD_ARG;
-  momentum_kernel<<<(unsigned)(n / 1024), 256, 0, S_>>>(theta, grad, accum, chunk_seg, seg_wd, lr_ptr, momentum, grad_scale);
+  pnp_launch(momentum_kernel, (unsigned)(n / 1024), 256, 0, S_, theta, grad, accum, chunk_seg, seg_wd, lr_ptr, momentum, grad_scale);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
 
 extern "C" int pnp_fill(float* p, float v, long long n, void* stream) {
   if (!p || n <= 0) return PNP_ERR_BAD_ARG;
-  fill_kernel<<<grid_for(n / 4 + 1, 256 * 4), 256, 0, S_>>>(p, v, n);
+  pnp_launch(fill_kernel, grid_for(n / 4 + 1, 256 * 4), 256, 0, S_, p, v, n);
   PNP_LAUNCH_CHECK();
   return PNP_OK;
 }
