@@ -731,6 +731,144 @@ ps_mirror_conv_kernel(const float* __restrict__ X, const float* __restrict__ w, 
   }
 }
 
+// 5x5 specialisation (the only size the graphs use), register-tiled: a thread owns a COLUMN of 8 output rows (lanes run along x, so
+// every shared-memory read is conflict-free) and slides the 5 vertical taps over 12 activations held in registers: per (channel,
+// kx) 12 activation loads + 7 broadcast 128-bit weight loads feed 200 FMAs, where the generic kernel above spends 9 loads per 20
+// FMAs and is shared-memory-issue bound (r2: 262 us per B = 8 call at 20 TFLOP/s).  128 threads per 32x32 tile.  Measured (r2y, B = 16):
+// 266 us against the generic kernel's 436 us.
+template <int NO>
+__global__ void __launch_bounds__(128)
+ps_mirror_conv5_kernel(const float* __restrict__ X, const float* __restrict__ w, float* __restrict__ y, int B, int a, int b, int G,
+                       int r, int order_b1) {
+  pnp_pdl_enter();
+  constexpr int T = 32, CC = 8, HALO = T + 4, RY = 8, KS = 5, NT = 128;
+  constexpr int WPAD = ((KS * NO + 3) / 4) * 4;          // the KS x NO weights of one (channel, kx), padded to whole float4s
+  __shared__ float s_x[CC][HALO][HALO + 1];
+  __shared__ __align__(16) float s_w[CC][KS][WPAD];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * T, y0 = blockIdx.y * T, n = blockIdx.z;
+  const int H = a * r, W = b * r, rr = r * r;
+  constexpr int ph = 2, pw = 2, hh = HALO, hw = HALO;
+  const int nby = (hh + 7) >> 3, nbx = (hw + 3) >> 2;
+  const long long Ctot = (long long)G * rr;
+  float acc[RY][NO];
+#pragma unroll
+  for (int j = 0; j < RY; ++j)
+#pragma unroll
+    for (int o = 0; o < NO; ++o) acc[j][o] = 0.f;
+  const float* Xn = X + (long long)n * a * b * Ctot;
+  for (int c0 = 0; c0 < G; c0 += CC) {
+    __syncthreads();
+    if (r == 8 && !order_b1) {
+      // one (source pixel, group) = 64 contiguous floats = the 8x8 block flat[8*iy + q][8*ix + p] = X[.., g*64 + p*8 + q]: a warp
+      // reads the 256-byte line with one float2 per lane and scatters it into the tile; blocks outside the image are the mirror
+      // images of the border blocks.  Warp w owns channels w and w + 4 of the chunk and walks the (<= 6 x 6) source blocks of the
+      // halo with nested loops -- no division by run-time values (ncu r2x: the first version of this kernel executed MORE
+      // instructions than the generic one, 387 M vs 347 M at B = 16 against 164 M FMAs, nearly all of the surplus in a loader that
+      // decoded a linear item index) -- and issues the 12 loads of one block row before scattering any of them.
+      static_assert(CC == 8 && NT == 128, "loader assumes 4 warps x 2 channels");
+      const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
+      const int bY0 = (y0 - ph) >> 3, bX0 = (x0 - pw) >> 3;            // first source block touched (floor: may be -1)
+      const int nbY = ((y0 - ph + hh - 1) >> 3) - bY0 + 1, nbX = ((x0 - pw + hw - 1) >> 3) - bX0 + 1;      // <= 6 each
+      const int p_ = ln >> 2, q_ = (ln & 3) * 2;                          // this lane's elements: (p_, q_) and (p_, q_ + 1)
+      const bool on0 = c0 + wid < G, on1 = c0 + wid + 4 < G;
+      const float* Xc = Xn + (long long)(c0 + wid) * 64 + ln * 2;
+      for (int sy = 0; sy < nbY; ++sy) {
+        const int bY = bY0 + sy;
+        const int sbY = bY < 0 ? 0 : (bY >= a ? a - 1 : bY);
+        const int Yi = sbY * 8 + q_;
+        const bool my = bY < 0 || bY >= a;                               // mirrored block: its rows run backwards
+        const int Yp = bY < 0 ? (-1 - Yi) : (bY >= a ? 2 * H - 1 - Yi : Yi);
+        const int py0 = Yp - (y0 - ph), py1 = py0 + (my ? -1 : 1);
+        const bool ok0 = py0 >= 0 && py0 < hh, ok1 = py1 >= 0 && py1 < hh;
+        const float* Xrow = Xc + (long long)sbY * b * Ctot;
+        float2 v0[6], v1[6];
+#pragma unroll
+        for (int sx = 0; sx < 6; ++sx) {
+          const int bX = bX0 + sx;
+          const int sbX = bX < 0 ? 0 : (bX >= b ? b - 1 : bX);
+          const float* src = Xrow + (long long)sbX * Ctot;
+          v0[sx] = (sx < nbX && on0) ? __ldg(reinterpret_cast<const float2*>(src)) : make_float2(0.f, 0.f);
+          v1[sx] = (sx < nbX && on1) ? __ldg(reinterpret_cast<const float2*>(src + 4 * 64)) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int sx = 0; sx < 6; ++sx) {
+          if (sx < nbX) {
+            const int bX = bX0 + sx;
+            const int sbX = bX < 0 ? 0 : (bX >= b ? b - 1 : bX);
+            const int Xi = sbX * 8 + p_;
+            const int Xp = bX < 0 ? (-1 - Xi) : (bX >= b ? 2 * W - 1 - Xi : Xi);
+            const int px = Xp - (x0 - pw);
+            if (px >= 0 && px < hw) {
+              if (ok0) { s_x[wid][py0][px] = v0[sx].x; s_x[wid + 4][py0][px] = v1[sx].x; }
+              if (ok1) { s_x[wid][py1][px] = v0[sx].y; s_x[wid + 4][py1][px] = v1[sx].y; }
+            }
+          }
+        }
+      }
+    } else {
+      const int total = nby * nbx * 32 * CC;
+      for (int e = threadIdx.x; e < total; e += NT) {
+        const int ly = e & 7, lx = (e >> 3) & 3;
+        int rest = e >> 5;
+        const int c = rest % CC;
+        rest /= CC;
+        const int bx = rest % nbx, by = rest / nbx;
+        const int py = by * 8 + ly, px = bx * 4 + lx;
+        if (py < hh && px < hw) {
+          float v = 0.f;
+          if (c0 + c < G) {
+            const int Y = mirror_i(y0 + py - ph, H), Xc = mirror_i(x0 + px - pw, W);
+            const int iy = Y / r, qy = Y - iy * r, ix = Xc / r, qx = Xc - ix * r;
+            const int sub = order_b1 ? (qy * r + qx) : (qx * r + qy);
+            v = __ldg(Xn + ((long long)iy * b + ix) * Ctot + (long long)(c0 + c) * rr + sub);
+          }
+          s_x[c][py][px] = v;
+        }
+      }
+    }
+    for (int p = threadIdx.x; p < KS * KS * CC * NO; p += NT) {
+      const int o = p % NO, c = (p / NO) % CC, t = p / (NO * CC);
+      const int ky = t / KS, kx = t - ky * KS;
+      s_w[c][kx][ky * NO + o] = (c0 + c < G) ? __ldg(w + ((long long)t * G + c0 + c) * NO + o) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int c = 0; c < CC; ++c) {
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) {
+        float av[RY + KS - 1];
+#pragma unroll
+        for (int i = 0; i < RY + KS - 1; ++i) av[i] = s_x[c][ty * RY + i][tx + kx];
+        float wv[WPAD];
+#pragma unroll
+        for (int q = 0; q < WPAD / 4; ++q) {
+          const float4 t4 = *reinterpret_cast<const float4*>(&s_w[c][kx][4 * q]);
+          wv[4 * q] = t4.x; wv[4 * q + 1] = t4.y; wv[4 * q + 2] = t4.z; wv[4 * q + 3] = t4.w;
+        }
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+          for (int j = 0; j < RY; ++j)
+#pragma unroll
+            for (int o = 0; o < NO; ++o) acc[j][o] = fmaf(av[j + ky], wv[ky * NO + o], acc[j][o]);
+      }
+    }
+  }
+  const int ox = x0 + tx;
+  if (ox < W) {
+#pragma unroll
+    for (int j = 0; j < RY; ++j) {
+      const int oy = y0 + ty * RY + j;
+      if (oy < H) {
+        float* dst = y + (((long long)n * H + oy) * W + ox) * NO;
+#pragma unroll
+        for (int o = 0; o < NO; ++o) dst[o] = acc[j][o];
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Backward of the fused tail w.r.t. its feature-map input, in ONE kernel:
 //     dX = PS_r^T( mirror_pad^T( conv^T(dy, w) ) )        (the G step's path from d logits to d conv10)
@@ -826,6 +964,150 @@ ps_mirror_conv_bwd_kernel(const float* __restrict__ dy, const float* __restrict_
   }
 }
 
+// 5x5 specialisation of the backward tail, register-tiled like the forward one: a thread owns the 8 rows Y = 8*iy .. 8*iy + 7 of one
+// column X -- for r = 8 exactly the 8 sub-pixel rows of ONE source pixel, i.e. 8 CONTIGUOUS floats of dX per group (the kernel above
+// writes them as 8 scattered 4-byte stores per thread and runs at 85 GB/s of DRAM traffic) -- and 8 groups at a time: per (kx, o)
+// 12 dy loads + 10 broadcast 128-bit weight loads feed 320 FMAs.  The mirror fold (border rows / columns receive the reflected
+// padded positions as well) runs as a second, generic pass that only threads of edge pixels enter.
+template <int NO>
+__global__ void __launch_bounds__(128)
+ps_mirror_conv5_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dX, int B, int a, int b,
+                           int G, int r, int order_b1) {
+  pnp_pdl_enter();
+  constexpr int T = 32, CC = 8, HALO = T + 4, RY = 8, KS = 5, NT = 128;
+  constexpr int ph = 2, pw = 2, hh = HALO, hw = HALO;
+  __shared__ float s_d[NO][HALO][HALO + 1];                 // dy tile with halo (zero outside the image), channel-major
+  __shared__ __align__(16) float s_w[KS][NO][KS][CC];       // [kx][o][ky][group]: the 40 weights of one (kx, o) are contiguous
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * T, y0 = blockIdx.y * T, n = blockIdx.z;
+  const int H = a * r, W = b * r, rr = r * r;
+  const long long Ctot = (long long)G * rr;
+  const float* dyn = dy + (long long)n * H * W * NO;
+  for (int p = threadIdx.x; p < hh * hw; p += NT) {
+    const int py = p / hw, px = p - py * hw;
+    const int iy = y0 + py - ph, ix = x0 + px - pw;
+    const bool in = iy >= 0 && iy < H && ix >= 0 && ix < W;
+#pragma unroll
+    for (int o = 0; o < NO; ++o) s_d[o][py][px] = in ? __ldg(dyn + ((long long)iy * W + ix) * NO + o) : 0.f;
+  }
+  const int X = x0 + tx;
+  const int Yb = y0 + ty * RY;                               // first of this thread's 8 rows
+  const bool live = X < W && Yb < H;
+  // mirror images of column X in the padded frame (beyond the padded position X + pw itself)
+  int xs[2], nx = 0;
+  if (X < pw) xs[nx++] = pw - 1 - X;
+  if (X >= W - pw && X < W) xs[nx++] = 2 * W - 1 - X + pw;
+  const bool edge_rows = (Yb < ph) || (Yb + RY > H - ph);
+  float* dXn = dX + (long long)n * a * b * Ctot;
+  for (int c0 = 0; c0 < G; c0 += CC) {
+    __syncthreads();
+    for (int p = threadIdx.x; p < KS * KS * CC * NO; p += NT) {
+      const int o = p % NO, c = (p / NO) % CC, t = p / (NO * CC);
+      const int ky = t / KS, kx = t - ky * KS;
+      s_w[kx][o][ky][c] = (c0 + c < G) ? __ldg(w + ((long long)t * G + c0 + c) * NO + o) : 0.f;
+    }
+    __syncthreads();
+    float acc[RY][CC];
+#pragma unroll
+    for (int j = 0; j < RY; ++j)
+#pragma unroll
+      for (int c = 0; c < CC; ++c) acc[j][c] = 0.f;
+    // padded position (Y + ph, X + pw) itself: dflat[Y, X] += sum_{ky,kx,o} dy[Y + ph - ky, X + pw - kx, o] * w[ky, kx, g, o];
+    // in halo coordinates (origin y0 - ph, x0 - pw) that is row (Y - y0) + 2*ph - ky, column tx + 2*pw - kx
+#pragma unroll 1
+    for (int kx = 0; kx < KS; ++kx) {
+#pragma unroll 1
+      for (int o = 0; o < NO; ++o) {
+        float dv[RY + KS - 1];
+#pragma unroll
+        for (int i = 0; i < RY + KS - 1; ++i) dv[i] = s_d[o][ty * RY + i][tx + 2 * pw - kx];
+        float wv[KS * CC];
+#pragma unroll
+        for (int q = 0; q < KS * CC / 4; ++q) {
+          const float4 t4 = *reinterpret_cast<const float4*>(&s_w[kx][o][0][0] + 4 * q);
+          wv[4 * q] = t4.x; wv[4 * q + 1] = t4.y; wv[4 * q + 2] = t4.z; wv[4 * q + 3] = t4.w;
+        }
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+          for (int j = 0; j < RY; ++j)
+#pragma unroll
+            for (int c = 0; c < CC; ++c) acc[j][c] = fmaf(dv[j + 2 * ph - ky], wv[ky * CC + c], acc[j][c]);
+      }
+    }
+    // mirror fold: reflected padded rows / columns of edge pixels (at most 2 rows x 2 columns of the image border)
+    if (live && (nx > 0 || edge_rows)) {
+#pragma unroll
+      for (int j = 0; j < RY; ++j) {
+        const int Y = Yb + j;
+        int ys[2], ny = 0;
+        if (Y < ph) ys[ny++] = ph - 1 - Y;
+        if (Y >= H - ph && Y < H) ys[ny++] = 2 * H - 1 - Y + ph;
+        // all (row, column) combinations except (self, self): index 0 = the padded position itself
+        for (int iyp = 0; iyp <= ny; ++iyp)
+          for (int ixp = 0; ixp <= nx; ++ixp) {
+            if (iyp == 0 && ixp == 0) continue;
+            const int Yp = iyp == 0 ? Y + ph : ys[iyp - 1];
+            const int Xp = ixp == 0 ? X + pw : xs[ixp - 1];
+            for (int ky = 0; ky < KS; ++ky) {
+              const int ry = Yp - ky - (y0 - ph);
+              if (ry < 0 || ry >= hh) continue;            // outside the halo == outside the image for these positions
+              for (int kx = 0; kx < KS; ++kx) {
+                const int rx = Xp - kx - (x0 - pw);
+                if (rx < 0 || rx >= hw) continue;
+#pragma unroll
+                for (int o = 0; o < NO; ++o) {
+                  const float d = s_d[o][ry][rx];
+                  const float4 w0 = *reinterpret_cast<const float4*>(&s_w[kx][o][ky][0]);
+                  const float4 w1 = *reinterpret_cast<const float4*>(&s_w[kx][o][ky][4]);
+                  acc[j][0] = fmaf(d, w0.x, acc[j][0]); acc[j][1] = fmaf(d, w0.y, acc[j][1]);
+                  acc[j][2] = fmaf(d, w0.z, acc[j][2]); acc[j][3] = fmaf(d, w0.w, acc[j][3]);
+                  acc[j][4] = fmaf(d, w1.x, acc[j][4]); acc[j][5] = fmaf(d, w1.y, acc[j][5]);
+                  acc[j][6] = fmaf(d, w1.z, acc[j][6]); acc[j][7] = fmaf(d, w1.w, acc[j][7]);
+                }
+              }
+            }
+          }
+      }
+    }
+    if (live) {
+      if (r == 8 && !order_b1) {
+        // rows Yb .. Yb+7 are the 8 sub-pixel rows q of source pixel (Yb/8, X/8): dX[.., g*64 + (X%8)*8 + q], 32 contiguous bytes
+        float* dst = dXn + ((long long)(Yb >> 3) * b + (X >> 3)) * Ctot + (X & 7) * 8;
+#pragma unroll
+        for (int c = 0; c < CC; ++c)
+          if (c0 + c < G) {
+            float4* d4 = reinterpret_cast<float4*>(dst + (long long)(c0 + c) * 64);
+            d4[0] = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+            d4[1] = make_float4(acc[4][c], acc[5][c], acc[6][c], acc[7][c]);
+          }
+      } else {
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          const int Y = Yb + j;
+          if (Y < H) {
+            const int iy = Y / r, qy = Y - iy * r, ix = X / r, qx = X - ix * r;
+            const int sub = order_b1 ? (qy * r + qx) : (qx * r + qy);
+            float* dst = dXn + ((long long)iy * b + ix) * Ctot + sub;
+#pragma unroll
+            for (int c = 0; c < CC; ++c)
+              if (c0 + c < G) dst[(long long)(c0 + c) * rr] = acc[j][c];
+          }
+        }
+      }
+    }
+  }
+}
+
+// PNP_TAIL5: bit 0 = register-tiled 5x5 forward tail, bit 1 = register-tiled 5x5 backward tail; 0 = the generic (any odd k <= 5)
+// kernels also for 5x5.  Default 1, as measured (r2y, B = 16): forward 436 -> 266 us per call (config 1: 4.44 -> 4.25 ms per step);
+// the backward variant is parity-clean but neutral on the config-2 step (20.20 vs 20.22 ms), so the generic one stays.
+int tail5_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PNP_TAIL5"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
 bool geom_ok(const pnp_conv_geom* g) {
   return g && g->B > 0 && g->H > 0 && g->W > 0 && g->Cin > 0 && g->Ho > 0 && g->Wo > 0 && g->Cout > 0 && g->kh > 0 &&
          g->kw > 0 && g->stride > 0 && g->dil > 0 && g->pad_t >= 0 && g->pad_l >= 0;
@@ -867,6 +1149,12 @@ extern "C" int pnp_ps_mirror_conv_fwd(const float* X, const float* w, float* y, 
   if (kh > 5 || kw > 5 || kh < 1 || kw < 1 || (kh & 1) == 0 || (kw & 1) == 0 || B > 65535) return PNP_ERR_UNSUPPORTED;
   if (kh / 2 > a * r || kw / 2 > b * r) return PNP_ERR_UNSUPPORTED;
   dim3 grid(pnp_cdiv(b * r, 32), pnp_cdiv(a * r, 32), B);
+  if (kh == 5 && kw == 5 && (Cout == 5 || Cout == 8) && (tail5_mode() & 1)) {      // the graphs' 5x5 output convolution: register-tiled kernel
+    if (Cout == 5) pnp_launch(ps_mirror_conv5_kernel<5>, grid, 128, 0, (cudaStream_t)stream, X, w, y, B, a, b, G, r, order_b1);
+    else pnp_launch(ps_mirror_conv5_kernel<8>, grid, 128, 0, (cudaStream_t)stream, X, w, y, B, a, b, G, r, order_b1);
+    PNP_LAUNCH_CHECK();
+    return PNP_OK;
+  }
   if (Cout == 5) pnp_launch(ps_mirror_conv_kernel<5>, grid, 256, 0, (cudaStream_t)stream, X, w, y, B, a, b, G, r, kh, kw, order_b1);
   else if (Cout == 8) pnp_launch(ps_mirror_conv_kernel<8>, grid, 256, 0, (cudaStream_t)stream, X, w, y, B, a, b, G, r, kh, kw, order_b1);
   else return PNP_ERR_UNSUPPORTED;
@@ -880,6 +1168,12 @@ extern "C" int pnp_ps_mirror_conv_bwd(const float* dy, const float* w, float* dX
   if (kh > 5 || kw > 5 || kh < 1 || kw < 1 || (kh & 1) == 0 || (kw & 1) == 0 || B > 65535) return PNP_ERR_UNSUPPORTED;
   if (kh / 2 > a * r || kw / 2 > b * r) return PNP_ERR_UNSUPPORTED;
   dim3 grid(pnp_cdiv(b * r, 32), pnp_cdiv(a * r, 32), B);
+  if (kh == 5 && kw == 5 && (Cout == 5 || Cout == 8) && (tail5_mode() & 2)) {
+    if (Cout == 5) pnp_launch(ps_mirror_conv5_bwd_kernel<5>, grid, 128, 0, (cudaStream_t)stream, dy, w, dX, B, a, b, G, r, order_b1);
+    else pnp_launch(ps_mirror_conv5_bwd_kernel<8>, grid, 128, 0, (cudaStream_t)stream, dy, w, dX, B, a, b, G, r, order_b1);
+    PNP_LAUNCH_CHECK();
+    return PNP_OK;
+  }
   if (Cout == 5) pnp_launch(ps_mirror_conv_bwd_kernel<5>, grid, 256, 0, (cudaStream_t)stream, dy, w, dX, B, a, b, G, r, kh, kw, order_b1);
   else if (Cout == 8) pnp_launch(ps_mirror_conv_bwd_kernel<8>, grid, 256, 0, (cudaStream_t)stream, dy, w, dX, B, a, b, G, r, kh, kw, order_b1);
   else return PNP_ERR_UNSUPPORTED;
