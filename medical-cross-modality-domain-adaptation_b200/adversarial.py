@@ -327,6 +327,7 @@ class Trainer(object):
         self.lr_update_flag = self.train_config.get("lr_update", False)
         self.mr_source, self.ct_source = mr_source, ct_source
         self.mr_train_list, self.ct_train_list = mr_train_list, ct_train_list
+        self.test_label_list, self.test_nii_list = test_label_list, test_nii_list
         self.dp = parallel.DataParallel()
         self.global_step = 0
         self.dis_sub_iter = self.train_config.get("dis_sub_iter", 1)
@@ -486,40 +487,55 @@ class Trainer(object):
                 f.write(json.dumps(dict(step=int(step), **scalars)) + "\n")
         return scalars
 
-    def test_eval_volume(self, raw, raw_y, flip_correction=True, shuffle_seed=None):
-        """adversarial.py:993-1052 for ONE subject without the NIfTI reader: `raw` [256,256,D] intensity volume, `raw_y` [256,256,D]
-        integer labels (what read_nii_image returns).  Like the reference: optional flip of both in-plane axes, frames 1..D-2 (each
-        fed with its two neighbours as channels) in shuffled order, floor(D / batch) full batches -- the remaining frames are
-        dropped as the reference drops them --, inference-mode forward (keep_prob 1, BN switches off), confusion matrix summed
-        over the subject.  Returns (per-class Dice, per-class Jaccard, confusion matrix, predicted label volume)."""
-        from .lib import _dice, _jaccard, _label_decomp
-        raw = np.asarray(raw, np.float32)
-        raw_y = np.asarray(raw_y)
-        if flip_correction:
-            raw, raw_y = np.flip(np.flip(raw, 0), 1), np.flip(np.flip(raw_y, 0), 1)
-        B, nc = self.net.batch_size, self.num_cls or self.net.n_class
-        frames = list(range(1, raw.shape[2] - 1))
-        (np.random if shuffle_seed is None else np.random.RandomState(shuffle_seed)).shuffle(frames)
+    def _predict_ct(self, vol, sl):
+        """one forward call of the test protocol: inference-mode adapted CT stream (keep_prob 1, every BN switch off -- the feed of
+        adversarial.py:1036-1038) -> (argmax labels, confusion counts [label, prediction]) on the host"""
+        from .lib import _label_decomp
+        nc = self.num_cls or self.net.n_class
         dev = rt.device()
-        cm = torch.zeros(nc, nc, dtype=torch.int64, device=dev)
-        pred_vol = np.zeros(raw_y.shape, np.int64)
-        for ii in range(raw.shape[2] // B):
-            idx = frames[ii * B:(ii + 1) * B]
-            vol = np.zeros((B,) + raw.shape[:2] + (3,), np.float32)
-            sl = np.zeros((B,) + raw.shape[:2], np.int64)
-            for k, jj in enumerate(idx):
-                vol[k] = raw[..., jj - 1:jj + 2]
-                sl[k] = raw_y[..., jj]
-            x = torch.from_numpy(vol).to(dev)
-            y = _label_decomp(nc, torch.from_numpy(sl).to(dev))
-            with torch.no_grad():
-                logits = self.net.segment(x, "ct", 1.0, front_bn=False, joint_bn=False)["logits"]
-                cm += F.confusion_counts(logits, y)
-                pred = logits.argmax(3).cpu().numpy()
-            for k, jj in enumerate(idx):
-                pred_vol[..., jj] = pred[k]
-        cmh = cm.cpu().numpy()
-        return _dice(cmh), _jaccard(cmh), cmh, pred_vol
+        x = torch.from_numpy(np.ascontiguousarray(vol, np.float32)).to(dev)
+        y = _label_decomp(nc, torch.from_numpy(np.ascontiguousarray(sl, np.int64)).to(dev))
+        with torch.no_grad():
+            logits = self.net.segment(x, "ct", 1.0, front_bn=False, joint_bn=False)["logits"]
+            cm = F.confusion_counts(logits, y)
+            pred = logits.argmax(3)
+        return pred.cpu().numpy(), cm.cpu().numpy()
+
+    def test_eval_volume(self, raw, raw_y, flip_correction=True, shuffle_seed=None):
+        """adversarial.py:993-1052 for ONE subject: `raw` [256,256,D] intensity volume, `raw_y` [256,256,D] integer labels (what
+        read_nii_image returns).  Like the reference: optional flip of both in-plane axes, frames 1..D-2 (each fed with its two
+        neighbours as channels) in shuffled order, floor(D / batch) full batches -- the remaining frames are dropped as the
+        reference drops them --, inference-mode forward (keep_prob 1, BN switches off), confusion matrix summed over the subject.
+        Returns (per-class Dice, per-class Jaccard, confusion matrix, predicted label volume)."""
+        from . import evaluation
+        rng = None if shuffle_seed is None else np.random.RandomState(shuffle_seed)
+        dice, jac, cm, pred_vol = evaluation.eval_volume(self._predict_ct, raw, raw_y, self.net.batch_size,
+                                                         self.num_cls or self.net.n_class, flip_correction, True, rng)
+        return dice, jac, cm.astype(np.int64), pred_vol
+
+    def test_eval(self, output_path, flip_correction=True, save_result=False):
+        """adversarial.py:993-1052: every (label, image) .nii pair of `test_label_list` / `test_nii_list` through the per-subject
+        protocol above; writes the summed confusion matrix to <output_path>/cm.csv and returns sample_metric_stddev's pair.
+        `save_result` (the segmenter trainer's switch, source_segmenter.py:625-626) also writes the predictions as .nii.gz."""
+        from . import evaluation
+        sample_eval_list, _ = evaluation.run_test_eval(
+            self._predict_ct, self.test_label_list, self.test_nii_list, self.net.batch_size, self.num_cls or self.net.n_class,
+            output_path, "dense_pred", flip_correction, save_result, shuffle=True, write_cm=True)
+        self.sample_eval_list = sample_eval_list
+        return self.sample_metric_stddev(sample_eval_list)
+
+    def sample_metric_stddev(self, sample_eval_list):
+        """adversarial.py:1054-1084"""
+        from . import evaluation
+        return evaluation.sample_metric_stddev(sample_eval_list, self.num_cls or self.net.n_class)
+
+    def test_model(self, this_model, output_path):
+        """adversarial.py:1097-1108: restore a checkpoint, run the test protocol"""
+        self.net.restore(this_model)
+        logging.info("model has been loaded!")
+        dice, jac = self.test_eval(output_path)
+        logging.info("testing finished")
+        return dice, jac
 
     # ---- steps as CUDA graphs -----------------------------------------------------------------------------------------
     def _capture(self, fn, warmup):

@@ -146,6 +146,7 @@ class Trainer(object):
         self.opt_kwargs = dict(opt_kwargs)
         self.lr_update_flag = lr_update_flag
         self.train_list, self.val_list = train_list, val_list
+        self.test_nii_list, self.test_label_list = test_nii_list, test_label_list
         if optimizer not in ("adam", "momentum"):
             raise ValueError("optimizer must be 'adam' or 'momentum' (source_segmenter.py:359-381)")
         self.optimizer_name = optimizer
@@ -312,3 +313,46 @@ class Trainer(object):
             wce, dice = self.net.losses(logits, batch_y)
             d, arr = self.net.dice_eval(logits, batch_y)
         return {"loss": self.net.cost_value(wce, dice), "dice_eval": float(d), "dice_arr": [float(a) for a in arr]}
+
+    # ---- test protocol on NIfTI subjects (source_segmenter.py:572-675) -----------------------------------------------
+    def _predict(self, vol, sl):
+        """one forward call of the test protocol: keep_prob 1, main_bn / adapt_bn off (the feed of source_segmenter.py:615-617)
+        -> (argmax labels, confusion counts [label, prediction]) on the host"""
+        dev = rt.device()
+        x = torch.from_numpy(np.ascontiguousarray(vol, np.float32)).to(dev)
+        y = _label_decomp(self.num_cls, torch.from_numpy(np.ascontiguousarray(sl, np.int64)).to(dev))
+        with torch.no_grad():
+            logits = self.net.forward(x, keep_prob=1.0, main_bn=False, adapt_bn=False)
+            cm = self.net.confusion_matrix(logits, y)
+            pred = logits.argmax(3)
+        return pred.cpu().numpy(), cm.cpu().numpy()
+
+    def test_eval_volume(self, raw, raw_y, flip_correction=True):
+        """one subject of test_eval: frames in order (see evaluation.subject_batches for the reference's broken loop header)"""
+        from . import evaluation
+        dice, jac, cm, pred_vol = evaluation.eval_volume(self._predict, raw, raw_y, self.net.batch_size, self.num_cls,
+                                                         flip_correction, False)
+        return dice, jac, cm.astype(np.int64), pred_vol
+
+    def test_eval(self, output_path, flip_correction=True, save_result=False):
+        """source_segmenter.py:572-632: inference on the (label, image) .nii pairs of test_label_list / test_nii_list; with
+        `save_result` the dense predictions and ground truths go to <output_path>/test_pred as .nii.gz"""
+        from . import evaluation
+        sample_eval_list, _ = evaluation.run_test_eval(self._predict, self.test_label_list, self.test_nii_list, self.net.batch_size,
+                                                       self.num_cls, output_path, "test_pred", flip_correction, save_result,
+                                                       shuffle=False, write_cm=False)
+        self.sample_eval_list = sample_eval_list
+        return self.sample_metric_stddev(sample_eval_list)
+
+    def sample_metric_stddev(self, sample_eval_list):
+        """source_segmenter.py:634-664"""
+        from . import evaluation
+        return evaluation.sample_metric_stddev(sample_eval_list, self.num_cls)
+
+    def test_choose_model(self, this_model, output_path):
+        """source_segmenter.py:666-675: restore a checkpoint, run the test protocol"""
+        self.net.restore(this_model)
+        logging.info("model has been loaded!")
+        dice, jac = self.test_eval(output_path)
+        logging.info("testing finished")
+        return dice, jac

@@ -194,3 +194,80 @@ def test_per_volume_evaluation_matches_oracle():
     assert cm.sum() == cm_ref.sum() == (D // B) * B * 256 * 256
     assert np.abs(cm - cm_ref).sum() <= 2e-3 * cm.sum()
     assert np.abs(dice - _dice(cm_ref)).max() <= 1e-3 and np.abs(jac - _jaccard(cm_ref)).max() <= 1e-3
+
+
+def test_test_eval_on_nifti_subjects_both_trainers(tmp_path):
+    """`Trainer.test_eval` of both trainers (adversarial.py:993-1052, source_segmenter.py:572-632) end to end: NIfTI subjects on disk
+    -> lib.read_nii_image -> flip -> frame batches -> inference-mode forward on the GPU -> confusion matrix / Dice / Jaccard ->
+    cm.csv, dense predictions as .nii.gz.  With every frame fed (D - 2 <= floor(D / B) * B) the subject's confusion matrix does not
+    depend on the shuffle, so it must equal `test_eval_volume` of the same arrays; the host protocol itself is pinned to the
+    executed reference on CPU (tests/test_nifti_eval_cpu.py)."""
+    import pnp_b200  # noqa: F401
+    from pnp_b200 import runtime as rt, adversarial as adv, source_segmenter as seg
+    from pnp_b200.data import label_maps
+    from pnp_b200.lib import write_nii, read_nii_image, _dice, _jaccard
+    from pnp_b200.train_gan import configure
+    from oracle.pnp_graphs import OracleAdversarial, OracleSegmenter, init_numpy_params
+    rt.set_conv_backend("auto")
+    depths = [5, 6]
+    rng = np.random.RandomState(21)
+    nii, lab, vols = [], [], []
+    for i, D in enumerate(depths):
+        raw = rng.randn(256, 256, D).astype(np.float32)
+        raw_y = np.transpose(label_maps(D, 70 + i), (1, 2, 0)).astype(np.int16)
+        nii.append(write_nii(raw, "ct_%d_image.nii.gz" % i, str(tmp_path)))
+        lab.append(write_nii(raw_y, "ct_%d_label.nii.gz" % i, str(tmp_path)))
+        vols.append((raw, raw_y))
+    # ---- adversarial trainer: the adapted CT stream -----------------------------------------------------------------
+    ws, bns = OracleAdversarial.layout()
+    P = init_numpy_params(ws, bns, 0, 0.05)
+    _bn_noise(P, bns, 6)
+    ck, nc, tc = configure("train-gan")
+    net = adv.Full_DRN(channels=3, n_class=5, batch_size=B, cost_kwargs=ck, network_config=nc)
+    rt.load_state_dict(P)
+    trainer = adv.Trainer(net, num_cls=5, batch_size=B, opt_kwargs={"learning_rate": 3e-4}, train_config=tc, test_label_list=lab,
+                          test_nii_list=nii)
+    out = str(tmp_path / "adv_out")
+    os.makedirs(out)
+    np.random.seed(3)
+    dice_list, jac_quirk = trainer.test_eval(out, flip_correction=True, save_result=True)
+    per_subject = [trainer.test_eval_volume(r, y, flip_correction=True, shuffle_seed=17) for r, y in vols]
+    cm_sum = sum(s[2] for s in per_subject)
+    cm_csv = np.loadtxt(os.path.join(out, "cm.csv"))
+    assert cm_csv.sum() == cm_sum.sum() == sum((D // B) * B for D in depths) * 256 * 256
+    assert np.abs(cm_csv - cm_sum).sum() <= 1e-4 * cm_sum.sum()
+    np.testing.assert_allclose(dice_list, np.mean([s[0] for s in per_subject], 0), atol=1e-3)
+    assert np.asarray(jac_quirk).shape == (1, 2)
+    for (d, j), s in zip(trainer.sample_eval_list, per_subject):
+        np.testing.assert_allclose(d, s[0], atol=1e-3)
+        np.testing.assert_allclose(j, s[1], atol=1e-3)
+    for i, D in enumerate(depths):
+        p = read_nii_image(os.path.join(out, "dense_pred", "dense_pred_ct_%d_image.nii.gz" % i))
+        assert p.shape == (256, 256, D) and p.min() >= 0 and p.max() <= 4 and not p[..., 0].any() and not p[..., D - 1].any()
+        agree = (p[..., 1:D - 1] == per_subject[i][3][..., 1:D - 1]).mean()
+        print("  subject %d: saved prediction agrees with test_eval_volume on %.5f of the voxels" % (i, agree))
+        assert agree >= 1 - 1e-4
+    # ---- segmenter trainer: frames in order --------------------------------------------------------------------------
+    ws, bns = OracleSegmenter.layout()
+    Ps = init_numpy_params(ws, bns, 0, 0.05)
+    _bn_noise(Ps, bns, 6)
+    snet = seg.Full_DRN(channels=3, n_class=5, batch_size=B,
+                        cost_kwargs={"cross_flag": True, "miu_cross": 1.0, "dice_flag": True, "miu_dice": 1.0})
+    rt.load_state_dict(Ps)
+    st = seg.Trainer(snet, None, None, num_cls=5, batch_size=B, test_nii_list=nii, test_label_list=lab, optimizer="adam",
+                     opt_kwargs={"learning_rate": 1e-3})
+    out2 = str(tmp_path / "seg_out")
+    os.makedirs(out2)
+    dice2, _ = st.test_eval(out2, flip_correction=False, save_result=True)
+    ref = [st.test_eval_volume(r, y, flip_correction=False) for r, y in vols]
+    np.testing.assert_allclose(dice2, np.mean([s[0] for s in ref], 0), atol=1e-12)
+    oracle = OracleSegmenter(Ps, B)
+    r0, y0 = vols[0]
+    vol = np.stack([r0[..., 0:3], r0[..., 1:4]])                                  # frames 1 and 2: the first batch of subject 0
+    with torch.no_grad():
+        p_ref = oracle.forward(torch.from_numpy(vol), 1.0, False)["logits"].argmax(3).numpy()
+    p = read_nii_image(os.path.join(out2, "test_pred", "dense_pred_ct_0_image.nii.gz"))
+    agree = np.mean([(p[..., 1] == p_ref[0]).mean(), (p[..., 2] == p_ref[1]).mean()])
+    print("  segmenter test_eval: saved prediction agrees with the oracle's argmax on %.5f of the voxels" % agree)
+    assert agree >= 1 - 2e-3
+    assert np.abs(ref[0][0] - _dice(ref[0][2])).max() == 0 and np.abs(ref[0][1] - _jaccard(ref[0][2])).max() == 0
