@@ -482,7 +482,14 @@ class Trainer(object):
         if detail:
             _indicator_eval(cm.cpu().numpy())
         if log_dir is not None and self.dp.rank == 0:
-            os.makedirs(log_dir, exist_ok=True)
+            # summary_writer.add_summary(summary_str, step); flush() (adversarial.py:989-991): a TensorBoard event file (scalars only)
+            # and the same numbers as one JSON line
+            from .summary import FileWriter
+            writers = self.__dict__.setdefault("_summary_writers", {})
+            if log_dir not in writers:
+                writers[log_dir] = FileWriter(log_dir)
+            writers[log_dir].add_scalars(scalars, step)
+            writers[log_dir].flush()
             with open(os.path.join(log_dir, "scalars.jsonl"), "a") as f:
                 f.write(json.dumps(dict(step=int(step), **scalars)) + "\n")
         return scalars
@@ -726,10 +733,11 @@ class Trainer(object):
                     logging.info("Training step %s epoch %s finished, %.3f s" % (step, epoch, time.time() - start))
                     # the monitoring passes of adversarial.py:894-922: a training batch, then a "validation" batch with the
                     # per-organ table (the synthetic / list sources stand in for the separate validation queues)
+                    tag = str(self.train_config.get("tag", ""))      # FileWriter(output_path + "/train_log" + tag) (adversarial.py:807-808)
                     for sub, detail in (("train_log", False), ("val_log", True)):
                         (ct, cty), (mr, mry) = ct_src.next(), mr_src.next()
                         self.output_minibatch_stats(step, to_device(ct, dev), to_device(cty, dev), to_device(mr, dev), to_device(mry, dev),
-                                                    os.path.join(output_path, sub), detail)
+                                                    os.path.join(output_path, sub + tag), detail)
                 if step % ckpt_space == 0 and step != 0:
                     self.save(save_path, output_path)
                     # "Model has been restored for re-allocation" (adversarial.py:929-935): the reference re-reads the checkpoint it

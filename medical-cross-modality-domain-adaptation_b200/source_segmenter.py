@@ -138,7 +138,8 @@ class Trainer(object):
     synthetic source unless `source` is given (anything with .next() -> (images, int labels))."""
 
     def __init__(self, net, train_list, val_list, num_cls, batch_size, test_nii_list=None, test_label_list=None,
-                 optimizer="momentum", opt_kwargs={}, num_epochs=100, checkpoint_space=500, lr_update_flag=False, source=None):
+                 optimizer="momentum", opt_kwargs={}, num_epochs=100, checkpoint_space=500, lr_update_flag=False, source=None,
+                 val_source=None):
         self.net = net
         self.batch_size = batch_size
         self.num_cls = num_cls
@@ -150,7 +151,7 @@ class Trainer(object):
         if optimizer not in ("adam", "momentum"):
             raise ValueError("optimizer must be 'adam' or 'momentum' (source_segmenter.py:359-381)")
         self.optimizer_name = optimizer
-        self.source = source
+        self.source, self.val_source = source, val_source
         self.global_step = 0
         self.dp = parallel.DataParallel()
         self._build_optimizer()
@@ -227,13 +228,41 @@ class Trainer(object):
         self.arena.bump_versions()
         return self._graph_out
 
-    def output_minibatch_stats(self, batch_x, batch_y):
+    # scalar tags of the merged summary op, in its order (source_segmenter.py:387-396)
+    SCALAR_TAGS = ("loss", "regularizer_loss", "weighted_loss", "dice_loss", "dice_eval", "dice_eval_c1", "dice_eval_c2", "dice_eval_c3",
+                   "dice_eval_c4")
+
+    def _scalars(self, logits, batch_y, wce, dice):
+        d, arr = self.net.dice_eval(logits, batch_y)
+        vals = [self.net.cost_value(wce, dice), self.net.regularizer_loss(), float(wce), float(dice), float(d)] + \
+               [float(arr[i]) for i in range(1, 5)]
+        return dict(zip(self.SCALAR_TAGS, vals))
+
+    def _write_scalars(self, log_dir, step, scalars):
+        """tf.summary.FileWriter(output_path + '/train_log' | '/val_log').add_summary(scalar_summary_op, step) (source_segmenter.py:
+        464-465, 537-539, 567-569): a TensorBoard event file plus the same numbers as one JSON line; rank 0 only"""
+        if log_dir is None or self.dp.rank != 0:
+            return
+        import json
+        from .summary import FileWriter
+        writers = self.__dict__.setdefault("_summary_writers", {})
+        if log_dir not in writers:
+            writers[log_dir] = FileWriter(log_dir)
+        writers[log_dir].add_scalars(scalars, step)
+        writers[log_dir].flush()
+        with open(os.path.join(log_dir, "scalars.jsonl"), "a") as f:
+            f.write(json.dumps(dict(step=int(step), **scalars)) + "\n")
+
+    def output_minibatch_stats(self, batch_x, batch_y, step=None, log_dir=None):
         """source_segmenter.py:525-539: the tensorboard pass on the training batch feeds x, y and keep_prob 1 ONLY -- both BN
         switches stay at their placeholder default True, so this forward runs batch-statistics BN and (updates_collections=None)
-        moves the moving averages once more.  Reproduced because it changes the trained model's moving statistics."""
+        moves the moving averages once more.  Reproduced because it changes the trained model's moving statistics.  With `log_dir`
+        the nine scalar summaries of the reference go to an event file there."""
         with torch.no_grad():
             logits = self.net.forward(batch_x, keep_prob=1.0, main_bn=True, adapt_bn=True)
             wce, dice = self.net.losses(logits, batch_y)
+            if log_dir is not None:
+                self._write_scalars(log_dir, step, self._scalars(logits, batch_y, wce, dice))
         return self.net.cost_value(wce, dice)
 
     def feed(self, images, raw_labels):
@@ -244,7 +273,8 @@ class Trainer(object):
         return x, y
 
     def train(self, output_path, restored_path=None, restore=False, training_iters=100, epochs=100, display_step=5, dropout=0.75):
-        """source_segmenter.py:429-525 without queues/summaries: Adam steps, periodic stats, checkpoint + LR*0.9."""
+        """source_segmenter.py:429-525: optimizer steps, the two monitoring passes every `display_step` (training batch with batch-statistics
+        BN, then a validation batch in inference mode) with their scalar summaries, checkpoint + LR*0.9."""
         save_path = os.path.join(output_path, "model.cpkt")
         if epochs == 0:
             return save_path
@@ -276,6 +306,14 @@ class Trainer(object):
             src = TFRecordSource(self.train_list, self.batch_size, seed=1234 + self.dp.rank)
         else:
             src = SyntheticSource(self.batch_size, seed=1234 + self.dp.rank, num_cls=self.num_cls)
+        # the validation queue of source_segmenter.py:325,467 (val_list), else a second synthetic stream
+        if self.val_source is not None:
+            val_src = self.val_source
+        elif self.val_list:
+            from .tfrecord import TFRecordSource
+            val_src = TFRecordSource(self.val_list, self.batch_size, seed=4321 + self.dp.rank)
+        else:
+            val_src = SyntheticSource(self.batch_size, seed=4321 + self.dp.rank, num_cls=self.num_cls)
         for epoch in range(epochs):
             for step in range(epoch * training_iters, (epoch + 1) * training_iters):
                 start = time.time()
@@ -283,9 +321,12 @@ class Trainer(object):
                 x, y = self.feed(images, raw_y)
                 wce, dice = self.train_step(x, y, dropout)
                 if step % display_step == 0:
-                    loss = self.output_minibatch_stats(x, y)
+                    loss = self.output_minibatch_stats(x, y, step, os.path.join(output_path, "train_log"))
                     logging.info("Training at step %s epoch %s , loss is %0.4f" % (step, epoch, loss))
                     logging.info("Time elapsed %s seconds" % (time.time() - start))
+                    # source_segmenter.py:498-505: a validation batch right after it, always with the per-organ table
+                    vx, vy = self.feed(*val_src.next())
+                    self.val_stats(vx, vy, step, os.path.join(output_path, "val_log"), detail=True)
                 if step % self.checkpoint_space == 0 and step > 10000:
                     self.save(save_path, output_path)
                     self.optimizer.set_lr(self.optimizer.get_lr() * 0.9)
@@ -306,12 +347,18 @@ class Trainer(object):
             _save(st, os.path.join(output_path, "latest"))
         self.dp.save_checkpoint(write)
 
-    def val_stats(self, batch_x, batch_y):
-        """source_segmenter.py:541-570: inference-mode forward (BN moving stats, keep_prob 1)"""
+    def val_stats(self, batch_x, batch_y, step=None, log_dir=None, detail=False):
+        """source_segmenter.py:541-570: inference-mode forward (BN moving stats, keep_prob 1) on a validation batch; `detail` prints
+        the per-organ Dice / Jaccard table of the batch's confusion matrix; with `log_dir` the scalar summaries go to an event file"""
+        from .lib import _indicator_eval
         with torch.no_grad():
             logits = self.net.forward(batch_x, keep_prob=1.0, main_bn=False, adapt_bn=False)
             wce, dice = self.net.losses(logits, batch_y)
             d, arr = self.net.dice_eval(logits, batch_y)
+            if detail:
+                _indicator_eval(self.net.confusion_matrix(logits, batch_y).cpu().numpy())
+            if log_dir is not None:
+                self._write_scalars(log_dir, step, self._scalars(logits, batch_y, wce, dice))
         return {"loss": self.net.cost_value(wce, dice), "dice_eval": float(d), "dice_arr": [float(a) for a in arr]}
 
     # ---- test protocol on NIfTI subjects (source_segmenter.py:572-675) -----------------------------------------------

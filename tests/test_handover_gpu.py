@@ -271,3 +271,62 @@ def test_test_eval_on_nifti_subjects_both_trainers(tmp_path):
     print("  segmenter test_eval: saved prediction agrees with the oracle's argmax on %.5f of the voxels" % agree)
     assert agree >= 1 - 2e-3
     assert np.abs(ref[0][0] - _dice(ref[0][2])).max() == 0 and np.abs(ref[0][1] - _jaccard(ref[0][2])).max() == 0
+
+
+def _read_events(log_dir):
+    from tensorboard.backend.event_processing.event_file_loader import RawEventFileLoader
+    from tensorboard.compat.proto import event_pb2
+    (fn,) = [f for f in os.listdir(log_dir) if f.startswith("events.out.tfevents.")]
+    evs = [event_pb2.Event.FromString(raw) for raw in RawEventFileLoader(os.path.join(log_dir, fn)).Load()]
+    assert evs[0].file_version == "brain.Event:2"
+    return [(ev.step, [(v.tag, v.simple_value) for v in ev.summary.value]) for ev in evs[1:]]
+
+
+def test_training_loops_run_end_to_end_on_the_device(tmp_path):
+    """`Trainer.train` of both trainers on the GPU for a few iterations, the way the entry scripts call them (source_segmenter.py:429-523,
+    adversarial.py:767-946): optimizer steps, the monitoring passes with their TensorBoard scalar summaries (event files read back with
+    the `tensorboard` package), and for the GAN loop the checkpoint -> re-read -> LR x 0.98 sequence."""
+    pytest.importorskip("tensorboard")
+    import pnp_b200  # noqa: F401
+    from pnp_b200 import runtime as rt, adversarial as adv, source_segmenter as seg
+    from pnp_b200.train_gan import configure
+    rt.set_conv_backend("auto")
+    # ---- source segmenter: 6 Adam steps, monitoring at steps 0 and 5 -------------------------------------------------
+    torch.manual_seed(0)
+    net = seg.Full_DRN(channels=3, n_class=5, batch_size=B,
+                       cost_kwargs={"cross_flag": True, "miu_cross": 1.0, "dice_flag": True, "miu_dice": 1.0, "regularizer": 1e-4})
+    tr = seg.Trainer(net, [], [], num_cls=5, batch_size=B, optimizer="adam", opt_kwargs={"learning_rate": 1e-3})
+    out = str(tmp_path / "seg")
+    tr.train(out, training_iters=6, epochs=1, display_step=5, dropout=0.75)
+    assert tr.global_step == 6
+    for sub in ("train_log", "val_log"):
+        evs = _read_events(os.path.join(out, sub))
+        assert [s for s, _ in evs] == [0, 5]
+        for _, vals in evs:
+            d = dict(vals)
+            assert tuple(t for t, _ in vals) == seg.Trainer.SCALAR_TAGS and all(np.isfinite(v) for v in d.values())
+            assert abs(d["loss"] - (d["weighted_loss"] + d["dice_loss"])) <= 1e-5 * max(1.0, abs(d["loss"]))
+            assert 0.0 <= d["dice_eval"] <= 1.0 and d["regularizer_loss"] > 0
+        lines = [json.loads(ln) for ln in open(os.path.join(out, sub, "scalars.jsonl"))]
+        assert [ln["step"] for ln in lines] == [0, 5] and abs(lines[1]["loss"] - dict(evs[1][1])["loss"]) <= 1e-6 * max(1.0, abs(lines[1]["loss"]))
+    # ---- GAN loop: steps 0..4, D and G updates at 1..4, monitoring at 0/2/4, checkpoint + re-read + LR decay at step 3 -----------
+    ck, nc, tc = configure("train-gan")
+    tc.update(dis_sub_iter=1, gen_sub_iter=1, checkpoint_space=3, iter_upd_interval=2, dis_sub_iter_inc=1)
+    anet = adv.Full_DRN(channels=3, n_class=5, batch_size=B, cost_kwargs=ck, network_config=nc)
+    atr = adv.Trainer(anet, num_cls=5, batch_size=B, opt_kwargs={"learning_rate": 3e-4}, train_config=tc)
+    out = str(tmp_path / "gan")
+    atr.train(out, restore=False, training_iters=5, epochs=1, dropout=0.75, display_step=2)
+    # D updates: steps 1, 2 x1, steps 3, 4 x2 (the sub-iteration count grows AFTER the updates of steps 2 and 4) = 6; G updates: 4
+    assert atr.global_step == 10 and atr.dis_sub_iter == 3
+    assert os.path.exists(os.path.join(out, "latest.npz")) and any(f.startswith("model.cpkt-") for f in os.listdir(out))
+    assert atr.dis_optimizer.get_lr() == pytest.approx(3e-4 * 0.98) and atr.gen_optimizer.get_lr() == pytest.approx(3e-4 * 0.98)
+    for sub in ("train_log", "val_log"):
+        evs = _read_events(os.path.join(out, sub + tc["tag"]))
+        assert [s for s, _ in evs] == [0, 2, 4]
+        for _, vals in evs:
+            assert tuple(t for t, _ in vals) == adv.Trainer.SCALAR_TAGS and all(np.isfinite(v) for _, v in vals)
+        assert dict(evs[0][1])["learning_rate"] == pytest.approx(3e-4) and dict(evs[2][1])["learning_rate"] == pytest.approx(3e-4 * 0.98)
+    ckpt = dict(np.load(os.path.join(out, "latest.npz")))
+    assert any(k.endswith("/RMSProp") for k in ckpt) and "cls_scope/cls_out/Variable" in ckpt
+    w = ckpt["cls_scope/cls_out/Variable"]
+    assert np.abs(w).max() <= 0.03 + 1e-7                                   # the clip after every D update

@@ -428,7 +428,10 @@ def test_training_schedule_and_step_feeds_match_the_reference(tmp_path):
     tr.output_minibatch_stats = lambda step, ct, cty, mr, mry, log_dir=None, detail=False: mon.append((step, os.path.basename(log_dir), detail))
     tr.train(output_path=str(tmp_path), restore=True, restored_path=str(tmp_path), **sched["train_args"])
     # the monitoring passes (adversarial.py:894-922): every display_step a training batch, then a validation batch with the table
-    assert mon and all(a[1:] == ("train_log", False) and b[1:] == ("val_log", True) and a[0] == b[0] for a, b in zip(mon[0::2], mon[1::2]))
+    # into FileWriter(output_path + "/train_log" + tag) / "/val_log" + tag (adversarial.py:807-808)
+    tag = sched["train_config"].get("tag", "")
+    assert mon and all(a[1:] == ("train_log" + tag, False) and b[1:] == ("val_log" + tag, True) and a[0] == b[0]
+                       for a, b in zip(mon[0::2], mon[1::2]))
     assert [g[0] for g in got] == ref_ops
     assert all(g[1] == 0.75 for g in got) and all(g[2] == (B, 256, 256, 3) for g in got)
     assert tr.dis_sub_iter == 4 and tr.gen_sub_iter == 1
@@ -553,14 +556,19 @@ def test_segmenter_training_schedule_feeds_and_adam_match_the_reference(tmp_path
     assert all(f == {"x": "batch", "y": "batch", "main_bn": False, "adapt_bn": False, "keep_prob": 1.0} for f in val_feeds)
 
     # ---- schedule: one Adam step per iteration, the stats pass (and validation) every display_step = 5 iterations, after it
-    ref_ops = [e["op"] for e in evs if e["op"] != "val_stats"]          # (no validation source in the product's loop)
-    assert ref_ops == ["optimizer", "minibatch_stats"] + ["optimizer"] * 5 + ["minibatch_stats", "optimizer"]
+    ref_ops = [e["op"] for e in evs]
+    assert ref_ops == ["optimizer", "minibatch_stats", "val_stats"] + ["optimizer"] * 5 + ["minibatch_stats", "val_stats", "optimizer"]
+    assert all(e["detail"] is True for e in evs if e["op"] == "val_stats")
     got = []
     tr.train_step = lambda x, y, keep_prob=0.75: got.append(("optimizer", keep_prob)) or (0.0, 0.0)
-    tr.output_minibatch_stats = lambda x, y: got.append(("minibatch_stats", None)) or 0.0
+    tr.output_minibatch_stats = lambda x, y, step=None, log_dir=None: got.append(("minibatch_stats", os.path.basename(log_dir), step)) or 0.0
+    tr.val_stats = lambda x, y, step=None, log_dir=None, detail=False: got.append(("val_stats", os.path.basename(log_dir), step, detail)) or {}
     tr.feed = lambda images, raw: (images, raw)
     tr.train(output_path=str(tmp_path), training_iters=7, epochs=1, restore=True, restored_path=str(tmp_path))
     assert [g[0] for g in got] == ref_ops and all(g[1] == 0.75 for g in got if g[0] == "optimizer")
+    # the two writers of source_segmenter.py:464-465, the step each summary is filed under, the always-on per-organ table
+    assert [g[1:] for g in got if g[0] == "minibatch_stats"] == [("train_log", 0), ("train_log", 5)]
+    assert [g[1:] for g in got if g[0] == "val_stats"] == [("val_log", 0, True), ("val_log", 5, True)]
 
     # ---- the BN switches the product's three passes use
     calls = []
