@@ -1100,11 +1100,11 @@ ps_mirror_conv5_bwd_kernel(const float* __restrict__ dy, const float* __restrict
 }
 
 // PNP_TAIL5: bit 0 = register-tiled 5x5 forward tail, bit 1 = register-tiled 5x5 backward tail; 0 = the generic (any odd k <= 5)
-// kernels also for 5x5.  Default 1, as measured (r2y, B = 16): forward 436 -> 266 us per call (config 1: 4.44 -> 4.25 ms per step);
-// the backward variant is parity-clean but neutral on the config-2 step (20.20 vs 20.22 ms), so the generic one stays.
+// kernels also for 5x5.  Default 3, as measured: forward 436 -> 266 us per B = 16 call (r2y; config 1: 4.44 -> 4.25 ms per step);
+// backward 419 -> 298 us per B = 8 call (r2z; config 4, whose G update is the step that runs it: 28.41 -> 28.29 ms).
 int tail5_mode() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("PNP_TAIL5"); v = e ? atoi(e) : 1; }
+  if (v < 0) { const char* e = getenv("PNP_TAIL5"); v = e ? atoi(e) : 3; }
   return v;
 }
 

@@ -1,7 +1,6 @@
 """Opt-in launch modes of the C-ABI library, each in its own process (the switches are read once per process):
 PNP_PDL=1 (programmatic dependent launch on every kernel), PNP_TC_PAIR=7 (CTA pairs on the 128x256, 128x128 and 128x64 tiles) and
-PNP_TAIL5=3 / 0 (register-tiled 5x5 tail kernels in both directions / the generic tail kernels; the default is tiled forward, generic
-backward) must give the same operator parity as the defaults, eagerly and through CUDA-graph replay."""
+PNP_TAIL5=3 / 0 (register-tiled 5x5 tail kernels in both directions -- the default, set explicitly here -- / the generic tail kernels) must give the same operator parity as the defaults, eagerly and through CUDA-graph replay."""
 import os
 import subprocess
 import sys
