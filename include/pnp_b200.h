@@ -195,6 +195,19 @@ int pnp_maxpool2_fwd(const float* x, float* y, int B, int H, int W, int C, void*
 int pnp_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, void* stream);
 /* tf.nn.avg_pool 2x2/2 (layers.py:105-106); backward != 0: in = dy [B,H/2,W/2,C], out = dx [B,H,W,C] */
 int pnp_avgpool2(const float* in, float* out, int B, int H, int W, int C, int backward, void* stream);
+/* tf.nn.max_pool / tf.nn.avg_pool with ksize = strides = [1,n,n,1], padding 'SAME', any n >= 1 (layers.py:102-106): Ho = ceil(H/n),
+ * the window grid is centred as TensorFlow centres it (pad_before = (Ho*n - H) / 2), padding never wins a max and is not counted by
+ * the average.  avg != 0 selects the average.  y = [B,Ho,Wo,C].  Backward: dx = [B,H,W,C]; the max routes to the first maximal
+ * element of a window in row-major order (x may be NULL for the average). */
+int pnp_pool_fwd(const float* x, float* y, int B, int H, int W, int C, int n, int avg, void* stream);
+int pnp_pool_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, int n, int avg, void* stream);
+/* crop_and_concat (layers.py:108-115): out[B,H2,W2,C1+C2] = [ centre crop of x1[B,H1,W1,C1] to H2 x W2 (offsets (H1-H2)/2,
+ * (W1-W2)/2) | x2[B,H2,W2,C2] ]; simple_concat2d (layers.py:117-127) is the H1 == H2, W1 == W2 case.  Backward: dx1 (zero outside
+ * the crop) and dx2 from dout; either output may be NULL. */
+int pnp_crop_concat_fwd(const float* x1, const float* x2, float* out, int B, int H1, int W1, int C1, int H2, int W2, int C2,
+                        void* stream);
+int pnp_crop_concat_bwd(const float* dout, float* dx1, float* dx2, int B, int H1, int W1, int C1, int H2, int W2, int C2,
+                        void* stream);
 /* tf.pad(..., 'SYMMETRIC') by p on each spatial side (layers.py:19-23,68-72) */
 int pnp_mirror_pad_fwd(const float* x, float* y, int B, int H, int W, int C, int p, void* stream);
 int pnp_mirror_pad_bwd(const float* dy, float* dx, int B, int H, int W, int C, int p, void* stream);
@@ -234,6 +247,11 @@ int pnp_fc_fwd(const float* x, const float* w, float* out, int B, int F, void* s
 int pnp_fc_bwd(const float* x, const float* w, const float* dout, float* dx, float* dw, int B, int F, void* stream);
 /* out[0] = ca*mean(a) + cb*mean(b) (b may be NULL)   (adversarial.py:455-459) */
 int pnp_mean_combo(const float* a, float ca, const float* b, float cb, int n, float* out, void* stream);
+/* cross_entropy (layers.py:140-141): out[0] = -mean(y * log(clip(p, 1e-10, 1))) over n elements; acc = one ZEROED fp64 device
+ * scalar (receives the sum).  Backward from the scalar's gradient gout[0]: dy = -g/n * log(clip p), dp = -g/n * y / p where
+ * 1e-10 <= p <= 1, else 0 (tf.clip_by_value's gradient); either output may be NULL. */
+int pnp_cross_entropy_fwd(const float* y, const float* p, long long n, double* acc, float* out, void* stream);
+int pnp_cross_entropy_bwd(const float* y, const float* p, const float* gout, long long n, float* dy, float* dp, void* stream);
 /* out[0] += 0.5 * sum(w^2)   (tf.nn.l2_loss) */
 int pnp_l2_loss_acc(const float* w, long long n, double* out, void* stream);
 

@@ -73,6 +73,12 @@ SIGNATURES = {
     "pnp_maxpool2_fwd": [P, P, c_int, c_int, c_int, c_int, P],
     "pnp_maxpool2_bwd": [P, P, P, c_int, c_int, c_int, c_int, P],
     "pnp_avgpool2": [P, P, c_int, c_int, c_int, c_int, c_int, P],
+    "pnp_pool_fwd": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "pnp_pool_bwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "pnp_crop_concat_fwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "pnp_crop_concat_bwd": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "pnp_cross_entropy_fwd": [P, P, c_ll, P, P, P],
+    "pnp_cross_entropy_bwd": [P, P, P, c_ll, P, P, P],
     "pnp_mirror_pad_fwd": [P, P, c_int, c_int, c_int, c_int, c_int, P],
     "pnp_mirror_pad_bwd": [P, P, c_int, c_int, c_int, c_int, c_int, P],
     "pnp_phase_shift_fwd": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],

@@ -719,6 +719,87 @@ def avg_pool2(x):
     return _AvgPool2Fn.apply(x)
 
 
+class _PoolFn(torch.autograd.Function):
+    """tf.nn.max_pool / avg_pool, ksize = strides = n, padding 'SAME', any n (layers.py:102-106)"""
+
+    @staticmethod
+    def forward(ctx, x, n, avg):
+        x = x.contiguous()
+        B, H, W, C = x.shape
+        y = torch.empty(B, -(-H // n), -(-W // n), C, dtype=x.dtype, device=x.device)
+        call("pnp_pool_fwd", ptr(x), ptr(y), B, H, W, C, n, 1 if avg else 0, rt.stream())
+        ctx.meta = (B, H, W, C, n, avg)
+        ctx.save_for_backward(*(() if avg else (x,)))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, H, W, C, n, avg = ctx.meta
+        x = None if avg else ctx.saved_tensors[0]
+        dx = torch.empty(B, H, W, C, dtype=dy.dtype, device=dy.device)
+        call("pnp_pool_bwd", ptr(x), ptr(dy.contiguous()), ptr(dx), B, H, W, C, n, 1 if avg else 0, rt.stream())
+        return dx, None, None
+
+
+def pool_same(x, n, avg=False):
+    return _PoolFn.apply(x, int(n), bool(avg))
+
+
+class _CropConcatFn(torch.autograd.Function):
+    """crop_and_concat / simple_concat2d (layers.py:108-127): [centre crop of x1 to x2's height and width | x2] along channels"""
+
+    @staticmethod
+    def forward(ctx, x1, x2):
+        x1, x2 = x1.contiguous(), x2.contiguous()
+        B, H1, W1, C1 = x1.shape
+        B2, H2, W2, C2 = x2.shape
+        out = torch.empty(B, H2, W2, C1 + C2, dtype=x1.dtype, device=x1.device)
+        call("pnp_crop_concat_fwd", ptr(x1), ptr(x2), ptr(out), B, H1, W1, C1, H2, W2, C2, rt.stream())
+        ctx.meta = (B, H1, W1, C1, H2, W2, C2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, H1, W1, C1, H2, W2, C2 = ctx.meta
+        n1, n2 = ctx.needs_input_grad
+        dx1 = torch.empty(B, H1, W1, C1, dtype=dout.dtype, device=dout.device) if n1 else None
+        dx2 = torch.empty(B, H2, W2, C2, dtype=dout.dtype, device=dout.device) if n2 else None
+        if n1 or n2:
+            call("pnp_crop_concat_bwd", ptr(dout.contiguous()), ptr(dx1), ptr(dx2), B, H1, W1, C1, H2, W2, C2, rt.stream())
+        return dx1, dx2
+
+
+def crop_concat(x1, x2):
+    return _CropConcatFn.apply(x1, x2)
+
+
+class _CrossEntropyFn(torch.autograd.Function):
+    """layers.cross_entropy (layers.py:140-141): -mean(y_ * log(clip(output_map, 1e-10, 1)))"""
+
+    @staticmethod
+    def forward(ctx, y_, p):
+        y_, p = y_.contiguous(), p.contiguous()
+        acc = torch.zeros(1, dtype=torch.float64, device=p.device)
+        out = torch.empty(1, dtype=torch.float32, device=p.device)
+        call("pnp_cross_entropy_fwd", ptr(y_), ptr(p), p.numel(), ptr(acc), ptr(out), rt.stream())
+        ctx.save_for_backward(y_, p)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        y_, p = ctx.saved_tensors
+        ny, np_ = ctx.needs_input_grad
+        dy = torch.empty_like(y_) if ny else None
+        dp = torch.empty_like(p) if np_ else None
+        if ny or np_:
+            call("pnp_cross_entropy_bwd", ptr(y_), ptr(p), ptr(g.contiguous().reshape(1).float()), p.numel(), ptr(dy), ptr(dp), rt.stream())
+        return dy, dp
+
+
+def cross_entropy(y_, p):
+    return _CrossEntropyFn.apply(y_, p)
+
+
 class _PhaseShiftFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, r, G, order_b1):

@@ -188,17 +188,25 @@ class _BNOnly(torch.autograd.Function):
 
 # ---- pooling / concat / softmax ------------------------------------------------------------------------
 def max_pool2d(x, n):
-    """layers.py:102-103 (n must be 2: the only use in the reference graphs)"""
-    if n != 2:
-        raise NotImplementedError("max_pool2d: only the 2x2/2 pooling of the reference graphs is implemented")
-    return F.max_pool2(x)
+    """layers.py:102-103: tf.nn.max_pool, ksize = strides = [1,n,n,1], 'SAME'.  n = 2 on even maps (every use in the reference
+    graphs) takes the vectorised 2x2 kernel; any other n / odd maps the general SAME-geometry kernel."""
+    n = int(n)
+    if n < 1:
+        raise ValueError("max_pool2d: n must be a positive integer")
+    if n == 2 and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0:
+        return F.max_pool2(x)
+    return F.pool_same(x, n, avg=False)
 
 
 def avg_pool2d(x, n):
-    """layers.py:105-106 (n must be 2; never called by the reference graphs, kept for surface completeness)"""
-    if n != 2:
-        raise NotImplementedError("avg_pool2d: only 2x2/2 pooling is implemented")
-    return F.avg_pool2(x)
+    """layers.py:105-106: tf.nn.avg_pool, ksize = strides = [1,n,n,1], 'SAME' (padding is not counted).  Never called by the reference
+    graphs."""
+    n = int(n)
+    if n < 1:
+        raise ValueError("avg_pool2d: n must be a positive integer")
+    if n == 2 and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0:
+        return F.avg_pool2(x)
+    return F.pool_same(x, n, avg=True)
 
 
 def simple_concat2d(x1, x2):
@@ -208,14 +216,15 @@ def simple_concat2d(x1, x2):
         print("x1_shape: %s" % str(list(x1.shape)))
         print("x2_shape: %s" % str(list(x2.shape)))
         raise ValueError("Cannot concatenate tensors with different shape, igonoring feature map depth")
-    return torch.cat([x1, x2], 3)
+    return F.crop_concat(x1, x2)
 
 
 def crop_and_concat(x1, x2, name="default"):
-    """layers.py:108-115 -- centre-crop x1 to x2 and concat (unused by the reference graphs)"""
-    oy = (x1.shape[1] - x2.shape[1]) // 2
-    ox = (x1.shape[2] - x2.shape[2]) // 2
-    return torch.cat([x1[:, oy:oy + x2.shape[1], ox:ox + x2.shape[2], :], x2], 3)
+    """layers.py:108-115 -- centre-crop x1 to x2's height and width (offsets (H1-H2)//2, (W1-W2)//2) and concat along channels
+    (unused by the reference graphs)"""
+    if x1.shape[0] != x2.shape[0] or x1.shape[1] < x2.shape[1] or x1.shape[2] < x2.shape[2]:
+        raise ValueError("crop_and_concat: x1 %s cannot be cropped to x2 %s" % (list(x1.shape), list(x2.shape)))
+    return F.crop_concat(x1, x2)
 
 
 def pixel_wise_softmax_2(output_map):
@@ -231,8 +240,10 @@ def pixel_wise_softmax(output_map):
 
 
 def cross_entropy(y_, output_map):
-    """layers.py:140-141 (unused by the reference graphs; host-side convenience)"""
-    return -torch.mean(y_ * torch.log(torch.clamp(output_map, 1e-10, 1.0)))
+    """layers.py:140-141: -mean(y_ * log(clip(output_map, 1e-10, 1))) (unused by the reference graphs)"""
+    if tuple(y_.shape) != tuple(output_map.shape):
+        raise ValueError("cross_entropy: labels %s and probabilities %s differ in shape" % (list(y_.shape), list(output_map.shape)))
+    return F.cross_entropy(y_, output_map)
 
 
 # ---- residual blocks -----------------------------------------------------------------------------------

@@ -147,6 +147,23 @@ def max_pool2x2(x):
     return x.reshape(B, H // 2, 2, W // 2, 2, C).max(axis=(2, 4))
 
 
+def pool_same(x, n, avg=False):
+    """tf.nn.max_pool / tf.nn.avg_pool with ksize = strides = [1,n,n,1], padding 'SAME' (layers.py:102-106), naive loops.
+    Published TF behaviour (GetWindowedOutputSizeVerbose): out = ceil(in / n), pad_needed = out * n - in, pad_before = pad_needed // 2;
+    padded positions never win a max and AvgPool divides by the number of VALID elements of a window."""
+    B, H, W, C = x.shape
+    Ho, Wo = -(-H // n), -(-W // n)
+    pt, pl = (Ho * n - H) // 2, (Wo * n - W) // 2
+    y = np.zeros((B, Ho, Wo, C), x.dtype)
+    for oy in range(Ho):
+        y0, y1 = max(oy * n - pt, 0), min(oy * n - pt + n, H)
+        for ox in range(Wo):
+            x0, x1 = max(ox * n - pl, 0), min(ox * n - pl + n, W)
+            win = x[:, y0:y1, x0:x1, :].reshape(B, -1, C)
+            y[:, oy, ox, :] = win.mean(1) if avg else win.max(1)
+    return y
+
+
 def channel_pad_skip(x):
     """tf.pad(x, [[0,0],[0,0],[0,0],[C//2, C//2]]) (layers.py:160,182)."""
     C = x.shape[-1]

@@ -154,6 +154,31 @@ def max_pool2d(x, n=2):
     return _nhwc(F.max_pool2d(_nchw(x), n, n))
 
 
+def pool_same(x, n, avg=False):
+    """layers.py:102-106 for any n and any map size: TF 'SAME' geometry (tf14_numpy.pool_same), differentiable"""
+    B, H, W, C = x.shape
+    Ho, Wo = -(-H // n), -(-W // n)
+    pt, pl = (Ho * n - H) // 2, (Wo * n - W) // 2
+    pad = (pl, Wo * n - W - pl, pt, Ho * n - H - pt)
+    xc = _nchw(x)
+    if not avg:
+        return _nhwc(F.max_pool2d(F.pad(xc, pad, value=float("-inf")), n, n))
+    ssum = F.avg_pool2d(F.pad(xc, pad), n, n) * (n * n)
+    cnt = F.avg_pool2d(F.pad(torch.ones(1, 1, H, W, dtype=x.dtype), pad), n, n) * (n * n)
+    return _nhwc(ssum / cnt)
+
+
+def crop_and_concat(x1, x2):
+    """layers.py:108-115"""
+    oy, ox = (x1.shape[1] - x2.shape[1]) // 2, (x1.shape[2] - x2.shape[2]) // 2
+    return torch.cat([x1[:, oy:oy + x2.shape[1], ox:ox + x2.shape[2], :], x2], 3)
+
+
+def cross_entropy(y_, output_map):
+    """layers.py:140-141; torch.clamp passes the gradient inside [min, max] (bounds included) like tf.clip_by_value"""
+    return -torch.mean(y_ * torch.log(torch.clamp(output_map, 1e-10, 1.0)))
+
+
 def PS(X, r, n_channel, batch_size):
     """ops.py:23-27 via the closed-form index law pinned in tests/test_oracle_kat.py against the
     literal emulation (tf14_numpy.PS_literal).

@@ -125,7 +125,14 @@ def test_layers_error_behaviour_without_a_gpu():
         L.conv2d(x, w, 1.0, strides=[1, 2, 1, 1])
     with pytest.raises(ValueError):
         L.simple_concat2d(torch.zeros(2, 8, 8, 1), torch.zeros(2, 4, 8, 1))
-    assert L.simple_concat2d(torch.zeros(2, 8, 8, 1), torch.zeros(2, 8, 8, 3)).shape == (2, 8, 8, 4)
+    with pytest.raises(ValueError):
+        L.crop_and_concat(torch.zeros(2, 4, 8, 1), torch.zeros(2, 8, 8, 3))           # x1 smaller than x2: nothing to crop
+    with pytest.raises(ValueError):
+        L.cross_entropy(torch.zeros(2, 8, 8, 2), torch.zeros(2, 8, 8, 3))
+    with pytest.raises(ValueError):
+        L.max_pool2d(x, 0)
+    with pytest.raises(ValueError):
+        L.avg_pool2d(x, -1)
     with pytest.raises(ValueError):
         ops.PS(torch.zeros(2, 4, 4, 64), 8, n_channel=1, batch_size=3)
     with pytest.raises(ValueError):

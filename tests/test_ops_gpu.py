@@ -327,6 +327,81 @@ def test_avgpool():
     check("dx", xg.grad, xo.grad, 1e-6)
 
 
+@pytest.mark.parametrize("H,W,C,n", [(5, 7, 6, 2), (9, 9, 16, 4), (4, 4, 3, 3), (6, 5, 8, 1), (3, 10, 5, 5), (8, 12, 6, 2), (256, 256, 16, 3)])
+@pytest.mark.parametrize("avg", [False, True])
+def test_pool_same_any_n(H, W, C, n, avg):
+    """layers.max_pool2d / avg_pool2d for any n and any map size (tf.nn.*_pool ksize = strides = n, 'SAME', layers.py:102-106) vs the
+    oracle (KAT-pinned SAME geometry); n = 2 on even maps is the vectorised 2x2 kernel and must agree with the general one"""
+    L, ops, F, rt = _prod()
+    T = _oracle()
+    B = 2 if H < 256 else 1
+    x = randn((B, H, W, C), 151)
+    xo = x.double().requires_grad_(True)
+    yo = T.pool_same(xo, n, avg)
+    r = randn(tuple(yo.shape), 152)
+    (yo * r.double()).sum().backward()
+    xg = _var(x)
+    y = (L.avg_pool2d if avg else L.max_pool2d)(xg, n)
+    assert tuple(y.shape) == (B, -(-H // n), -(-W // n), C)
+    check("y", y, yo, 1e-6)
+    y.backward(r.to(DEV))
+    check("dx", xg.grad, xo.grad, 1e-6)
+    if n == 2 and H % 2 == 0 and W % 2 == 0:
+        xs = _var(x)
+        ys = F.pool_same(xs, 2, avg)
+        ys.backward(r.to(DEV))
+        assert torch.equal(ys, y) and torch.equal(xs.grad, xg.grad)
+
+
+@pytest.mark.parametrize("shape1,shape2", [((2, 8, 12, 3), (2, 8, 12, 5)), ((2, 10, 13, 4), (2, 6, 8, 2)), ((1, 9, 9, 1), (1, 8, 8, 7)),
+                                           ((2, 64, 64, 16), (2, 64, 64, 16))])
+def test_crop_and_concat(shape1, shape2):
+    """layers.crop_and_concat / simple_concat2d (layers.py:108-127): centre crop + channel concat, and its gradients (zero outside the
+    crop) -- exact copies, so bit equality"""
+    L, ops, F, rt = _prod()
+    T = _oracle()
+    x1, x2 = randn(shape1, 161), randn(shape2, 162)
+    o1, o2 = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+    yo = T.crop_and_concat(o1, o2)
+    r = randn(tuple(yo.shape), 163)
+    (yo * r).sum().backward()
+    g1, g2 = _var(x1), _var(x2)
+    y = L.crop_and_concat(g1, g2)
+    assert torch.equal(y.cpu(), yo.detach())
+    y.backward(r.to(DEV))
+    assert torch.equal(g1.grad.cpu(), o1.grad) and torch.equal(g2.grad.cpu(), o2.grad)
+    if shape1[:3] == shape2[:3]:
+        assert torch.equal(L.simple_concat2d(g1.detach(), g2.detach()).cpu(), yo.detach())
+    # only one side needs a gradient
+    g1, g2 = _var(x1), _var(x2, False)
+    L.crop_and_concat(g1, g2).backward(r.to(DEV))
+    assert torch.equal(g1.grad.cpu(), o1.grad) and g2.grad is None
+
+
+def test_cross_entropy():
+    """layers.cross_entropy (layers.py:140-141): -mean(y * log(clip(p, 1e-10, 1))), gradients w.r.t. both arguments; probabilities
+    outside [1e-10, 1] are clipped in the value and receive no gradient"""
+    L, ops, F, rt = _prod()
+    T = _oracle()
+    p = torch.softmax(randn((2, 16, 16, 5), 171) * 3, -1)
+    p[0, 0, 0] = torch.tensor([0.0, 1e-12, 1.5, 1.0, 0.5])                # below / above the clip range, on its upper bound
+    y = torch.nn.functional.one_hot(torch.randint(0, 5, (2, 16, 16), generator=torch.Generator().manual_seed(3)), 5).float()
+    y[0, 0, 0] = torch.tensor([0.2, 0.2, 0.2, 0.2, 0.2])
+    y[1, 3, 3] = torch.tensor([0.3, 0.2, 0.5, 0.0, 0.0])                  # soft labels are legal inputs
+    yo, po = y.double().requires_grad_(True), p.double().requires_grad_(True)
+    ce_o = T.cross_entropy(yo, po)
+    (ce_o * 1.7).backward()
+    yg, pg = _var(y), _var(p)
+    ce = L.cross_entropy(yg, pg)
+    assert ce.dim() == 0
+    check("cross_entropy", ce, ce_o, 1e-6)
+    (ce * 1.7).backward()
+    check("d labels", yg.grad, yo.grad, 1e-6)
+    check("d probabilities", pg.grad, po.grad, 1e-5)
+    assert float(pg.grad[0, 0, 0, 0]) == 0.0 and float(pg.grad[0, 0, 0, 1]) == 0.0 and float(pg.grad[0, 0, 0, 2]) == 0.0
+    assert float(pg.grad[0, 0, 0, 3]) != 0.0
+
+
 @pytest.mark.parametrize("B", [1, 2, 3])
 @pytest.mark.parametrize("G", [1, 5])
 def test_phase_shift(B, G):

@@ -232,3 +232,23 @@ def test_same_padding_agrees_with_an_independent_port_of_tensorflows_rule():
                 assert N.same_pad(n, k, s) == (before, total - before), (n, k, s)
                 assert tuple(F.same_pad(n, k, s)) == (before, total - before), (n, k, s)
                 assert y.shape[-1] >= k and (y.shape[-1] - k) // s + 1 == -(-n // s)            # SAME output size ceil(n / s)
+
+
+def test_kat13_pooling_same_geometry_for_any_n():
+    """tf.nn.max_pool / avg_pool, ksize = strides = n, 'SAME' (layers.py:102-106): out = ceil(in / n), pad_before = (out * n - in) // 2,
+    padding never wins a max and is not counted by the average.  Hand-derived on arange maps; both oracle forms."""
+    import torch
+    from oracle import tf14_torch as T
+    x = np.arange(25, dtype=np.float64).reshape(1, 5, 5, 1)              # 5 -> 3 windows: rows [0,2) [2,4) [4,5)
+    assert N.pool_same(x, 2)[0, :, :, 0].tolist() == [[6, 8, 9], [16, 18, 19], [21, 23, 24]]
+    assert N.pool_same(x, 2, avg=True)[0, :, :, 0].tolist() == [[3, 5, 6.5], [13, 15, 16.5], [20.5, 22.5, 24]]
+    x = np.arange(16, dtype=np.float64).reshape(1, 4, 4, 1)              # n = 3: pad_needed 2, one row of padding BEFORE: rows [0,2) [2,4)
+    assert N.pool_same(x, 3)[0, :, :, 0].tolist() == [[5, 7], [13, 15]]
+    assert N.pool_same(x, 3, avg=True)[0, :, :, 0].tolist() == [[2.5, 4.5], [10.5, 12.5]]
+    assert np.array_equal(N.pool_same(x, 1), x) and np.array_equal(N.pool_same(x, 2), N.max_pool2x2(x))
+    rng = np.random.RandomState(0)
+    for (H, W, n) in [(5, 7, 2), (8, 12, 2), (9, 9, 4), (4, 4, 3), (6, 5, 1), (3, 10, 5)]:
+        x = rng.standard_normal((2, H, W, 3))
+        for avg in (False, True):
+            a, b = N.pool_same(x, n, avg), T.pool_same(torch.from_numpy(x), n, avg).numpy()
+            assert a.shape == b.shape == (2, -(-H // n), -(-W // n), 3) and np.abs(a - b).max() < 1e-12
