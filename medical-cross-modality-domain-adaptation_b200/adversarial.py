@@ -327,6 +327,7 @@ class Trainer(object):
         self.lr_update_flag = self.train_config.get("lr_update", False)
         self.mr_source, self.ct_source = mr_source, ct_source
         self.mr_train_list, self.ct_train_list = mr_train_list, ct_train_list
+        self.mr_val_list, self.ct_val_list = mr_val_list, ct_val_list
         self.test_label_list, self.test_nii_list = test_label_list, test_nii_list
         self.dp = parallel.DataParallel()
         self.global_step = 0
@@ -708,6 +709,9 @@ class Trainer(object):
             return SyntheticSource(B, seed=seed + self.dp.rank, num_cls=self.num_cls or 5, **kw)
         mr_src = source(self.mr_source, self.mr_train_list, 1234)
         ct_src = source(self.ct_source, self.ct_train_list, 4321, shift=0.3, scale=0.8)
+        # the validation queues of adversarial.py:811-815 (lists/{mr,ct}_val_list), else further synthetic streams
+        mr_val = source(None, self.mr_val_list, 2234)
+        ct_val = source(None, self.ct_val_list, 5321, shift=0.3, scale=0.8)
         dev = rt.device()
         dis_interval, gen_interval = cfg.get("dis_interval", 1), cfg.get("gen_interval", 1)
         dis_inc, gen_inc = cfg.get("dis_sub_iter_inc", 0), cfg.get("gen_sub_iter_inc", 0)
@@ -731,11 +735,10 @@ class Trainer(object):
                     self.gen_sub_iter += gen_inc
                 if step % display_step == 0:
                     logging.info("Training step %s epoch %s finished, %.3f s" % (step, epoch, time.time() - start))
-                    # the monitoring passes of adversarial.py:894-922: a training batch, then a "validation" batch with the
-                    # per-organ table (the synthetic / list sources stand in for the separate validation queues)
+                    # the monitoring passes of adversarial.py:894-922: a training batch, then a validation batch with the per-organ table
                     tag = str(self.train_config.get("tag", ""))      # FileWriter(output_path + "/train_log" + tag) (adversarial.py:807-808)
-                    for sub, detail in (("train_log", False), ("val_log", True)):
-                        (ct, cty), (mr, mry) = ct_src.next(), mr_src.next()
+                    for sub, detail, cs, ms in (("train_log", False, ct_src, mr_src), ("val_log", True, ct_val, mr_val)):
+                        (ct, cty), (mr, mry) = cs.next(), ms.next()
                         self.output_minibatch_stats(step, to_device(ct, dev), to_device(cty, dev), to_device(mr, dev), to_device(mry, dev),
                                                     os.path.join(output_path, sub + tag), detail)
                 if step % ckpt_space == 0 and step != 0:

@@ -11,7 +11,9 @@ from . import nifti
 
 
 def _read_lists(fid):
-    """lib.py:7-20: read a text file of paths, one per line (lines shorter than 3 chars skipped)."""
+    """lib.py:7-20: read a text file of paths, one per line (lines shorter than 3 chars skipped); None when the file is absent."""
+    if not os.path.isfile(fid):
+        return None
     with open(fid, 'r') as fd:
         lines = fd.readlines()
     return [ln.split('\n')[0] for ln in lines if len(ln) >= 3]

@@ -1,6 +1,7 @@
 """Entry point mirroring the reference's train_gan.py (:24-157): `--phase pre-train | train-gan | fine-tune`
 with the reference's configuration dictionaries and per-phase overrides (keys kept verbatim)."""
 import argparse
+import os
 import logging
 
 from . import adversarial as drn
@@ -61,6 +62,8 @@ def main(phase, argv=None):
     ap.add_argument("--epochs", type=int, default=None)
     ap.add_argument("--keep-prob", type=float, default=0.75)
     ap.add_argument("--conv-backend", default=None, choices=["auto", "simt", "tc3", "tc1"])
+    ap.add_argument("--lists", default="./lists", help="directory of mr_train_list, mr_val_list, ct_train_list, ct_val_list")
+    ap.add_argument("--synthetic", action="store_true", help="ignore the list files and train on the synthetic sources")
     a = ap.parse_args(argv)
     logging.basicConfig(level=logging.INFO)
     parallel.init_from_env()
@@ -71,7 +74,13 @@ def main(phase, argv=None):
     out = "./tmp_exps/mr2ct" + date + str(rate)[0] + str(rate)[2]
     net = drn.Full_DRN(channels=3, batch_size=a.batch_size, n_class=num_cls, cost_kwargs=ck, network_config=nc)
     print("Network has been built ...")
-    trainer = drn.Trainer(net, num_cls=num_cls, batch_size=a.batch_size, opt_kwargs=dict(opt_kwargs), train_config=tc)
+    # train_gan.py:69-72; the four variable-name lists the reference also reads (:74-77) are not inputs here: the MR -> CT copy
+    # pairs and the BN hand-over pairs are derived from the graph (and pinned to those very lists by tests/test_reference_graph_trace.py)
+    from .train_segmenter import resolve_lists
+    mr_train, mr_val, ct_train, ct_val = resolve_lists(*[os.path.join(a.lists, n) for n in
+                                                         ("mr_train_list", "mr_val_list", "ct_train_list", "ct_val_list")], a.synthetic)
+    trainer = drn.Trainer(net, mr_train, mr_val, ct_train, ct_val, num_cls=num_cls, batch_size=a.batch_size,
+                          opt_kwargs=dict(opt_kwargs), train_config=tc)
     print("Now start training...")
     return trainer.train(output_path=out, restored_path=out, training_iters=a.training_iters or tc["training_iters"],
                          epochs=a.epochs or tc["epochs"], dropout=a.keep_prob)

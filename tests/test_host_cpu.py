@@ -452,3 +452,68 @@ def test_bucketed_overlapped_allreduce_gloo_world_size_2():
         assert any(launched_early), "no bucket was reduced before the backward pass ended"
         assert local == float(r + 1) and after == 3.0
         assert out["err%d" % r] is not None and "more gradient contributions" in out["err%d" % r]
+
+
+def test_entry_scripts_read_the_reference_list_files(tmp_path):
+    """train_segmenter.py:60-61 / train_gan.py:69-72: `_read_lists` on ./lists/*_list (None when the file is absent, as in lib.py:11-12);
+    a present list selects the TFRecord source of that stream -- training AND validation --, an absent one the synthetic source, and a
+    list that points at missing data stops the run instead of silently training on synthetic slices."""
+    import pnp_b200  # noqa: F401
+    from pnp_b200 import tfrecord as tfr, source_segmenter as S, adversarial as A
+    from pnp_b200.lib import _read_lists
+    from pnp_b200.train_segmenter import resolve_lists
+    from pnp_b200.train_gan import configure
+    rng = np.random.RandomState(4)
+    lists = tmp_path / "lists"
+    lists.mkdir()
+    truth = {}
+    for name, n in (("mr_train_list", 3), ("mr_val_list", 2), ("ct_train_list", 3)):
+        files = []
+        for i in range(n):
+            img = rng.randn(256, 256, 3).astype(np.float32)
+            lab = rng.randint(0, 5, (256, 256, 3)).astype(np.float32)
+            p = str(tmp_path / ("%s_%d.tfrecords" % (name, i)))
+            tfr.write_record(p, [tfr.encode_example(img, lab)])
+            files.append(p)
+            truth[p] = img
+        (lists / name).write_text("\n".join(files) + "\n\n")              # trailing blank lines are skipped (len < 3)
+    assert _read_lists(str(lists / "ct_val_list")) is None
+    assert _read_lists(str(lists / "mr_val_list")) == [str(tmp_path / ("mr_val_list_%d.tfrecords" % i)) for i in range(2)]
+    mr_train, mr_val, ct_train, ct_val = resolve_lists(*[str(lists / n) for n in ("mr_train_list", "mr_val_list", "ct_train_list",
+                                                                                  "ct_val_list")], False)
+    assert len(mr_train) == 3 and len(mr_val) == 2 and len(ct_train) == 3 and ct_val == []
+    assert resolve_lists(str(lists / "mr_train_list"), True) == [[]]                           # --synthetic
+    (lists / "broken_list").write_text(str(tmp_path / "gone.tfrecords") + "\n")
+    with pytest.raises(IOError, match="does not exist"):
+        resolve_lists(str(lists / "broken_list"), False)
+
+    # ---- the segmenter loop draws its training batches from train_list and its validation batches from val_list
+    net = S.Full_DRN(3, 5, 2, cost_kwargs={"cross_flag": True, "miu_cross": 1.0, "dice_flag": True, "miu_dice": 1.0})
+    tr = S.Trainer(net, train_list=mr_train, val_list=mr_val, num_cls=5, batch_size=2, opt_kwargs={"learning_rate": 1e-3}, optimizer="adam")
+    seen = {"train": [], "val": []}
+    tr.feed = lambda images, raw: (images, raw)
+    tr.train_step = lambda x, y, keep_prob=0.75: seen["train"].append(x.clone()) or (0.0, 0.0)
+    tr.output_minibatch_stats = lambda x, y, step=None, log_dir=None: 0.0
+    tr.val_stats = lambda x, y, step=None, log_dir=None, detail=False: seen["val"].append(x.clone()) or {}
+    tr.train(output_path=str(tmp_path / "seg"), training_iters=3, epochs=1, display_step=2)
+    imgs = lambda lst: [truth[p] for p in lst]
+    member = lambda x, pool: any(np.array_equal(x.numpy(), im) for im in pool)
+    assert len(seen["train"]) == 3 and len(seen["val"]) == 2
+    assert all(member(b[k], imgs(mr_train)) for b in seen["train"] for k in range(2))
+    assert all(member(b[k], imgs(mr_val)) for b in seen["val"] for k in range(2))
+
+    # ---- the GAN loop: MR from its lists, CT training from its list, CT validation (no list) from the synthetic stream
+    ck, nc, tc = configure("pre-train")
+    tc.update(training_iters=3, epochs=1)
+    anet = A.Full_DRN(3, 5, 2, cost_kwargs=ck, network_config=nc)
+    atr = A.Trainer(anet, mr_train, mr_val, ct_train, ct_val, num_cls=5, batch_size=2, opt_kwargs={"learning_rate": 3e-4}, train_config=tc)
+    got = {"d": [], "mon": []}
+    atr.d_step = lambda mr, ct, keep_prob=0.75, apply=True: got["d"].append((mr.clone(), ct.clone()))
+    atr.g_step = lambda ct, keep_prob=0.75, apply=True: None
+    atr.output_minibatch_stats = lambda step, ct, cty, mr, mry, log_dir=None, detail=False: got["mon"].append((detail, ct.clone(), mr.clone()))
+    atr.train(output_path=str(tmp_path / "gan"), restore=False, training_iters=3, epochs=1, display_step=2)
+    assert len(got["d"]) == 2 and len(got["mon"]) == 4
+    assert all(member(mr[k], imgs(mr_train)) and member(ct[k], imgs(ct_train)) for mr, ct in got["d"] for k in range(2))
+    for detail, ct, mr in got["mon"]:
+        assert all(member(mr[k], imgs(mr_val) if detail else imgs(mr_train)) for k in range(2))
+        assert all(member(ct[k], imgs(ct_train)) != detail for k in range(2))            # validation CT: synthetic, not from a list
