@@ -15,6 +15,12 @@ against the reference's own ops.py:3-27 and lib.py:75-92; softmax_weighted_loss 
 source_segmenter.py:241-273 evaluated numerically.  Everything that is defined by TensorFlow kernels (conv padding
 offsets, batch norm, dropout scaling, Adam / RMSProp) remains UNPINNED restatement.
 
+CROSS-CHECKED AGAINST THIRD-PARTY TF SEMANTICS (tests/test_tf_semantics_opencv_cpu.py): conv2d ('SAME', every stride / kernel parity
+class of the graphs), the dilated convolution against the SpaceToBatchND -> Conv2D -> BatchToSpaceND graph TF 1.4 emits for
+atrous_conv2d, pool_same, inference-mode batch_norm, leaky_relu / relu, softmax -- executed by OpenCV's TensorFlow importer
+(cv2.dnn.readNetFromTensorflow) on GraphDefs built from the TF protos in `tensorboard`.  Train-mode batch norm, dropout scaling and
+the optimizers have no such counterpart in this image and stay unpinned.
+
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
 this package.  The product path (medical-cross-modality-domain-adaptation_b200/) never does.
 
