@@ -199,3 +199,27 @@ def test_reference_adversarial_segmenter_streams_in_opencv_equal_the_oracle(tmp_
     with torch.no_grad():
         ref = oracle.segment(x, stream, 1.0, False)
     _compare("adversarial.Full_DRN %s stream" % stream, c9, logits, ref)
+
+
+def test_committed_opencv_vectors_match_the_oracle():
+    """the fixture the GPU tests compare the CUDA path with (tests/golden/opencv_reference_graph_vectors.npz) -- read back through the
+    very helper the GPU tests use and held against the oracle here, so a fixture / indexing mistake cannot hide behind a GPU tolerance"""
+    from oracle.pnp_graphs import OracleSegmenter, OracleAdversarial, init_numpy_params, synthetic_images
+    from tests.test_parity_configs_gpu import _bn_noise
+    from tests.util import compare_with_opencv_vectors
+    ws, bns = OracleSegmenter.layout()
+    P = init_numpy_params(ws, bns, 0, 0.05)
+    _bn_noise(P, bns, 6)
+    with torch.no_grad():
+        lg = OracleSegmenter(P, B).forward(synthetic_images(B, 1234), 1.0, False)["logits"]
+    err, agree = compare_with_opencv_vectors("segmenter", lg, 2e-5, 0.99995)
+    ws, bns = OracleAdversarial.layout()
+    P = init_numpy_params(ws, bns, 0, 0.05)
+    _bn_noise(P, bns, 6)
+    with torch.no_grad():
+        lg = OracleAdversarial(P, B, lambda_mask_loss=0.3, dis_sub_iter=1, gen_sub_iter=1).segment(
+            synthetic_images(B, 4321, 0.3, 0.8), "ct", 1.0, False)["logits"]
+    compare_with_opencv_vectors("gan_ct", lg, 2e-5, 0.99995)
+    # a shifted input must NOT pass: the comparison is not vacuous
+    with pytest.raises(AssertionError):
+        compare_with_opencv_vectors("gan_ct", torch.roll(lg, 1, dims=2), 2e-5, 0.99995)

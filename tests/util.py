@@ -39,3 +39,22 @@ def check_grad(name, got, ref, tol_max, tol_l2):
     print("  %-40s rel_err %.3e (tol %.1e)  l2 %.3e (tol %.1e)" % (name, e, tol_max, l, tol_l2))
     assert tuple(got.shape) == tuple(ref.shape)
     assert np.isfinite(e) and e <= tol_max and l <= tol_l2, "%s: max %.3e l2 %.3e" % (name, e, l)
+
+
+def compare_with_opencv_vectors(tag, logits, tol_rel=1e-3, min_agree=0.999):
+    """`logits` [B,256,256,5] (torch / numpy) against tests/golden/opencv_reference_graph_vectors.npz: the same graph -- the reference's,
+    from its recorded trace -- executed by OpenCV's TensorFlow importer (tests/golden/make_opencv_reference_vectors.py).
+    Returns (max error at the stored positions relative to the largest |logit|, argmax agreement over the full maps)."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "opencv_reference_graph_vectors.npz"))
+    lg = logits.detach().float().cpu().numpy() if hasattr(logits, "detach") else np.asarray(logits, np.float32)
+    B = int(gold["batch"])
+    assert lg.shape == (B, 256, 256, 5), lg.shape
+    pos = gold["positions"]
+    flat = lg.reshape(B, 256 * 256, 5)
+    got = np.stack([flat[b][pos[b]] for b in range(B)])
+    err = float(np.abs(got - gold[tag + "_logits_at_positions"]).max() / float(gold[tag + "_max_abs_logit"]))
+    agree = float((lg.argmax(-1) == gold[tag + "_argmax"]).mean())
+    print("  %-12s vs OpenCV-executed reference graph: logits max rel err %.3e (tol %.1e), argmax agreement %.6f" % (tag, err, tol_rel, agree))
+    assert np.isfinite(err) and err <= tol_rel and agree >= min_agree, (tag, err, agree)
+    return err, agree
