@@ -321,6 +321,17 @@ class OracleSegmenter:
 # ==============================================================================================
 # adversarial graph
 # ==============================================================================================
+def disc_input(c4, c6, b7, c9, logits, B):
+    """adversarial.py:324-335: the 32-channel discriminator input [PS(c4, 2 groups) tiled x3 | PS(c6, 4) | PS(b7, 8) | PS(c9, 8) | logits |
+    float(argmax logits)]; pinned numerically to the executed reference lines (tests/golden/make_reference_disc_input_vectors.py)"""
+    f4 = T.PS(c4, 8, 2, B).repeat(1, 1, 1, 3)
+    f6 = T.PS(c6, 8, 4, B)
+    f7 = T.PS(b7, 8, 8, B)
+    f9 = T.PS(c9, 8, 8, B)
+    am = logits.argmax(3).to(logits.dtype).unsqueeze(3)
+    return torch.cat([f4, f6, f7, f9, logits, am], dim=3)
+
+
 # (scope, weight shapes, [bn scopes]) for the feature discriminator, adversarial.py:337-398
 CLS_BLOCKS = [
     # name, cin, cout, inc, down_k, down_stride
@@ -411,12 +422,7 @@ class OracleAdversarial:
     def classifier(self, c4, c6, b7, c9, logits):
         """adversarial.py:320-400.  BN always batch statistics; dropout always critic_keep_prob."""
         ps, B, kp = self.ps, self.batch_size, self.critic_keep_prob
-        f4 = T.PS(c4, 8, 2, B).repeat(1, 1, 1, 3)
-        f6 = T.PS(c6, 8, 4, B)
-        f7 = T.PS(b7, 8, 8, B)
-        f9 = T.PS(c9, 8, 8, B)
-        am = logits.argmax(3).to(logits.dtype).unsqueeze(3)
-        h = torch.cat([f4, f6, f7, f9, logits, am], dim=3)
+        h = disc_input(c4, c6, b7, c9, logits, B)
         d_input = h
         for name, cin, cout, inc, dk, ds in CLS_BLOCKS:
             s = "cls_scope/" + name

@@ -93,3 +93,25 @@ def test_oracle_dice_eval_equals_the_reference_code():
     mt, at = T.dice_eval(torch.from_numpy(pred), torch.from_numpy(y), 5)
     np.testing.assert_allclose(np.array([float(a) for a in at]), GOLD["de_arr"], rtol=1e-12)
     assert float(mt) == pytest.approx(float(GOLD["de_mean"]), rel=1e-12)
+
+
+@pytest.mark.parametrize("B", [2, 1, 3])
+def test_oracle_discriminator_input_equals_the_executed_reference_head(B):
+    """adversarial.py:320-335 executed numerically (tests/golden/make_reference_disc_input_vectors.py: the head of `create_classifier`
+    run unmodified up to its first `residual_block` call, with the reference's own PS and simple_concat2d): the 32-channel tensor the
+    feature discriminator sees -- PS'ed taps, the x3 tile, logits, float(argmax) with the first-index tie rule -- bit for bit; B = 1
+    takes the transposed sub-pixel branch of ops.py:11-20"""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_reference_disc_input_vectors as gen
+    from oracle.pnp_graphs import disc_input
+    gold = np.load(os.path.join(HERE, "golden", "reference_disc_input_vectors.npz"))
+    c4, c6, b7, c9, logits = gen.make_inputs(B, int(gold["seed_B%d" % B]))
+    want = gold["input_comp_B%d" % B]
+    got = disc_input(*[torch.from_numpy(t) for t in (c4, c6, b7, c9, logits)], B).numpy()
+    assert got.shape == want.shape == (B, 16, 16, 32) and got.dtype == np.float32
+    assert np.array_equal(got, want)
+    assert want[0, 0, 0, 31] == 1.0                                        # the planted tie [1, 3, 3, 0, -1] -> first maximum
+    # channel map of KAT 8 on the executed tensor: 0-5 = (c4 g0, c4 g1) x 3, 26-30 logits, 31 argmax
+    assert np.array_equal(want[..., 0:2], want[..., 2:4]) and np.array_equal(want[..., 0:2], want[..., 4:6])
+    assert np.array_equal(want[..., 26:31], logits) and np.array_equal(want[..., 31], logits.argmax(-1).astype(np.float32))
