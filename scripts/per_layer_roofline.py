@@ -20,7 +20,10 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    tf_peak = float(peaks.get("bf16_tflops_sustained", 1448.3))
+    # every launch is timed ALONE under ncu (serialised, clocks free to boost): the burst bf16 figure is the fair denominator; the
+    # sustained one (clocks under a long power-limited run) is what bench.py uses for kernels timed inside a step
+    tf_peak = float(peaks.get("bf16_tflops", 1684.6))
+    tf_sust = float(peaks.get("bf16_tflops_sustained", 1448.3))
     hbm_peak = float(peaks.get("hbm_gbs_burst", peaks.get("hbm_gbs", 6570.0)))
     rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", "r2_launches_c1_forward_fixed.csv"))) if len(r) > 10 and r[0].isdigit()]
     L = collections.OrderedDict()
@@ -38,9 +41,9 @@ def main():
     print("# Config 1 (segmenter forward, B = 16): every launch of one forward against both roofs\n")
     print("Source: `profiles/r2_launches_c1_forward_fixed.csv` (one `ncu --metrics gpu__time_duration.sum, sm__pipe_tensor_subpipe_hmma_cycles_active…,"
           " dram__bytes_*.sum --clock-control none` pass; per-launch times are serialised and cold-cache), layers from the reference trace. "
-          "Peaks: %.1f TFLOP/s sustained bf16 (the fp32-grade path issues 3 bf16 MMAs per algorithmic MAC, so 1/3 of it is the ceiling of the "
-          "algorithmic figure), %.0f GB/s HBM copy. `bound` = the roof that would take longer for this launch; `of roof` = that roof's time / "
-          "measured time. Produced by `scripts/per_layer_roofline.py`.\n" % (tf_peak, hbm_peak))
+          "Peaks: %.1f TFLOP/s burst bf16 -- launches are timed alone under ncu; the sustained figure bench.py uses inside a step is %.1f -- "
+          "(the fp32-grade path issues 3 bf16 MMAs per algorithmic MAC, so 1/3 of it is the ceiling of the algorithmic figure), %.0f GB/s HBM copy. `bound` = the roof that would take longer for this launch; `of roof` = that roof's time / "
+          "measured time. Produced by `scripts/per_layer_roofline.py`.\n" % (tf_peak, tf_sust, hbm_peak))
     print("| # | kernel | layer (filter, Cin→Cout @ H, dilation) | µs | GFLOP | TFLOP/s (frac of bf16 peak) | tensor pipe % | DRAM MB | GB/s | bound | of roof |")
     print("|---:|---|---|---:|---:|---:|---:|---:|---:|---|---:|")
     tot_t = tot_f = tot_b = 0.0
@@ -68,12 +71,13 @@ def main():
     print("| | **one forward, B = 16** | 33 convolutions, 3 poolings, PS | **%.0f** | **%.1f** | **%.0f (%.3f)** | | **%.0f** | %.0f | | |" % (
         tot_t * 1e6, tot_f * 1e-9, tot_f / tot_t * 1e-12, tot_f / tot_t * 1e-12 / tf_peak, tot_b * 1e-6, tot_b / tot_t * 1e-9))
     print("\nReading: the 19 launches of the 128×256 tile (`conv_tc_kernel<256, 3, 32>`) carry 95 % of the forward's FLOPs. Against the roof "
-          "the fp32-grade path can reach -- one third of the sustained bf16 peak, three bf16 MMAs per algorithmic MAC -- the 512-channel 32×32 "
-          "layers run at **0.83–0.94** and g10 (512→2560, 640 tiles: 4.3 waves) at **0.99**; the 256-channel layers (64 tiles for 148 SMs at "
-          "B = 16) at 0.61–0.68, the 128→256 layer at 0.48. What is left of the forward is bound by neither roof: the two 16-channel 256² "
-          "layers (0.05 / 0.13 of their HBM roof: TMA row rate, DESIGN §4.2.1), the 32/64/128-channel layers (0.07–0.43 of the tensor roof: "
-          "few tiles + shared-memory port) and the fused tail (issue-bound on the fp32 pipe; since this capture 436 → 266 µs, "
-          "`r2_tail5_ab.md`). The capture predates the CTA-pair kernel (−3 % on the 128×256 launches) and the register-tiled tail.")
+          "the fp32-grade path can reach -- one third of the bf16 peak, three bf16 MMAs per algorithmic MAC -- the 512-channel 32×32 layers run "
+          "at **0.71–0.81** and g10 (512→2560, 640 tiles: 4.3 waves) at **0.85** of the burst figure (0.83–0.94 / 0.99 of the sustained one); the "
+          "256-channel layers (64 tiles for 148 SMs at B = 16) at 0.53–0.58, the 128→256 layer at 0.42. What is left of the forward is bound by "
+          "neither roof: the two 16-channel 256² layers (0.05 / 0.13 of their HBM roof: TMA row rate, DESIGN §4.2.1), the 32/64/128-channel "
+          "layers (0.06–0.37 of the tensor roof: few tiles + shared-memory port) and the fused tail (issue-bound on the fp32 pipe; since this "
+          "capture 436 → 266 µs, `r2_tail5_ab.md`). The capture predates the CTA-pair kernel (−3 % on the 128×256 launches) and the "
+          "register-tiled tail.")
 
 
 if __name__ == "__main__":
