@@ -57,4 +57,14 @@ def compare_with_opencv_vectors(tag, logits, tol_rel=1e-3, min_agree=0.999):
     agree = float((lg.argmax(-1) == gold[tag + "_argmax"]).mean())
     print("  %-12s vs OpenCV-executed reference graph: logits max rel err %.3e (tol %.1e), argmax agreement %.6f" % (tag, err, tol_rel, agree))
     assert np.isfinite(err) and err <= tol_rel and agree >= min_agree, (tag, err, agree)
+    # north star: hard Dice (lib.py:96-110, background included) on held-out synthetic labels (seed 7777) within 1e-3 of the reference --
+    # here the reference IS the third-party execution of the reference graph
+    from oracle.pnp_graphs import synthetic_labels
+    lab = np.asarray(synthetic_labels(B, 7777))
+
+    def hard_dice(pred):
+        return np.array([2.0 * np.sum((pred == c) & (lab == c)) / (np.sum(pred == c) + np.sum(lab == c) + 1e-7) for c in range(5)])
+    d_got, d_ref = hard_dice(lg.argmax(-1)), hard_dice(gold[tag + "_argmax"].astype(np.int64))
+    print("  %-12s hard Dice on held-out labels: ours %s, OpenCV %s" % (tag, np.round(d_got, 5), np.round(d_ref, 5)))
+    assert np.abs(d_got - d_ref).max() <= 1e-3 and abs(d_got.mean() - d_ref.mean()) <= 1e-3
     return err, agree
