@@ -99,3 +99,20 @@ def test_masked_crc32c_and_framing_agree_with_tensorboard(tmp_path):
     with pytest.raises(IOError):
         R.load_slice(p, record_index=0, check_crc=True)
     assert struct.unpack("<Q", buf[:8])[0] == len(payloads[0])
+
+
+def test_event_bytes_known_answer():
+    """protobuf wire format by hand: Event{wall_time = 1.0 (field 1, fixed64), step = 3 (field 2, varint), summary (field 5, bytes)
+    {value (field 1) {tag = "a" (field 1), simple_value = 2.0 (field 2, fixed32)}}} and the TFRecord frame around it"""
+    import pnp_b200  # noqa: F401
+    from pnp_b200 import summary, tfrecord
+    ev = summary.encode_event(1.0, step=3, summary=summary.encode_scalar_summary([("a", 2.0)]))
+    assert ev == bytes.fromhex("09" "000000000000f03f" "10" "03" "2a" "0a" "0a" "08" "0a" "01" "61" "15" "00000040")
+    fr = summary.frame(ev)
+    assert fr[:8] == struct.pack("<Q", len(ev)) and fr[12:12 + len(ev)] == ev and len(fr) == len(ev) + 16
+    assert struct.unpack("<I", fr[8:12])[0] == tfrecord.masked_crc(fr[:8]) and struct.unpack("<I", fr[-4:])[0] == tfrecord.masked_crc(ev)
+    # masked CRC32C of the empty string: crc32c("") = 0 -> ((0 >> 15) | (0 << 17)) + 0xa282ead8
+    assert tfrecord.masked_crc(b"") == 0xA282EAD8 and tfrecord.crc32c(b"123456789") == 0xE3069283          # RFC 3720 check value
+    # negative steps are two's-complement 10-byte varints, version events carry field 3
+    assert summary.encode_event(0.0, step=-1)[9:] == bytes.fromhex("10" + "ff" * 9 + "01")
+    assert summary.encode_event(0.0, file_version="brain.Event:2")[9:] == b"\x1a\x0dbrain.Event:2"
